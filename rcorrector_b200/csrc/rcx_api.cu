@@ -1,0 +1,435 @@
+// rcx_api.cu — the extern "C" boundary of librcx.so (include/rcx.h).
+//
+// One rcx_ctx = one GPU: it owns the k-mer count table in HBM, a stream, the
+// intermediate buffers of the hot path (counts[], thresholds, flags) and grow-
+// only staging buffers for host batches.  There is no CPU fallback anywhere in
+// this file: every entry point either runs the sm_100a kernels or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rcx.h"
+#include "rcx_internal.h"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(_e == cudaErrorMemoryAllocation ? RCX_ERR_NOMEM : RCX_ERR_CUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct rcx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // table
+    RcxBucket* buckets = nullptr;
+    unsigned long long nbuckets = 0;
+    unsigned long long entries = 0;
+    int k = 0;
+    // params
+    rcx_params params{};
+    bool have_params = false;
+    // intermediates + staging
+    DevBuf<char> d_seq, d_qual;
+    DevBuf<uint32_t> d_off;
+    DevBuf<int32_t> d_counts, d_thr, d_corr, d_l, d_m, d_h;
+    DevBuf<uint8_t> d_flags;
+    unsigned long long* d_counters = nullptr;
+    cudaEvent_t ev[6]{};
+    rcx_stats stats{};
+};
+
+extern "C" int rcx_abi_version(void) { return RCX_ABI_VERSION; }
+extern "C" const char* rcx_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rcx_create(int device, rcx_ctx** out) {
+    if (!out) return fail(RCX_ERR_ARG, "rcx_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(RCX_ERR_CUDA, std::string("rcx_create: no CUDA device (") + cudaGetErrorString(e) +
+                                      "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RCX_ERR_ARG, "rcx_create: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    rcx_ctx* c = new rcx_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * RCX_C_COUNT));
+    CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT));
+    for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+    *out = c;
+    return RCX_OK;
+}
+
+extern "C" void rcx_destroy(rcx_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->buckets) cudaFree(c->buckets);
+    c->d_seq.release(); c->d_qual.release(); c->d_off.release(); c->d_counts.release(); c->d_thr.release();
+    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release();
+    if (c->d_counters) cudaFree(c->d_counters);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" void* rcx_stream(rcx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" void* rcx_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        g_err = "rcx_host_alloc: cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void rcx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int rcx_sync(rcx_ctx* c) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_sync: null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ table
+extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, const int32_t* counts, uint64_t n,
+                               int src_on_device) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_table_build: null context");
+    if (k < 2 || k > RCX_MAX_K) return fail(RCX_ERR_ARG, "rcx_table_build: k must be in [2, 32]");
+    if (n && (!fwd_codes || !counts)) return fail(RCX_ERR_ARG, "rcx_table_build: null input arrays");
+    if (n >= 0xffffffffull) return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^32-2 records in one table");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->buckets) { cudaFree(c->buckets); c->buckets = nullptr; }
+    // two slots per bucket, load factor <= 0.5 over slots => nbuckets >= n, rounded up to a power of two
+    unsigned long long nb = 1024;
+    while (nb < n) nb <<= 1;
+    CUDA_TRY(cudaMalloc(&c->buckets, nb * sizeof(RcxBucket)));
+    c->nbuckets = nb;
+    c->k = k;
+    c->entries = 0;
+    CUDA_TRY(rcx_launch_table_init(c->buckets, nb, c->stream));
+    unsigned long long* d_new = nullptr;
+    CUDA_TRY(cudaMalloc(&d_new, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_new, 0, sizeof(unsigned long long), c->stream));
+    if (src_on_device) {
+        CUDA_TRY(rcx_launch_table_insert(c->buckets, nb - 1, k, (const unsigned long long*)fwd_codes, counts, n, 0, d_new, c->stream));
+    } else {
+        // stream the records through a bounded device staging area
+        const uint64_t chunk = 1ull << 24;
+        unsigned long long* d_codes = nullptr;
+        int32_t* d_cnt = nullptr;
+        const uint64_t m = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
+        CUDA_TRY(cudaMalloc(&d_codes, m * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&d_cnt, m * sizeof(int32_t)));
+        for (uint64_t s = 0; s < n; s += chunk) {
+            const uint64_t len = std::min<uint64_t>(chunk, n - s);
+            CUDA_TRY(cudaMemcpyAsync(d_codes, fwd_codes + s, len * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(d_cnt, counts + s, len * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(rcx_launch_table_insert(c->buckets, nb - 1, k, d_codes, d_cnt, len, s, d_new, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        cudaFree(d_codes);
+        cudaFree(d_cnt);
+    }
+    unsigned long long h_new = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_new, d_new, sizeof h_new, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(d_new);
+    c->entries = h_new;
+    return RCX_OK;
+}
+
+static RcxTable table_of(const rcx_ctx* c) {
+    RcxTable t;
+    t.buckets = c->buckets;
+    t.bucket_mask = c->nbuckets - 1;
+    t.k = c->k;
+    return t;
+}
+
+extern "C" int rcx_table_lookup(rcx_ctx* c, const uint64_t* fwd_codes, int32_t* counts_out, uint64_t n) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_table_lookup: null context");
+    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_table_lookup: no table built");
+    if (n && (!fwd_codes || !counts_out)) return fail(RCX_ERR_ARG, "rcx_table_lookup: null arrays");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint64_t chunk = 1ull << 24;
+    unsigned long long* d_codes = nullptr;
+    int32_t* d_out = nullptr;
+    const uint64_t m = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
+    CUDA_TRY(cudaMalloc(&d_codes, m * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d_out, m * sizeof(int32_t)));
+    for (uint64_t s = 0; s < n; s += chunk) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - s);
+        CUDA_TRY(cudaMemcpyAsync(d_codes, fwd_codes + s, len * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(rcx_launch_table_lookup(table_of(c), d_codes, d_out, len, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(counts_out + s, d_out, len * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(d_codes);
+    cudaFree(d_out);
+    return RCX_OK;
+}
+
+extern "C" int rcx_table_info(rcx_ctx* c, uint64_t* entries, uint64_t* slots, uint64_t* bytes) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_table_info: null context");
+    if (entries) *entries = c->entries;
+    if (slots) *slots = c->nbuckets * 2;
+    if (bytes) *bytes = c->nbuckets * sizeof(RcxBucket);
+    return RCX_OK;
+}
+
+extern "C" int rcx_set_params(rcx_ctx* c, const rcx_params* p) {
+    if (!c || !p) return fail(RCX_ERR_ARG, "rcx_set_params: null argument");
+    if (p->k < 2 || p->k > RCX_MAX_K) return fail(RCX_ERR_ARG, "rcx_set_params: k must be in [2, 32]");
+    if (p->max_fix_per_k < 0) return fail(RCX_ERR_ARG, "rcx_set_params: max_fix_per_k < 0");
+    if (!(p->error_rate > 0)) return fail(RCX_ERR_ARG, "rcx_set_params: error_rate must be > 0");
+    c->params = *p;
+    c->have_params = true;
+    return RCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hot path
+static int check_ready(const rcx_ctx* c, const char* who) {
+    if (!c) return fail(RCX_ERR_ARG, std::string(who) + ": null context");
+    if (!c->buckets) return fail(RCX_ERR_STATE, std::string(who) + ": no table built (rcx_table_build)");
+    if (!c->have_params) return fail(RCX_ERR_STATE, std::string(who) + ": parameters not set (rcx_set_params)");
+    if (c->params.k != c->k) return fail(RCX_ERR_STATE, std::string(who) + ": params.k differs from the table's k");
+    return RCX_OK;
+}
+
+static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const char* d_qual, const uint32_t* d_off,
+                           uint64_t total_bases, int32_t max_len, int32_t* d_corr, int32_t* d_l, int32_t* d_m, int32_t* d_h,
+                           bool correct) {
+    CUDA_TRY(c->d_counts.ensure(total_bases + 1));
+    CUDA_TRY(c->d_thr.ensure((size_t)n + 2));
+    CUDA_TRY(c->d_flags.ensure((size_t)n + 2));
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, c->stream));
+    RcxScanArgs sa;
+    sa.t = table_of(c);
+    sa.seq = d_seq; sa.off = d_off; sa.n = n; sa.max_len = max_len;
+    sa.counts = c->d_counts.p; sa.thr = c->d_thr.p; sa.flags = c->d_flags.p; sa.counters = c->d_counters;
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_TRY(rcx_launch_scan(sa, c->sm_count, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    c->stats.kernel_launches = 1;
+    if (correct) {
+        RcxCorrectArgs ca;
+        ca.t = sa.t;
+        ca.seq = d_seq; ca.qual = d_qual; ca.off = d_off; ca.n = n; ca.max_len = max_len; ca.mode = mode;
+        ca.max_fix_per_k = c->params.max_fix_per_k; ca.error_rate = c->params.error_rate; ca.bad_qual = c->params.bad_qual;
+        ca.counts = c->d_counts.p; ca.thr = c->d_thr.p; ca.flags = c->d_flags.p;
+        ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = c->d_counters;
+        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, c->stream));
+        c->stats.kernel_launches = 2;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    c->stats.reads = (uint64_t)n;
+    c->stats.bases = total_bases;
+    return RCX_OK;
+}
+
+static int scan_lengths(const uint32_t* off, int64_t n, int32_t* max_len) {
+    uint32_t mx = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        if (off[r + 1] < off[r]) return fail(RCX_ERR_ARG, "offsets are not non-decreasing");
+        mx = std::max(mx, off[r + 1] - off[r]);
+    }
+    if (mx > RCX_MAX_READ_LENGTH) return fail(RCX_ERR_ARG, "a read is longer than RCX_MAX_READ_LENGTH (1023)");
+    *max_len = (int32_t)mx;
+    return RCX_OK;
+}
+
+extern "C" int rcx_correct_batch_device(rcx_ctx* c, int mode, int64_t n, char* seq, const char* qual, const uint32_t* off,
+                                        uint64_t total, int32_t max_len, int32_t* correction, int32_t* l, int32_t* m,
+                                        int32_t* h) {
+    int rc = check_ready(c, "rcx_correct_batch_device");
+    if (rc) return rc;
+    if (n < 0 || (mode != RCX_SINGLE && mode != RCX_INTERLEAVED)) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: bad n or mode");
+    if (mode == RCX_INTERLEAVED && (n & 1)) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: interleaved batch needs an even n");
+    if (n == 0) return RCX_OK;
+    if (!seq || !qual || !off || !correction || !l || !m || !h) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: null pointer");
+    if (max_len < 1 || max_len > RCX_MAX_READ_LENGTH) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: bad max_len");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    rc = launch_pipeline(c, mode, n, seq, qual, off, total, max_len, correction, l, m, h, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+    return RCX_OK;
+}
+
+extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* seq_in, const char* qual, const uint32_t* off,
+                                 char* seq_out, int32_t* correction, int32_t* l, int32_t* m, int32_t* h) {
+    int rc = check_ready(c, "rcx_correct_batch");
+    if (rc) return rc;
+    if (n < 0 || (mode != RCX_SINGLE && mode != RCX_INTERLEAVED)) return fail(RCX_ERR_ARG, "rcx_correct_batch: bad n or mode");
+    if (mode == RCX_INTERLEAVED && (n & 1)) return fail(RCX_ERR_ARG, "rcx_correct_batch: interleaved batch needs an even n");
+    if (n == 0) return RCX_OK;
+    if (!seq_in || !qual || !off || !seq_out || !correction || !l || !m || !h) return fail(RCX_ERR_ARG, "rcx_correct_batch: null pointer");
+    if (off[0] != 0) return fail(RCX_ERR_ARG, "rcx_correct_batch: off[0] must be 0");
+    int32_t max_len = 0;
+    rc = scan_lengths(off, n, &max_len);
+    if (rc) return rc;
+    const uint64_t total = off[n];
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->d_seq.ensure(total + 64));
+    CUDA_TRY(c->d_qual.ensure(total + 64));
+    CUDA_TRY(c->d_off.ensure((size_t)n + 1));
+    CUDA_TRY(c->d_corr.ensure((size_t)n));
+    CUDA_TRY(c->d_l.ensure((size_t)n));
+    CUDA_TRY(c->d_m.ensure((size_t)n));
+    CUDA_TRY(c->d_h.ensure((size_t)n));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_seq.p, seq_in, total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_qual.p, qual, total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_off.p, off, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (max_len < 1) max_len = 1;
+    rc = launch_pipeline(c, mode, n, c->d_seq.p, c->d_qual.p, c->d_off.p, total, max_len, c->d_corr.p, c->d_l.p, c->d_m.p,
+                         c->d_h.p, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(seq_out, c->d_seq.p, total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(correction, c->d_corr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(l, c->d_l.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m, c->d_m.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_h.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RCX_OK;
+}
+
+extern "C" int rcx_scan_batch(rcx_ctx* c, int64_t n, const char* seq, const uint32_t* off, int32_t* counts_out,
+                              int32_t* strong_threshold_out) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_scan_batch: null context");
+    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_scan_batch: no table built");
+    if (n <= 0) return n == 0 ? RCX_OK : fail(RCX_ERR_ARG, "rcx_scan_batch: n < 0");
+    if (!seq || !off || !counts_out || !strong_threshold_out) return fail(RCX_ERR_ARG, "rcx_scan_batch: null pointer");
+    int32_t max_len = 0;
+    int rc = scan_lengths(off, n, &max_len);
+    if (rc) return rc;
+    if (max_len < 1) max_len = 1;
+    const uint64_t total = off[n];
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->d_seq.ensure(total + 64));
+    CUDA_TRY(c->d_off.ensure((size_t)n + 1));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_seq.p, seq, total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_off.p, off, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c->d_counts.ensure(total + 1));
+    CUDA_TRY(cudaMemsetAsync(c->d_counts.p, 0, (total + 1) * sizeof(int32_t), c->stream));
+    rc = launch_pipeline(c, RCX_SINGLE, n, c->d_seq.p, nullptr, c->d_off.p, total, max_len, nullptr, nullptr, nullptr, nullptr, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(counts_out, c->d_counts.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(strong_threshold_out, c->d_thr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RCX_OK;
+}
+
+extern "C" int rcx_get_stats(rcx_ctx* c, rcx_stats* out) {
+    if (!c || !out) return fail(RCX_ERR_ARG, "rcx_get_stats: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    unsigned long long h[RCX_C_COUNT];
+    CUDA_TRY(cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    c->stats.scan_probes = h[RCX_C_SCAN_PROBES];
+    c->stats.search_probes = h[RCX_C_SEARCH_PROBES];
+    c->stats.rescan_probes = h[RCX_C_RESCAN_PROBES];
+    c->stats.search_nodes = h[RCX_C_SEARCH_NODES];
+    auto ms = [&](int a, int b) {
+        float v = 0;
+        if (cudaEventElapsedTime(&v, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); v = 0; }
+        return v;
+    };
+    c->stats.ms_h2d = ms(0, 1);
+    c->stats.ms_scan = ms(1, 2);
+    c->stats.ms_correct = ms(2, 3);
+    c->stats.ms_d2h = ms(4, 5);
+    c->stats.ms_total = ms(0, 5);
+    *out = c->stats;
+    return RCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ERROR_RATE (main.cpp:310-358)
+extern "C" int rcx_estimate_error_rate(rcx_ctx* c, const uint64_t* fwd_codes, uint64_t n, double wk, double* out) {
+    if (!c || !out) return fail(RCX_ERR_ARG, "rcx_estimate_error_rate: null argument");
+    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_estimate_error_rate: no table built");
+    const int k = c->k;
+    const uint64_t cap = 100000;
+    std::vector<double> rates;
+    rates.reserve(cap + 1);
+    const uint64_t chunk = 1ull << 20;
+    std::vector<uint64_t> var;
+    std::vector<int32_t> cnt;
+    for (uint64_t s = 0; s < n && rates.size() < cap; s += chunk) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - s);
+        var.resize(len * 4);
+        cnt.resize(len * 4);
+        for (uint64_t i = 0; i < len; ++i)
+            for (uint64_t b = 0; b < 4; ++b) var[4 * i + b] = (fwd_codes[s + i] & ~3ull) | b;  // ShiftRight(1) + Append(b)
+        int rc = rcx_table_lookup(c, var.data(), cnt.data(), len * 4);
+        if (rc) return rc;
+        for (uint64_t i = 0; i < len && rates.size() < cap; ++i) {
+            int best = 0, second = 0;
+            for (int b = 0; b < 4; ++b) {
+                const int v = cnt[4 * i + b];
+                if (v > best) { second = best; best = v; }
+                else if (v > second) second = v;
+            }
+            if (best < 1000) continue;
+            rates.push_back((double)second / (double)best);
+        }
+    }
+    (void)k;
+    double er = 0;
+    const size_t kq = rates.size();
+    if (kq > 0) {
+        std::sort(rates.begin(), rates.end());
+        rates.push_back(rates.back());
+        er = rates[(size_t)(int)(kq * wk)];
+    }
+    if (er == 0 || kq < 100) er = 0.01;
+    *out = er;
+    return RCX_OK;
+}

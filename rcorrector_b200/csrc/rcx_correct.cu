@@ -1,0 +1,771 @@
+// rcx_correct.cu — K2: per-read correction, one warp owns one read.
+//
+// Restates ErrorCorrection (ErrorCorrection.cpp:682-1480), SearchPaths_Right /
+// SearchPaths_Left (:201-442 / :444-678), InferPosThreshold (:144-173) and
+// GetKmerInformation (:1567-1602) as a warp-cooperative state machine:
+//
+//  * every lane keeps the (warp-uniform) scalar state of the algorithm in
+//    registers, so control flow never diverges; lanes split the data-parallel
+//    parts: bit-plane construction, trusted-k-mer ballots, range fills, the
+//    four one-base-extension probes of a search node (lanes 0..3, one 32-byte
+//    sector each), best-path copies, filters and the final re-scan;
+//  * the recursion of the reference becomes an explicit stack of 48-byte
+//    frames in shared memory (depth <= kcnt + 2); children are visited in the
+//    reference's order (keep-base / rescue, A, C, G, T, jump) and all state
+//    the reference shares by reference across the recursion (maxFixCnt,
+//    bestFixCnt, bestFixBottleNeck, top2, trialCnt, the never-rolled-back
+//    path[] / fix[] arrays) is shared here in the same way;
+//  * the four extension k-mers of a node serve InferPosThreshold, the
+//    keep-base test and the three alternatives at once (the CPU probes the
+//    same k-mers 8 times).
+//
+// counts[] and the per-read GetStrongTrustedThreshold come from the scan
+// kernel (rcx_scan.cu); the pair threshold is min over the two mates
+// (ErrorCorrection.cpp:96-106).
+#include "rcx_internal.h"
+
+#define COR_WARPS 4
+#define FRAME_WORDS 12
+
+enum { ST_ENTER = 0, ST_KEEP = 1, ST_ALT0 = 2, ST_JUMP = 6, ST_DONE = 7 };
+
+struct CorLayout {
+    int pkw, mw, lpad, n2, nseg, depth;
+    int words;  // total 32-bit words per warp
+};
+
+__host__ __device__ inline CorLayout cor_layout(int max_len, int k) {
+    CorLayout L;
+    int kc = max_len - k + 1;
+    if (kc < 1) kc = 1;
+    L.pkw = rcx_pk_words(max_len);
+    L.mw = rcx_mask_words(max_len);
+    L.lpad = ((max_len + 31) / 32) * 32 + 32;
+    L.n2 = rcx_pow2_at_least(kc);
+    L.nseg = max_len / k + 4;
+    L.depth = kc + 3;
+    int un = L.depth * FRAME_WORDS;
+    if (un < L.n2) un = L.n2;
+    L.words = L.pkw + 10 * L.mw + L.lpad /*counts*/ + L.lpad / 2 /*path+fix as int8*/ + L.nseg + un;
+    return L;
+}
+
+size_t rcx_correct_smem_per_warp(int max_len, int k) { return sizeof(unsigned int) * (size_t)cor_layout(max_len, k).words; }
+
+struct WarpMem {
+    RcxPlanes P;
+    unsigned int* strong;   // isStrongTrusted, bit per base
+    unsigned int* island;   // islands used to derive segments (== strong unless the fallback island is used)
+    unsigned int* pstrict;  // isPolyAKmer (threshold 2), bit per k-mer
+    unsigned int* trusted;  // trusted k-mers of this pass
+    unsigned int* fixm;     // scratch masks for the post-filters
+    int* counts;
+    signed char* path;
+    signed char* fix;
+    int* segtop;            // top2FixBottleNeck[1] per segment
+    int* sbuf;              // sort buffer (aliases the search stack)
+    unsigned int* stack;
+};
+
+// state shared by the whole search of one segment (the by-reference parameters of SearchPaths_*)
+struct SearchState {
+    int max_fix, best_cnt, best_bn, trial, top2a, top2b;
+};
+
+__device__ __forceinline__ int getbit(const unsigned int* m, int i) { return (m[i >> 5] >> (i & 31)) & 1; }
+
+// first index in [from, limit) whose bit equals `want`, or `limit`; warp-cooperative, all lanes must call
+__device__ __forceinline__ int next_bit(const unsigned int* m, int from, int limit, bool want, int lane) {
+    int best = limit;
+    if (from < limit) {
+        const int w0 = from >> 5;
+        for (int w = w0 + lane; (w << 5) < limit; w += 32) {
+            unsigned int x = want ? m[w] : ~m[w];
+            if (w == w0) x &= 0xffffffffu << (from & 31);
+            if (x) {
+                const int idx = (w << 5) + __ffs(x) - 1;
+                if (idx < best) best = idx;
+                break;
+            }
+        }
+    }
+    best = __reduce_min_sync(RCX_FULL, best);
+    return best < limit ? best : limit;
+}
+
+// set bits [a, b] (inclusive) of a mask plane; warp-cooperative
+__device__ __forceinline__ void set_range(unsigned int* m, int a, int b, int mw, int lane) {
+    if (a > b) return;
+    for (int w = (a >> 5) + lane; w <= (b >> 5) && w < mw; w += 32) {
+        const int lo = a > (w << 5) ? a - (w << 5) : 0;
+        const int hi = b < (w << 5) + 31 ? b - (w << 5) : 31;
+        const unsigned int bits = (hi - lo == 31) ? 0xffffffffu : (((1u << (hi - lo + 1)) - 1) << lo);
+        m[w] |= bits;
+    }
+}
+
+__device__ __forceinline__ int sel4(int b, int c0, int c1, int c2, int c3) { return b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3; }
+
+// counts of the four one-base extensions of kc (lanes 0..3 probe, everyone receives)
+__device__ __forceinline__ void probe4(const RcxTable& t, const RcxKmer& kc, bool right, unsigned long long mask, int lane, int& c0,
+                                       int& c1, int& c2, int& c3) {
+    int mine = 0;
+    if (lane < 4) {
+        RcxKmer x = kc;
+        if (right) rcx_k_append(x, lane, false, t.k, mask);
+        else rcx_k_prepend(x, lane, false, t.k, mask);
+        mine = rcx_k_count(t, x);
+    }
+    __syncwarp();
+    c0 = __shfl_sync(RCX_FULL, mine, 0);
+    c1 = __shfl_sync(RCX_FULL, mine, 1);
+    c2 = __shfl_sync(RCX_FULL, mine, 2);
+    c3 = __shfl_sync(RCX_FULL, mine, 3);
+}
+
+// InferPosThreshold (:144-173) given the four extension counts
+__device__ __forceinline__ int infer_thr(int c0, int c1, int c2, int c3, int upper, double er) {
+    int mx = c0 > c1 ? c0 : c1;
+    int my = c2 > c3 ? c2 : c3;
+    mx = mx > my ? mx : my;
+    if (mx < 0) mx = 0;
+    int r = rcx_bound_i(mx, er);
+    if (r < 1) r = 1;
+    return (upper > r || upper <= 0) ? r : upper;
+}
+
+// One whole SearchPaths_Right (right = true) or SearchPaths_Left call tree.
+__device__ void search_segment(const RcxTable& tab, const WarpMem& M, SearchState& S, const bool right, const int start,
+                               const int to, const int t0, RcxKmer kc, const int len, const double er, const int lane,
+                               unsigned long long& n_nodes, unsigned long long& n_probes) {
+    const int k = tab.k;
+    const unsigned long long mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    int pos = start, t = t0, fix_cnt = 0, bn = RCX_INF, thr = 0, ext = 0, stage = ST_ENTER;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    int sp = 0;
+
+#define PUSH_CHILD(npos, nt, nfix, nbn, nkc)                                                          \
+    do {                                                                                              \
+        if (lane == 0) {                                                                              \
+            unsigned int* f = M.stack + sp * FRAME_WORDS;                                             \
+            f[0] = (unsigned int)kc.code;                                                             \
+            f[1] = (unsigned int)(kc.code >> 32);                                                     \
+            f[2] = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)stage << 20) | \
+                   ((unsigned int)(ext != 0) << 24);                                                  \
+            f[3] = (unsigned int)t; f[4] = (unsigned int)fix_cnt; f[5] = (unsigned int)bn; f[6] = (unsigned int)thr; \
+            f[7] = (unsigned int)c0; f[8] = (unsigned int)c1; f[9] = (unsigned int)c2; f[10] = (unsigned int)c3; \
+        }                                                                                             \
+        ++sp;                                                                                         \
+        { const int _p = (npos), _t = (nt), _f = (nfix), _b = (nbn); const RcxKmer _k = (nkc);        \
+          pos = _p; t = _t; fix_cnt = _f; bn = _b; kc = _k; }                                         \
+        stage = ST_ENTER;                                                                             \
+        __syncwarp();                                                                                 \
+    } while (0)
+    // the jump child is always the last child of its node, so the parent frame is not needed again: no push.
+    // (This also bounds the stack: a Left jump can re-enter the same position, ErrorCorrection.cpp:672-676.)
+#define TAIL_CHILD(npos, nt, nfix, nkc)                                                               \
+    do {                                                                                              \
+        { const int _p = (npos), _t = (nt), _f = (nfix); const RcxKmer _k = (nkc);                    \
+          pos = _p; t = _t; fix_cnt = _f; kc = _k; }                                                  \
+        stage = ST_ENTER;                                                                             \
+        __syncwarp();                                                                                 \
+    } while (0)
+
+    for (;;) {
+        if (stage == ST_ENTER) {
+            ++n_nodes;
+            bool leave = false;
+            // step 0 (:211-224 / :453-467)
+            if (S.trial > RCX_MAX_TRIAL) {
+                if (S.max_fix > 2) { --S.max_fix; S.best_cnt = 0; S.best_bn = -1; S.trial = 0; }
+                else leave = true;
+            }
+            if (!leave && fix_cnt > S.max_fix) leave = true;
+            if (!leave && (right ? pos >= to : pos < to)) {
+                // terminal (:228-285 / :468-524)
+                int fc = fix_cnt;
+                if (bn < t) ++fc;
+                if (fc < S.max_fix) { S.top2a = bn; S.top2b = -1; }
+                else if (fc == S.max_fix) {
+                    if (bn > S.top2a) { S.top2b = S.top2a; S.top2a = bn; }
+                    else if (bn > S.top2b) S.top2b = bn;
+                }
+                if (fc < S.max_fix || (fc == S.max_fix && bn > S.best_bn)) {
+                    if (fc < S.max_fix) S.trial = -(S.max_fix - fc + 1) * RCX_MAX_TRIAL;
+                    const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
+                    __syncwarp();
+                    for (int i = lo + lane; i <= hi; i += 32) M.fix[i] = M.path[i];
+                    __syncwarp();
+                    S.max_fix = fc; S.best_bn = bn; S.best_cnt = 1;
+                } else if (fc == S.max_fix && bn == S.best_bn) {
+                    S.best_cnt += 1;
+                }
+                leave = true;
+            }
+            if (leave) {
+                stage = ST_DONE;
+            } else {
+                probe4(tab, kc, right, mask, lane, c0, c1, c2, c3);
+                n_probes += 4;
+                thr = infer_thr(c0, c1, c2, c3, t, er);
+                ext = 0;
+                stage = ST_KEEP;
+            }
+        }
+        const bool here_ok = stage != ST_DONE && !getbit(M.P.inv, pos);
+        const int hb = stage != ST_DONE ? rcx_base(M.P.pk, pos) : 0;
+        if (stage == ST_KEEP) {
+            stage = ST_ALT0;
+            if (here_ok) {  // :294-339 / :532-574
+                int c = sel4(hb, c0, c1, c2, c3);
+                RcxKmer x = kc;
+                if (right) rcx_k_append(x, hb, false, k, mask); else rcx_k_prepend(x, hb, false, k, mask);
+                if (c >= thr) {
+                    if (lane == 0) M.path[pos] = -1;
+                    ext = 1;
+                    PUSH_CHILD(right ? pos + 1 : pos - 1, right ? t : thr, fix_cnt, c < bn ? c : bn, x);
+                    continue;
+                } else if (thr == 1 && t <= 2) {
+                    // "accidentally below the threshold" rescue (:313-338 / :550-573)
+                    int i = pos, steps = 0;
+                    for (; c < thr && steps < k; ++steps) {
+                        if (right) { ++i; if (i >= to) break; } else { --i; if (i < to) break; }
+                        const bool bad = getbit(M.P.inv, i);
+                        const int b = rcx_base(M.P.pk, i);
+                        if (right) rcx_k_append(x, b, bad, k, mask); else rcx_k_prepend(x, b, bad, k, mask);
+                        c = rcx_k_count(tab, x);
+                        n_probes += 1;
+                    }
+                    if (steps < k && (right ? i < to : i >= to)) {
+                        const int lo = right ? pos : i, hi = right ? i : pos;
+                        for (int j = lo + lane; j <= hi; j += 32) M.path[j] = -1;
+                        ext = 1;
+                        PUSH_CHILD(right ? i + 1 : i - 1, right ? t : thr, fix_cnt + 1, bn, x);
+                        continue;
+                    }
+                }
+            }
+        }
+        if (stage >= ST_ALT0 && stage < ST_JUMP) {  // :343-372 / :577-608
+            const int pidx = right ? pos - k + 1 : pos;
+            const bool allowed = !getbit(M.strong, pos) && !(pidx >= 0 && getbit(M.pstrict, pidx));
+            bool pushed = false;
+            if (allowed) {
+                for (int b = stage - ST_ALT0; b < 4; ++b) {
+                    if (here_ok && b == hb) continue;
+                    const int c = sel4(b, c0, c1, c2, c3);
+                    if (c >= thr) {
+                        if (lane == 0) M.path[pos] = (signed char)b;
+                        ++S.trial;
+                        ext = 1;
+                        RcxKmer x = kc;
+                        if (right) rcx_k_append(x, b, false, k, mask); else rcx_k_prepend(x, b, false, k, mask);
+                        stage = ST_ALT0 + b + 1;
+                        PUSH_CHILD(right ? pos + 1 : pos - 1, right ? t : thr, fix_cnt + (here_ok ? 1 : 0), c < bn ? c : bn, x);
+                        pushed = true;
+                        break;
+                    }
+                }
+            }
+            if (pushed) continue;
+            stage = ST_JUMP;
+        }
+        if (stage == ST_JUMP) {
+            stage = ST_DONE;
+            if (ext == 0) {  // jump through an unfixable region (:393-441 / :629-677)
+                RcxKmer x = kc;
+                int i, th = thr;
+                if (right) {
+                    for (i = pos; i < to; ++i) {
+                        int d0, d1, d2, d3;
+                        probe4(tab, x, true, mask, lane, d0, d1, d2, d3);
+                        n_probes += 4;
+                        th = infer_thr(d0, d1, d2, d3, t, er);
+                        const bool bad = getbit(M.P.inv, i);
+                        const int b = rcx_base(M.P.pk, i);
+                        rcx_k_append(x, b, bad, k, mask);
+                        const int c = bad ? 0 : sel4(b, d0, d1, d2, d3);
+                        if (lane == 0) M.path[i] = -1;
+                        if (c >= th) break;
+                    }
+                    int kk = (i < len) ? i - pos - k + 1 : (i - pos) / 2;
+                    if (kk <= 0) kk = 1;
+                    if (i >= to) i -= 1;
+                    TAIL_CHILD(i + 1, t, fix_cnt + kk, x);
+                } else {
+                    for (i = pos; i >= to; --i) {
+                        int d0, d1, d2, d3;
+                        probe4(tab, x, false, mask, lane, d0, d1, d2, d3);
+                        n_probes += 4;
+                        th = infer_thr(d0, d1, d2, d3, t, er);
+                        const bool bad = getbit(M.P.inv, i);
+                        const int b = rcx_base(M.P.pk, i);
+                        rcx_k_prepend(x, b, bad, k, mask);
+                        const int c = bad ? 0 : sel4(b, d0, d1, d2, d3);
+                        if (lane == 0) M.path[i] = -1;
+                        if (c >= th) break;
+                    }
+                    int kk = (i >= 0) ? pos - i - k + 1 : pos - 1;
+                    if (kk <= 0) kk = 1;
+                    if (i <= to) ++i;
+                    TAIL_CHILD(i - 1, th, fix_cnt + kk, x);
+                }
+                continue;
+            }
+        }
+        // ST_DONE: return to the parent frame
+        if (sp == 0) break;
+        --sp;
+        {
+            const unsigned int* f = M.stack + sp * FRAME_WORDS;
+            kc.code = (unsigned long long)f[0] | ((unsigned long long)f[1] << 32);
+            const unsigned int w = f[2];
+            pos = (int)(w & 0xfff) - 1;
+            kc.inv = (int)((w >> 12) & 0xff) - 1;
+            stage = (int)((w >> 20) & 0xf);
+            ext = (int)((w >> 24) & 1);
+            t = (int)f[3]; fix_cnt = (int)f[4]; bn = (int)f[5]; thr = (int)f[6];
+            c0 = (int)f[7]; c1 = (int)f[8]; c2 = (int)f[9]; c3 = (int)f[10];
+        }
+    }
+#undef PUSH_CHILD
+#undef TAIL_CHILD
+}
+
+// window code / state for a seed k-mer built by Restart + k Appends of seq[j .. j+k) (j may be -1)
+__device__ __forceinline__ RcxKmer seed_kmer(const RcxPlanes& P, int j, int k, unsigned int kmask32) {
+    RcxKmer x;
+    if (j >= 0) {
+        x.code = rcx_window(P.pk, j, k);
+        const unsigned int m = rcx_bits(P.inv, j) & kmask32;
+        x.inv = m ? (k - 1) - (31 - __clz(m)) : -1;
+    } else {
+        // seq[-1] is read by the reference (ErrorCorrection.cpp:1139-1142 with tend = -1); whatever it holds is shifted
+        // out / reset by the first Append of the search, so any value gives the same result.
+        x.code = rcx_window(P.pk, 0, k) >> 2;
+        const unsigned int m = rcx_bits(P.inv, 0) & (kmask32 >> 1);
+        x.inv = m ? (k - 2) - (31 - __clz(m)) : -1;
+    }
+    return x;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RCX_FULL, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(COR_WARPS * 32) rcx_correct_kernel(RcxCorrectArgs a) {
+    extern __shared__ unsigned int smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = a.t.k, K = a.max_fix_per_k, Q = a.bad_qual;
+    const double er = a.error_rate;
+    const CorLayout L = cor_layout(a.max_len, k);
+    const int mw = L.mw;
+    WarpMem M;
+    {
+        unsigned int* p = smem + (size_t)warp * L.words;
+        M.P.pk = p; p += L.pkw;
+        M.P.inv = p; p += mw;
+        M.P.mA = p; p += mw;
+        M.P.mT = p; p += mw;
+        M.P.mN = p; p += mw;
+        M.strong = p; p += mw;
+        M.island = p; p += mw;
+        M.pstrict = p; p += mw;
+        M.trusted = p; p += mw;
+        M.fixm = p; p += 2 * mw;
+        M.counts = reinterpret_cast<int*>(p); p += L.lpad;
+        M.path = reinterpret_cast<signed char*>(p);
+        M.fix = M.path + L.lpad;
+        p += L.lpad / 2;
+        M.segtop = reinterpret_cast<int*>(p); p += L.nseg;
+        M.sbuf = reinterpret_cast<int*>(p);
+        M.stack = p;
+    }
+    const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
+    const int loose = (k / 2 > 7) ? k / 2 : 7;
+    unsigned long long n_nodes = 0, n_sprobes = 0, n_rprobes = 0;
+
+    for (;;) {
+        long long r = 0;
+        if (lane == 0) r = (long long)atomicAdd(&a.counters[RCX_C_WORK], 1ull);
+        r = __shfl_sync(RCX_FULL, r, 0);
+        if (r >= a.n) break;
+
+        const uint32_t o = a.off[r];
+        const int len = (int)(a.off[r + 1] - o);
+        const int kcnt = len - k + 1;
+        int result;           // return value of ErrorCorrection
+        bool changed = false; // seq was modified
+        int nN = 0, nA = 0, nT = 0;
+
+        if (kcnt <= 0) {  // :713 -> -1 ; GetKmerInformation gives 0,0,0
+            if (lane == 0) { a.correction[r] = -1; a.l[r] = 0; a.m[r] = 0; a.h[r] = 0; }
+            continue;
+        }
+        rcx_build_planes(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
+        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
+        const uint8_t fl = a.flags[r];
+        int pair_t = -1;
+        if (a.mode == 1) {
+            const int t1 = a.thr[r], t2 = a.thr[r ^ 1];
+            pair_t = t1 < t2 ? t1 : t2;
+        }
+        __syncwarp();
+
+        int total_fix = 0, bad_segments = 0;
+        if (fl & RCX_F_REJECT) {
+            result = -1;
+        } else {
+            // ---------------- A.3 initial thresholds (:772-842); the sort was done by the scan kernel
+            int strong = a.thr[r], trust;
+            bool flag = false;
+            trust = rcx_bound_i(strong, er);
+            if ((fl & RCX_F_DROP) && strong >= 20 && (fl & RCX_F_PREV2) && trust < 3) { flag = true; trust = 3; }
+            if (pair_t >= 1 && strong > pair_t) {
+                if (!flag || pair_t < 20) trust = rcx_bound_i(pair_t, er);
+                strong = pair_t;
+            }
+            for (int c = lane; c < mw; c += 32) M.pstrict[c] = 0;
+            __syncwarp();
+            for (int c = 0; (c << 5) < kcnt; ++c) {
+                const int j = (c << 5) + lane;
+                const unsigned int b = __ballot_sync(RCX_FULL, j < kcnt && rcx_polya(M.P, j, k, kmask32, 2));
+                if (lane == 0) M.pstrict[c] = b;
+            }
+            if (trust < 2) trust = 2;
+            __syncwarp();
+
+            int iter = 0;
+            result = -2;  // -2 = fall through to the post-filters
+            for (;;) {    // ---------------- A.4 (:853-1291)
+                bool unfixable = false, force_next = false;
+                total_fix = 0;
+                // trusted k-mers of this pass (:875)
+                for (int c = lane; c < mw; c += 32) { M.strong[c] = 0; M.trusted[c] = 0; }
+                __syncwarp();
+                for (int c = 0; (c << 5) < kcnt; ++c) {
+                    const int j = (c << 5) + lane;
+                    const unsigned int b = __ballot_sync(RCX_FULL, j < kcnt && M.counts[j] >= strong && !getbit(M.pstrict, j));
+                    if (lane == 0) M.trusted[c] = b;
+                }
+                __syncwarp();
+                if (next_bit(M.trusted, 0, kcnt, false, lane) >= kcnt) { result = 0; break; }  // longest == kcnt, :1110
+                // runs of trusted k-mers -> longest run, islands (runs >= 2), boundary adjustment, trusted positions
+                int longest = 0, tstart = 0, tend = -1;
+                {
+                    int pf = 0, pt = -1;
+                    bool have = false;
+                    int p = 0;
+                    while (p < kcnt) {
+                        const int s = next_bit(M.trusted, p, kcnt, true, lane);
+                        if (s >= kcnt) break;
+                        const int e = next_bit(M.trusted, s, kcnt, false, lane);
+                        const int rl = e - s;
+                        if (rl > longest) { longest = rl; tstart = s; tend = e - 1; }
+                        if (rl >= 2) {
+                            int cf = s, ct = e - 1;
+                            if (have) {
+                                if (cf <= pt + k) {  // :936-964
+                                    const int len1 = pt - pf, len2 = ct - cf, overlap = pt + k - cf;
+                                    const int j = pt + 1 + lane;
+                                    const bool low = j < cf && M.counts[j] <= 2 && M.counts[j] < trust;
+                                    if (__any_sync(RCX_FULL, low) && overlap <= 3) {
+                                        if (len1 < len2) pt -= overlap + 1; else cf += overlap + 1;
+                                    }
+                                }
+                                if (pf <= pt) set_range(M.strong, pf, pt + k - 1, mw, lane);
+                                __syncwarp();
+                            }
+                            pf = cf; pt = ct; have = true;
+                        }
+                        p = e;
+                    }
+                    if (have && pf <= pt) set_range(M.strong, pf, pt + k - 1, mw, lane);
+                    __syncwarp();
+                }
+                // islands that define the segments (:977-1007)
+                for (int c = lane; c < mw; c += 32) M.island[c] = M.strong[c];
+                __syncwarp();
+                if (next_bit(M.strong, 0, len, true, lane) >= len) {
+                    set_range(M.island, tstart, tend + k - 1, mw, lane);
+                    __syncwarp();
+                }
+                if (longest == kcnt) { result = 0; break; }  // :1110
+                for (int i = lane; i < len; i += 32) { M.fix[i] = -1; M.path[i] = -1; }
+                __syncwarp();
+
+                // ---------------- segments and searches (:1009-1046, :1118-1175)
+                bad_segments = 0;
+                int best_bn = RCX_INF, nseg = 0;
+                bool abort_read = false;
+                {
+                    int ifrom = next_bit(M.island, 0, len, true, lane);   // first island
+                    int ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
+                    int prev_to = -1, prev_len = 0;
+                    bool first = true;
+                    while (!abort_read) {
+                        // segment before island [ifrom, ito] (or the suffix segment when ifrom >= len)
+                        int sf, st, la, ra;
+                        bool is_seg;
+                        if (ifrom < len) {
+                            sf = prev_to + 1; st = ifrom - 1;
+                            la = first ? 0 : prev_len; ra = ito - ifrom + 1;
+                            is_seg = first ? ifrom > 0 : true;
+                        } else {
+                            sf = prev_to + 1; st = len; la = prev_len; ra = 0;
+                            is_seg = prev_to < len - 1;
+                        }
+                        if (is_seg) {
+                            SearchState S;
+                            S.trial = 0;
+                            S.max_fix = (st - sf + 1) * K / k * 2 + 1;
+                            if (S.max_fix < K) S.max_fix = K;
+                            S.best_bn = -1; S.best_cnt = -1; S.top2a = -1; S.top2b = -1;
+                            if (la >= ra) {
+                                const int extend = st == len ? 0 : k - 1;
+                                RcxKmer kc = seed_kmer(M.P, sf - k, k, kmask32);
+                                search_segment(a.t, M, S, true, sf, st + extend, trust, kc, len, er, lane, n_nodes, n_sprobes);
+                            } else {
+                                const int extend = sf == 0 ? 0 : k - 1;
+                                RcxKmer kc = seed_kmer(M.P, st + 1, k, kmask32);
+                                search_segment(a.t, M, S, false, st, sf - extend, trust, kc, len, er, lane, n_nodes, n_sprobes);
+                            }
+                            if (lane == 0 && nseg < L.nseg) M.segtop[nseg] = S.top2b;
+                            ++nseg;
+                            if (S.best_bn == -1) {
+                                ++bad_segments;
+                            } else {
+                                if (S.best_bn < best_bn) best_bn = S.best_bn;
+                                if (S.trial > RCX_MAX_TRIAL) abort_read = true;  // :1172
+                                else total_fix += S.max_fix;
+                            }
+                        }
+                        if (ifrom >= len) break;
+                        prev_to = ito; prev_len = ito - ifrom + 1; first = false;
+                        ifrom = next_bit(M.island, ito + 1, len, true, lane);
+                        ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
+                    }
+                }
+                if (abort_read) { result = -1; break; }
+                __syncwarp();
+                if (nseg > 0) {  // :1176-1230
+                    int best_fix_cnt = 1;
+                    for (int g = 0; g < nseg && g < L.nseg; ++g)
+                        if (M.segtop[g] >= best_bn) best_fix_cnt *= 2;
+                    if (iter == 0 && (double)best_bn < rcx_bound_d(strong, er)) force_next = true;  // :1195 FP64 compare
+                    if (best_fix_cnt >= 2) { result = -1; break; }
+                }
+                if (total_fix == 0 && force_next) { result = 0; break; }  // :1231
+                if (total_fix > len) unfixable = true;
+                if (!unfixable && !force_next) break;
+                if (trust < 10 && !force_next) { result = -1; break; }
+                // ---------------- re-threshold (:1247-1289)
+                const int n2 = rcx_pow2_at_least(kcnt);
+                for (int j = lane; j < n2; j += 32)
+                    M.sbuf[j] = j < kcnt ? (rcx_polya(M.P, j, k, kmask32, loose) ? -1 : M.counts[j]) : 0x7fffffff;
+                __syncwarp();
+                rcx_warp_sort(M.sbuf, n2, lane);
+                int ibreak = 0;
+                bool any_drop = false;
+                for (int i = 1 + lane; i < kcnt; i += 32) {
+                    const int v = M.sbuf[i], pv = M.sbuf[i - 1];
+                    if (v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5)) && v < strong) ibreak = i;
+                }
+                ibreak = __reduce_max_sync(RCX_FULL, ibreak);
+                for (int i = 1 + lane; i < kcnt; i += 32) {
+                    const int v = M.sbuf[i], pv = M.sbuf[i - 1];
+                    if (i >= ibreak && v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5))) any_drop = true;
+                }
+                any_drop = __any_sync(RCX_FULL, any_drop);
+                if (!any_drop) break;
+                ++iter;
+                const int nv = M.sbuf[ibreak];
+                trust = rcx_bound_i(nv, er);
+                strong = nv;
+                __syncwarp();
+            }
+
+            if (result == -2) {
+                // ---------------- A.7 post-filters (:1296-1466)
+                const char* q = a.qual + o;
+                const int q0 = q[0];
+                int* P = M.sbuf;  // ascending positions with a fix on a non-N base
+                int np = 0;
+                for (int c = 0; (c << 5) < len; ++c) {
+                    const int i = (c << 5) + lane;
+                    const bool f = i < len && M.fix[i] != -1 && !getbit(M.P.mN, i);
+                    const unsigned int b = __ballot_sync(RCX_FULL, f);
+                    if (f) P[np + __popc(b & ((1u << lane) - 1))] = i;
+                    np += __popc(b);
+                }
+                __syncwarp();
+                for (int i = 1; i < np; ++i) {  // pair filter (:1314-1398)
+                    const int pa = P[i - 1], pb = P[i];
+                    if (q0 != 0 && q[pb] <= Q && q[pa] <= Q) continue;
+                    if (pb - pa + 1 > k) continue;
+                    const int lim = (i < np - 1) ? P[i + 1] - k + 1 : 0x7fffffff;  // j + k - 1 >= P[i+1]  <=>  j >= lim
+                    int j0 = pa - k + 1;
+                    if (j0 < 0) j0 = 0;
+                    // loop 1: [j0, e1), skipping j <= P[i-2]
+                    const int skip = (i >= 2) ? P[i - 2] : -1;  // j <= P[i-2] is skipped BEFORE the break tests
+                    int e1 = pb - k + 1;
+                    if (e1 > lim) e1 = lim;
+                    if (e1 < skip + 1) e1 = skip + 1;
+                    if (e1 < j0) e1 = j0;
+                    if (e1 > kcnt) e1 = kcnt;
+                    int e2 = pa + 1;
+                    if (e2 > lim) e2 = lim;
+                    if (e2 > kcnt) e2 = kcnt;
+                    if (e2 < e1) e2 = e1;
+                    int e3 = pb + 1;
+                    if (e3 > lim) e3 = lim;
+                    if (e3 > kcnt) e3 = kcnt;
+                    if (e3 < e2) e3 = e2;
+                    int ms = RCX_INF, md = RCX_INF;
+                    for (int j = j0 + lane; j < e3; j += 32) {
+                        const int c = M.counts[j];
+                        if (j < e1) { if (j > skip && c < ms) ms = c; }
+                        else if (j < e2) { if (c < md) md = c; }
+                        else { if (c < ms) ms = c; }
+                    }
+                    ms = __reduce_min_sync(RCX_FULL, ms);
+                    md = __reduce_min_sync(RCX_FULL, md);
+                    if (ms != RCX_INF && md != RCX_INF && ms > 1 && md > 1 && ms > md / 2 && ms < 2 * md) {
+                        if (lane == 0) { M.fix[pb] = -1; M.fix[pa] = -1; }
+                        int j = i - 2;
+                        while (j >= 0 && P[j + 1] - P[j] + 1 <= k) { if (lane == 0) M.fix[P[j]] = -1; --j; }
+                        while (i + 1 < np && P[i + 1] - P[i] + 1 <= k) { if (lane == 0) M.fix[P[i + 1]] = -1; ++i; }
+                    }
+                }
+                __syncwarp();
+                if (total_fix > 3 && len > 10) {  // edge filter (:1407-1430)
+                    {
+                        const int i = lane;
+                        const bool nn = i < 10 && !getbit(M.P.mN, i);
+                        const bool f = nn && M.fix[i] != -1 && q[i] > Q;
+                        if (__popc(__ballot_sync(RCX_FULL, f)) >= 2 && nn) M.fix[i] = -1;
+                    }
+                    __syncwarp();
+                    {
+                        const int i = len - 10 + lane;
+                        const bool nn = lane < 10 && !getbit(M.P.mN, i);
+                        const bool f = nn && M.fix[i] != -1 && q[i] > Q;
+                        if (__popc(__ballot_sync(RCX_FULL, f)) >= 3 && nn) M.fix[i] = -1;
+                    }
+                    __syncwarp();
+                }
+                if (total_fix >= K) {  // density filter (:1432-1455), weights doubled to stay in integers
+                    for (int c = lane; c < 2 * mw; c += 32) M.fixm[c] = 0;
+                    __syncwarp();
+                    for (int c = 0; (c << 5) < len; ++c) {
+                        const int i = (c << 5) + lane;
+                        const bool f = i < len && M.fix[i] != -1 && !getbit(M.P.mN, i);
+                        const bool good = f && q[i] > Q;
+                        const unsigned int bg = __ballot_sync(RCX_FULL, good), bb = __ballot_sync(RCX_FULL, f && !good);
+                        if (lane == 0) { M.fixm[c] = bg; M.fixm[mw + c] = bb; }
+                    }
+                    __syncwarp();
+                    bool dense = false;
+                    for (int j = lane; j < kcnt; j += 32) {
+                        const int w2 = 2 * __popc(rcx_bits(M.fixm, j) & kmask32) + __popc(rcx_bits(M.fixm + mw, j) & kmask32);
+                        if (w2 > 2 * K) dense = true;
+                    }
+                    if (__any_sync(RCX_FULL, dense)) result = -1;
+                }
+                if (result == -2) {  // apply (:1468-1479)
+                    int ret = 0;
+                    for (int c = 0; (c << 5) < len; ++c) {
+                        const int i = (c << 5) + lane;
+                        const bool f = i < len && M.fix[i] != -1;
+                        if (f) a.seq[o + i] = "ACGT"[M.fix[i]];
+                        ret += __popc(__ballot_sync(RCX_FULL, f));
+                    }
+                    if (ret == 0 && bad_segments > 0) result = -1;
+                    else { result = ret; changed = ret > 0; }
+                }
+            }
+        }
+
+        // ---------------- GetKmerInformation on the final sequence (:1567-1602)
+        __syncwarp();
+        if (changed) {
+            // fold the fixes into the bit planes, then re-probe only the windows that cover a fix
+            for (int c = lane; c < mw; c += 32) M.fixm[c] = 0;
+            __syncwarp();
+            for (int c = 0; (c << 5) < len; ++c) {
+                const int i = (c << 5) + lane;
+                const bool f = i < len && M.fix[i] != -1;
+                const unsigned int bf = __ballot_sync(RCX_FULL, f);
+                const unsigned int sh = (unsigned int)(f ? M.fix[i] : 0) << (30 - 2 * (lane & 15));
+                const unsigned int keep = f ? ~(3u << (30 - 2 * (lane & 15))) : 0xffffffffu;
+                const unsigned int hi = __reduce_or_sync(RCX_FULL, lane < 16 ? sh : 0u), lo = __reduce_or_sync(RCX_FULL, lane >= 16 ? sh : 0u);
+                const unsigned int khi = __reduce_and_sync(RCX_FULL, lane < 16 ? keep : 0xffffffffu);
+                const unsigned int klo = __reduce_and_sync(RCX_FULL, lane >= 16 ? keep : 0xffffffffu);
+                if (lane == 0) {
+                    M.fixm[c] = bf;
+                    M.P.inv[c] &= ~bf;
+                    M.P.pk[2 * c] = (M.P.pk[2 * c] & khi) | hi;
+                    M.P.pk[2 * c + 1] = (M.P.pk[2 * c + 1] & klo) | lo;
+                }
+            }
+            __syncwarp();
+            for (int j = lane; j < kcnt; j += 32) {
+                if ((rcx_bits(M.fixm, j) & kmask32) == 0) continue;
+                int c = 0;
+                if ((rcx_bits(M.P.inv, j) & kmask32) == 0) {
+                    c = rcx_probe(a.t, rcx_canonical(rcx_window(M.P.pk, j, k), k));
+                    ++n_rprobes;
+                }
+                M.counts[j] = c;
+            }
+            __syncwarp();
+        }
+        {
+            const int n2 = rcx_pow2_at_least(kcnt);
+            int nvalid = 0;
+            for (int j = lane; j < n2; j += 32) {
+                int v = 0x7fffffff;
+                if (j < kcnt && (rcx_bits(M.P.inv, j) & kmask32) == 0) {
+                    v = M.counts[j];
+                    if (v == 0) v = 1;
+                    ++nvalid;
+                }
+                M.sbuf[j] = v;
+            }
+            nvalid = __reduce_add_sync(RCX_FULL, nvalid);
+            __syncwarp();
+            rcx_warp_sort(M.sbuf, n2, lane);
+            if (lane == 0) {
+                a.correction[r] = result;
+                if (nvalid > 0) { a.l[r] = M.sbuf[0]; a.m[r] = M.sbuf[nvalid / 2]; a.h[r] = M.sbuf[nvalid - 1]; }
+                else { a.l[r] = 0; a.m[r] = 0; a.h[r] = 0; }
+            }
+            __syncwarp();
+        }
+    }
+    n_nodes = warp_sum_u64(lane == 0 ? n_nodes : 0);
+    n_sprobes = warp_sum_u64(lane == 0 ? n_sprobes : 0);
+    n_rprobes = warp_sum_u64(n_rprobes);
+    if (lane == 0) {
+        if (n_nodes) atomicAdd(&a.counters[RCX_C_SEARCH_NODES], n_nodes);
+        if (n_sprobes) atomicAdd(&a.counters[RCX_C_SEARCH_PROBES], n_sprobes);
+        if (n_rprobes) atomicAdd(&a.counters[RCX_C_RESCAN_PROBES], n_rprobes);
+    }
+}
+
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
+    const size_t smem = rcx_correct_smem_per_warp(a.max_len, a.t.k) * COR_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(rcx_correct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_correct_kernel, COR_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (a.n + COR_WARPS - 1) / COR_WARPS;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > want) grid = want;
+    rcx_correct_kernel<<<(unsigned int)grid, COR_WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}

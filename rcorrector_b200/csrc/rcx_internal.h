@@ -1,0 +1,61 @@
+// rcx_internal.h — host-side declarations shared by the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rcx_device.cuh"
+
+// per-read flags written by the scan kernel
+#define RCX_F_DROP 1      // a "drop" was found in the sorted counts (ErrorCorrection.cpp:787-794)
+#define RCX_F_PREV2 2     // the entry below the drop equals 2 (ErrorCorrection.cpp:800)
+#define RCX_F_REJECT 4    // too short / too many N / A / T (ErrorCorrection.cpp:713,735-755)
+
+// device counters (unsigned long long each)
+enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK, RCX_C_COUNT };
+
+struct RcxScanArgs {
+    RcxTable t;
+    const char* seq;
+    const uint32_t* off;
+    long long n;
+    int max_len;
+    int32_t* counts;   // [off[n]] counts[off[r] + j]
+    int32_t* thr;      // [n] GetStrongTrustedThreshold
+    uint8_t* flags;    // [n]
+    unsigned long long* counters;
+};
+
+struct RcxCorrectArgs {
+    RcxTable t;
+    char* seq;             // corrected in place
+    const char* qual;
+    const uint32_t* off;
+    long long n;
+    int max_len;
+    int mode;              // rcx_mode
+    int max_fix_per_k;
+    double error_rate;
+    int bad_qual;
+    const int32_t* counts;
+    const int32_t* thr;
+    const uint8_t* flags;
+    int32_t* correction;
+    int32_t* l;
+    int32_t* m;
+    int32_t* h;
+    unsigned long long* counters;
+};
+
+// table (rcx_table.cu)
+cudaError_t rcx_launch_table_init(RcxBucket* buckets, unsigned long long nbuckets, cudaStream_t s);
+cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long bucket_mask, int k, const unsigned long long* codes,
+                                    const int32_t* counts, unsigned long long n, unsigned long long first_index,
+                                    unsigned long long* new_keys, cudaStream_t s);
+cudaError_t rcx_launch_table_lookup(RcxTable t, const unsigned long long* codes, int32_t* out, unsigned long long n,
+                                    cudaStream_t s);
+// scan (rcx_scan.cu)
+size_t rcx_scan_smem_per_warp(int max_len, int k);
+cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s);
+// correction (rcx_correct.cu)
+size_t rcx_correct_smem_per_warp(int max_len, int k);
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);

@@ -1,0 +1,148 @@
+// rcx_scan.cu — K1, the lookup kernel: one warp owns one read.
+//
+// Restates the scan shared by ErrorCorrection (ErrorCorrection.cpp:716-723)
+// and GetStrongTrustedThreshold (:1494-1501): counts[j] = GetCount of the
+// k-window starting at base j (0 for a window holding a non-ACGT base), plus
+// the whole of GetStrongTrustedThreshold (:1482-1565): reject tests, the
+// loose-polyA-masked ascending sort and the "drop" search.  The reference
+// runs this scan twice per paired read (pair threshold, then correction); on
+// the GPU it runs once and the correction kernel consumes counts[] from HBM.
+//
+// Data flow per warp: coalesced byte loads of the read -> bit planes in shared
+// memory (rcx_build_planes) -> every lane funnel-shifts its own k-windows out
+// of the packed plane, canonicalises and issues up to 4 independent 32-byte
+// bucket loads before consuming any (a 150 bp read = 128 windows = 4 sectors
+// in flight per lane) -> counts to shared + HBM -> warp bitonic sort.
+#include "rcx_internal.h"
+
+#define SCAN_WARPS 8
+#define SCAN_ILP 4
+
+size_t rcx_scan_smem_per_warp(int max_len, int k) {
+    int kcnt = max_len - k + 1;
+    if (kcnt < 1) kcnt = 1;
+    return sizeof(unsigned int) * (size_t)(rcx_pk_words(max_len) + 4 * rcx_mask_words(max_len) + rcx_pow2_at_least(kcnt));
+}
+
+__global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a) {
+    extern __shared__ unsigned int smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = a.t.k;
+    const int pkw = rcx_pk_words(a.max_len), mw = rcx_mask_words(a.max_len);
+    int maxk = a.max_len - k + 1;
+    if (maxk < 1) maxk = 1;
+    const int per_warp = pkw + 4 * mw + rcx_pow2_at_least(maxk);
+    unsigned int* base = smem + (size_t)warp * per_warp;
+    RcxPlanes P;
+    P.pk = base;
+    P.inv = base + pkw;
+    P.mA = P.inv + mw;
+    P.mT = P.mA + mw;
+    P.mN = P.mT + mw;
+    int* sbuf = reinterpret_cast<int*>(P.mN + mw);
+    const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
+    const int loose = (k / 2 > 7) ? k / 2 : 7;
+    unsigned long long probes = 0;
+
+    for (long long r = (long long)blockIdx.x * SCAN_WARPS + warp; r < a.n; r += (long long)gridDim.x * SCAN_WARPS) {
+        const uint32_t o = a.off[r];
+        const int len = (int)(a.off[r + 1] - o);
+        const int kcnt = len - k + 1;
+        if (kcnt <= 0) {  // strlen(seq) < kmerLength, :1491
+            if (lane == 0) { a.thr[r] = -1; a.flags[r] = RCX_F_REJECT; }
+            continue;
+        }
+        int nN, nA, nT;
+        rcx_build_planes(P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
+
+        // ---- probes: SCAN_ILP windows per lane in flight
+        for (int j0 = 0; j0 < kcnt; j0 += 32 * SCAN_ILP) {
+            unsigned long long canon[SCAN_ILP], bkt[SCAN_ILP], k0[SCAN_ILP], v0[SCAN_ILP], k1[SCAN_ILP], v1[SCAN_ILP];
+            bool live[SCAN_ILP];
+#pragma unroll
+            for (int u = 0; u < SCAN_ILP; ++u) {
+                const int j = j0 + u * 32 + lane;
+                live[u] = j < kcnt && (rcx_bits(P.inv, j < kcnt ? j : 0) & kmask32) == 0;
+                if (live[u]) {
+                    canon[u] = rcx_canonical(rcx_window(P.pk, j, k), k);
+                    bkt[u] = rcx_hash(canon[u]) & a.t.bucket_mask;
+                    rcx_load_bucket(a.t.buckets + bkt[u], k0[u], v0[u], k1[u], v1[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_ILP; ++u) {
+                const int j = j0 + u * 32 + lane;
+                int c = 0;
+                if (live[u]) {
+                    ++probes;
+                    for (;;) {
+                        if (k0[u] == canon[u]) { c = (int)(unsigned int)v0[u]; break; }
+                        if (k0[u] == RCX_EMPTY_KEY) break;
+                        if (k1[u] == canon[u]) { c = (int)(unsigned int)v1[u]; break; }
+                        if (k1[u] == RCX_EMPTY_KEY) break;
+                        bkt[u] = (bkt[u] + 1) & a.t.bucket_mask;
+                        rcx_load_bucket(a.t.buckets + bkt[u], k0[u], v0[u], k1[u], v1[u]);
+                    }
+                }
+                if (j < kcnt) {
+                    a.counts[o + j] = c;
+                    sbuf[j] = rcx_polya(P, j, k, kmask32, loose) ? -1 : c;  // :1530-1539
+                }
+            }
+        }
+        // ---- reject tests (:1507-1527)
+        const bool rej = nN > 5 || nA > len - k || nT > len - k;
+        if (rej) {
+            if (lane == 0) { a.thr[r] = -1; a.flags[r] = RCX_F_REJECT; }
+            __syncwarp();
+            continue;
+        }
+        // ---- masked sort + drop search (:1540-1563)
+        const int n2 = rcx_pow2_at_least(kcnt);
+        for (int j = kcnt + lane; j < n2; j += 32) sbuf[j] = 0x7fffffff;
+        __syncwarp();
+        rcx_warp_sort(sbuf, n2, lane);
+        int di = 0, nonpos = 0;
+        for (int i = lane; i < kcnt; i += 32) {
+            const int v = sbuf[i];
+            if (i >= 1) {
+                const int pv = sbuf[i - 1];
+                if (v > 2 * pv && v > 10) di = i;  // indices ascend per lane, so the last hit is the largest
+            }
+            nonpos += v <= 0;
+        }
+        di = __reduce_max_sync(RCX_FULL, di);
+        nonpos = __reduce_add_sync(RCX_FULL, nonpos);
+        if (lane == 0) {
+            int thr;
+            uint8_t fl = 0;
+            if (di >= 1) {
+                thr = sbuf[di];
+                fl = RCX_F_DROP | (sbuf[di - 1] == 2 ? RCX_F_PREV2 : 0);
+            } else {
+                thr = sbuf[(nonpos + kcnt - 1) / 2];  // first index with a positive value == number of entries <= 0
+            }
+            a.thr[r] = thr;
+            a.flags[r] = fl;
+        }
+        __syncwarp();
+    }
+    probes = __reduce_add_sync(RCX_FULL, (unsigned int)probes);
+    if (lane == 0 && probes) atomicAdd(&a.counters[RCX_C_SCAN_PROBES], probes);
+}
+
+cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
+    const size_t smem = rcx_scan_smem_per_warp(a.max_len, a.t.k) * SCAN_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(rcx_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_kernel, SCAN_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (a.n + SCAN_WARPS - 1) / SCAN_WARPS;
+    long long grid = (long long)sm_count * per_sm;  // persistent grid: a multiple of the SM count
+    if (grid > want) grid = want;
+    rcx_scan_kernel<<<(unsigned int)grid, SCAN_WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}

@@ -1,0 +1,126 @@
+"""GPU parity: the CUDA path through the C ABI (librcx.so) against the CPU oracle
+on the same seeded inputs.  Bit-exact: corrected bases, correction code, l/m/h."""
+import numpy as np
+import pytest
+
+import rcx_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+# name, k, paired, maxcorK, synth kwargs
+CASES = [
+    ("p100", 23, True, 4, dict(seed=1, ntx=50, reads=20000, len=100, err=0.01)),
+    ("s100", 23, False, 4, dict(seed=2, ntx=50, reads=20000, len=100, err=0.01)),
+    ("k31deep", 31, True, 8, dict(seed=5, ntx=20, reads=5000, len=150, err=0.04)),
+    ("repeat", 23, True, 4, dict(seed=11, ntx=25, reads=30000, len=100, err=0.02, paralog=0.4, repeat=0.4, nrate=0.01)),
+    ("maxcor1", 23, True, 1, dict(seed=12, ntx=25, reads=10000, len=100, err=0.02, paralog=0.4, repeat=0.4, nrate=0.01)),
+    ("maxcor2", 23, True, 2, dict(seed=13, ntx=25, reads=10000, len=100, err=0.03, paralog=0.5, repeat=0.5, nrate=0.01)),
+    ("hicov", 23, True, 4, dict(seed=14, ntx=10, reads=30000, len=100, err=0.01, sigma=1.0)),
+    ("k32", 32, True, 4, dict(seed=15, ntx=30, reads=5000, len=120, err=0.02)),
+    ("k15", 15, False, 4, dict(seed=16, ntx=30, reads=5000, len=60, err=0.02, txmin=100)),
+    ("long250", 25, True, 4, dict(seed=17, ntx=30, reads=4000, len=250, err=0.02, txmin=400)),
+]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from rcorrector_b200 import Corrector
+
+    c = Corrector(0)
+    yield c
+    c.close()
+
+
+def _load(workdir, name, k, paired, kw):
+    d = T.synth(workdir, name, k=k, paired=paired, **kw)
+    bs = [T.read_fastq(f) for f in d["fq"]]
+    b = T.interleave(*bs) if paired else bs[0]
+    codes, counts = T.load_table_arrays(d["tab"])
+    return d, bs, b, codes, counts
+
+
+@pytest.mark.parametrize("name,k,paired,maxcor,kw", CASES, ids=[c[0] for c in CASES])
+def test_correct_batch_matches_oracle(gpu, workdir, name, k, paired, maxcor, kw):
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    mode = T.INTERLEAVED if paired else T.SINGLE
+    exp = T.oracle_correct(table, b, k, mode, er, bq, maxcor)
+
+    gpu.build_table(k, codes, counts)
+    assert gpu.table_info()["entries"] == len(table)
+    gpu.set_params(k, er, bq, maxcor)
+    got = gpu.correct(mode, b.seq, b.qual, b.off)
+    st = gpu.stats()
+    assert st["kernel_launches"] == 2
+
+    names = ["seq", "correction", "l", "m", "h"]
+    for nm, e, g in zip(names, exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "%s: %d mismatches, first at %d (exp %r got %r)" % (nm, len(bad), bad[0], e[bad[0]], g[bad[0]])
+    assert int((exp[1] > 0).sum()) > 0  # the case really exercises corrections
+
+
+@pytest.mark.parametrize("name,k,paired,maxcor,kw", CASES[:4], ids=[c[0] for c in CASES[:4]])
+def test_scan_matches_oracle(gpu, workdir, name, k, paired, maxcor, kw):
+    """Stage parity for the lookup kernel: counts[] and GetStrongTrustedThreshold."""
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    b = b.slice(0, min(b.n, 4000))
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    exp_counts, exp_thr = T.oracle_scan_counts(table, b)
+    gpu.build_table(k, codes, counts)
+    got_counts, got_thr = gpu.scan(b.seq, b.off)
+    # only the first kcnt entries of each read are defined
+    lens = np.diff(b.off.astype(np.int64))
+    valid = np.zeros(len(b.seq), dtype=bool)
+    for r in range(b.n):
+        kc = max(0, lens[r] - k + 1)
+        valid[b.off[r] : b.off[r] + kc] = True
+    assert np.array_equal(exp_counts[valid], got_counts[valid])
+    assert np.array_equal(exp_thr, got_thr)
+
+
+def test_table_lookup_and_duplicates(gpu):
+    """Store::Put semantics: canonicalisation, count<=1 skipped, last writer wins."""
+    rng = np.random.default_rng(3)
+    k = 23
+    codes = rng.integers(0, 1 << 46, size=200000, dtype=np.uint64)
+    counts = rng.integers(0, 500, size=len(codes), dtype=np.int32)
+    # duplicates (same code again, later record) and reverse-complement duplicates
+    codes = np.concatenate([codes, codes[:5000]])
+    counts = np.concatenate([counts, rng.integers(2, 9, size=5000, dtype=np.int32)])
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    gpu.build_table(k, codes, counts)
+    assert gpu.table_info()["entries"] == len(table)
+    q = np.concatenate([codes[:50000], rng.integers(0, 1 << 46, size=50000, dtype=np.uint64)])
+    exp = np.array([T.oracle().orc_table_count(table.h, int(x)) for x in q], dtype=np.int32)
+    assert np.array_equal(gpu.lookup(q), exp)
+
+
+def test_edge_cases(gpu, workdir):
+    """Empty batch, reads shorter than k, all-N, poly-A, exactly-k reads, N-rich reads."""
+    k = 23
+    d, bs, b, codes, counts = _load(workdir, "edge", k, False, dict(seed=21, ntx=10, reads=2000, len=80, err=0.02))
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, 0.01, 48, 4)
+    # empty batch
+    so, corr, l, m, h = gpu.correct(T.SINGLE, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint32))
+    assert len(corr) == 0
+    base = b.seq[: b.off[1]].tobytes()
+    reads = [b"ACGT", b"N" * 40, b"A" * 60, base[:k], base[: k + 1], base[:40] + b"NNNNNNN" + base[47:80],
+             base[:30] + b"N" + base[31:80], b"T" * 22 + base[22:80], base[:79], b"ACGTN" * 12, base]
+    seq = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    qual = np.full(len(seq), ord("I"), dtype=np.uint8)
+    off = np.zeros(len(reads) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    eb = T.Batch([b"@x"] * len(reads), seq, qual, off)
+    exp = T.oracle_correct(table, eb, k, T.SINGLE, 0.01, 48, 4)
+    got = gpu.correct(T.SINGLE, eb.seq, eb.qual, eb.off)
+    for e, g in zip(exp, got):
+        assert np.array_equal(e, g)
