@@ -153,6 +153,8 @@ int main(int argc, char** argv) {
     }
 
     // ---------------------------------------------------------------- reads
+    const long nrec_all = o.paired ? 2 * o.reads : o.reads;  // the table's expected coverage always uses the full workload
+    if (!o.bin && o.fq1 && o.fqlimit >= 0 && o.fqlimit < o.reads) o.reads = o.fqlimit;  // FASTQ sample only: generate just that prefix
     const long nrec = o.paired ? 2 * o.reads : o.reads;
     const bool want_reads = o.bin || o.fq1;
     std::vector<uint32_t> off;
@@ -265,7 +267,7 @@ int main(int argc, char** argv) {
         const int k = o.k;
         const uint64_t mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
         // expected per-base coverage of transcript t
-        const double total_bases = (double)nrec * o.len;
+        const double total_bases = (double)nrec_all * o.len;
         struct KC { uint64_t code; int32_t cnt; };
         std::vector<size_t> base(T + 1, 0);
         for (long t = 0; t < T; ++t) base[t + 1] = base[t] + (tx[t].size() >= (size_t)k ? tx[t].size() - k + 1 : 0);
