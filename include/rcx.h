@@ -112,6 +112,8 @@ int rcx_scan_batch(rcx_ctx* ctx, int64_t n, const char* seq, const uint32_t* off
                    int32_t* strong_threshold_out);
 
 int rcx_get_stats(rcx_ctx* ctx, rcx_stats* out);
+/* raw device counters of the last call (profiling builds add a search breakdown and per-phase cycle sums) */
+int rcx_debug_counters(rcx_ctx* ctx, uint64_t* out, int n);
 /* raw CUDA stream handle (cudaStream_t) of the context, for callers that enqueue their own copies */
 void* rcx_stream(rcx_ctx* ctx);
 /* pinned host memory for batch buffers (cudaHostAlloc / cudaFreeHost) */

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librcx.so")
+LIB_PATH = os.environ.get("RCX_LIB", os.path.join(_HERE, "librcx.so"))  # RCX_LIB: profiling build (make prof)
 
 SINGLE, INTERLEAVED = 0, 1
 
@@ -19,7 +19,7 @@ SINGLE, INTERLEAVED = 0, 1
 SYMBOLS = [
     "rcx_abi_version", "rcx_last_error", "rcx_create", "rcx_destroy", "rcx_table_build", "rcx_table_lookup",
     "rcx_table_info", "rcx_set_params", "rcx_correct_batch", "rcx_correct_batch_device", "rcx_sync",
-    "rcx_scan_batch", "rcx_get_stats", "rcx_stream", "rcx_host_alloc", "rcx_host_free", "rcx_estimate_error_rate",
+    "rcx_scan_batch", "rcx_get_stats", "rcx_debug_counters", "rcx_stream", "rcx_host_alloc", "rcx_host_free", "rcx_estimate_error_rate",
 ]
 
 
@@ -67,6 +67,7 @@ def load_library():
     lib.rcx_sync.argtypes = [vp]
     lib.rcx_scan_batch.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.rcx_get_stats.argtypes = [vp, C.POINTER(RcxStats)]
+    lib.rcx_debug_counters.argtypes = [vp, vp, C.c_int]
     lib.rcx_stream.argtypes = [vp]
     lib.rcx_stream.restype = vp
     lib.rcx_host_alloc.argtypes = [u64]
@@ -178,6 +179,11 @@ class Corrector:
         s = RcxStats()
         self._check(self.lib.rcx_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def debug_counters(self, n=16):
+        out = np.zeros(n, dtype=np.uint64)
+        self._check(self.lib.rcx_debug_counters(self.h, _ptr(out), n))
+        return out
 
     def stream(self):
         return self.lib.rcx_stream(self.h)

@@ -1,0 +1,164 @@
+// fastq_io.h — host-side read I/O of the drop-in `rcorrector` binary.
+//
+// Behaviour follows the reference's reader/writer (Reads.h:108-162 AddReadFile,
+// :224-266 NextWithBuffer, :360-421 OutputBatch, :39-75 GetFileName;
+// File.h:51-69 gz detection by the last two characters of the path, gzopen
+// "w1") so that the bytes written equal the reference's; the implementation is
+// a chunked block reader + batch formatter instead of per-line fgets/Printf.
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace rcxio {
+
+inline bool ends_with_gz(const std::string& p) {  // File.h:51-55
+    return p.size() >= 2 && p[p.size() - 2] == 'g' && p[p.size() - 1] == 'z';
+}
+
+// Reads.h:39-75: basename without directory and without the last extension; for *.gz also a preceding
+// .fastq/.fasta/.fq/.fa is dropped.
+inline std::string output_stem(const std::string& in) {
+    const int len = (int)in.size();
+    int i = len - 1;  // last '.' or '/' scanning from the end
+    while (i >= 0 && in[i] != '.' && in[i] != '/') --i;
+    if (i >= 0 && in.compare(i, std::string::npos, ".gz") == 0) {
+        const int tmp = i;
+        int j = i - 1;
+        while (j >= 0 && in[j] != '.' && in[j] != '/') --j;
+        const std::string ext = j >= 0 ? in.substr(j, tmp - j) : std::string();
+        if (j >= 0 && (ext == ".fastq" || ext == ".fasta" || ext == ".fq" || ext == ".fa")) i = j;
+        else i = tmp;
+    }
+    int s = len - 1;
+    while (s >= 0 && in[s] != '/') --s;
+    if (i >= 0 && in[i] == '.') return in.substr(s + 1, i - (s + 1));
+    return in.substr(s + 1);
+}
+
+// Block reader over a plain or gzip file that hands out lines (without the '\n').
+class LineReader {
+   public:
+    bool open(const std::string& path) {
+        close();
+        gz_ = ends_with_gz(path);
+        if (gz_) {
+            g_ = gzopen(path.c_str(), "r");
+            if (g_) gzbuffer(g_, 1 << 20);
+            return g_ != nullptr;
+        }
+        f_ = fopen(path.c_str(), "r");
+        return f_ != nullptr;
+    }
+    void close() {
+        if (f_) fclose(f_);
+        if (g_) gzclose(g_);
+        f_ = nullptr;
+        g_ = nullptr;
+        beg_ = end_ = 0;
+        eof_ = false;
+    }
+    ~LineReader() { close(); }
+    // returns false at end of file; `had_nl` tells whether the line ended with '\n'
+    bool getline(const char*& p, size_t& n, bool& had_nl) {
+        for (;;) {
+            if (beg_ < end_) {
+                const char* s = buf_.data() + beg_;
+                const void* nl = memchr(s, '\n', end_ - beg_);
+                if (nl) {
+                    p = s;
+                    n = (const char*)nl - s;
+                    had_nl = true;
+                    beg_ += n + 1;
+                    return true;
+                }
+                if (eof_) {
+                    p = s;
+                    n = end_ - beg_;
+                    had_nl = false;
+                    beg_ = end_;
+                    return true;
+                }
+            } else if (eof_) {
+                return false;
+            }
+            fill();
+        }
+    }
+
+   private:
+    void fill() {
+        if (beg_ > 0) {
+            memmove(buf_.data(), buf_.data() + beg_, end_ - beg_);
+            end_ -= beg_;
+            beg_ = 0;
+        }
+        if (buf_.size() - end_ < (1u << 20)) buf_.resize(buf_.size() + (8u << 20));
+        long got;
+        if (gz_) got = gzread(g_, buf_.data() + end_, (unsigned)(buf_.size() - end_));
+        else got = (long)fread(buf_.data() + end_, 1, buf_.size() - end_, f_);
+        if (got <= 0) eof_ = true;
+        else end_ += (size_t)got;
+    }
+    FILE* f_ = nullptr;
+    gzFile g_ = nullptr;
+    bool gz_ = false, eof_ = false;
+    std::vector<char> buf_ = std::vector<char>(8u << 20);
+    size_t beg_ = 0, end_ = 0;
+};
+
+class Writer {
+   public:
+    bool open(const std::string& path, bool to_stdout) {  // File.h:38-75
+        if (to_stdout) { f_ = stdout; own_ = false; return true; }
+        if (ends_with_gz(path)) { g_ = gzopen(path.c_str(), "w1"); if (g_) gzbuffer(g_, 1 << 20); return g_ != nullptr; }
+        f_ = fopen(path.c_str(), "w");
+        return f_ != nullptr;
+    }
+    void write(const char* p, size_t n) {
+        if (g_) gzwrite(g_, p, (unsigned)n);
+        else fwrite(p, 1, n, f_);
+    }
+    void close() {
+        if (g_) gzclose(g_);
+        if (f_ && own_) fclose(f_);
+        else if (f_) fflush(f_);
+        g_ = nullptr;
+        f_ = nullptr;
+    }
+    ~Writer() { close(); }
+
+   private:
+    FILE* f_ = nullptr;
+    gzFile g_ = nullptr;
+    bool own_ = true;
+};
+
+// One chunk of records of ONE input file, in the layout the C ABI takes.
+struct Chunk {
+    std::vector<char> ids;          // id lines concatenated (newline stripped)
+    std::vector<uint32_t> id_off;   // n+1
+    std::vector<char> qual_text;    // only used when a quality line's length differs from its sequence (kept verbatim)
+    std::vector<uint32_t> qual_text_off;
+    bool ragged_qual = false;
+    size_t n = 0;
+    void clear() { ids.clear(); id_off.assign(1, 0); qual_text.clear(); qual_text_off.assign(1, 0); ragged_qual = false; n = 0; }
+};
+
+inline size_t format_int(char* p, int v) {  // "%d"
+    char tmp[16];
+    int n = 0;
+    unsigned int u = v < 0 ? 0u - (unsigned int)v : (unsigned int)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    size_t w = 0;
+    if (v < 0) p[w++] = '-';
+    while (n) p[w++] = tmp[--n];
+    return w;
+}
+
+}  // namespace rcxio

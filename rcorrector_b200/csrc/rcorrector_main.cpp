@@ -1,0 +1,555 @@
+// rcorrector_main.cpp — the drop-in `rcorrector` stage-3 binary (process surface of SURVEY §8b).
+//
+// Keeps the reference's command line (main.cpp:165-268), stderr lines
+// (main.cpp:308,358,364,81-86), exit codes and output naming / bytes
+// (Reads.h:138-157,360-421), so `run_rcorrector.pl ... -stage 3` can call it
+// unmodified.  Everything between "load the dump" and "write the records" is
+// replaced: the dump is parsed in bulk into (code, count) arrays, the table is
+// built in HBM through the C ABI (rcx_table_build), and where the reference
+// creates/joins its pthreads per 512*t reads (main.cpp:476-483) this binary
+// hands multi-million-read batches to rcx_correct_batch — one host thread per
+// GPU, reads sharded by record range (mates stay together), output in input
+// order.  There is no CPU correction path: without a GPU it exits 1.
+//
+// Extra options (not in the reference): -gpus N (default 1; env RCX_GPUS),
+// -batch N (records per device batch, default 4M).
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rcx.h"
+#include "fastq_io.h"
+
+using rcxio::Chunk;
+using rcxio::LineReader;
+using rcxio::Writer;
+
+static void print_help() {  // main.cpp:50-71 (same text: scripts and users read it)
+    fprintf(stderr,
+            "Usage: ./rcorrector [OPTIONS]\n"
+            "OPTIONS:\n"
+            "Required parameters:\n"
+            "\t-r seq_file: seq_file is the path to the sequence file. Can use multiple -r to specifiy multiple sequence files\n"
+            "\t-p seq_file_left seq_file_right: the paths to the paired-end data set. Can use multiple -p to specifiy multiple sequence files\n"
+            "\t-i seq_file: seq_file is the path to the interleaved mate-pair sequence file. Can use multiple -i\n"
+            "\t-c jf_dump: the kmer counts dumped by JellyFish\n"
+            "\t-k kmer_length\n"
+            "Other parameters:\n"
+            "\t-od output_file_directory (default: ./)\n"
+            "\t-t number of threads to use (default: 1)\n"
+            "\t-maxcor INT: the maximum number of correction every 100bp (default: 8)\n"
+            "\t-maxcorK INT: the maximum number of correction within k-bp window (default: 4)\n"
+            "\t-wk FLOAT: the proportion of kmers that are used to estimate weak kmer count threshold (default: 0.95)\n"
+            "\t-stdout: output the corrected sequences to stdout (default: not used)\n"
+            "\t-verbose: output some correction information to stdout (default: not used)\n");
+}
+
+static void die_rcx(const char* what) {
+    fprintf(stderr, "%s: %s\n", what, rcx_last_error());
+    exit(1);
+}
+
+struct ReadFile {
+    std::string path;
+    std::string mate_path;  // second mate for -p
+    bool paired = false, interleaved = false;
+    int type = 1;  // 0 FASTA, 1 FASTQ (Reads.h:118-132)
+    std::string out_path, mate_out_path;
+};
+
+static int sniff_type(const std::string& path) {  // Reads.h:108-132
+    LineReader r;
+    if (!r.open(path)) {
+        fprintf(stderr, "ERROR: Could not open file %s\n", path.c_str());
+        exit(1);
+    }
+    const char* p;
+    size_t n;
+    bool nl;
+    if (!r.getline(p, n, nl) || n == 0 || (p[0] != '>' && p[0] != '@')) {
+        fprintf(stderr, "\"%s\"'s format is wrong: %.*s\n", path.c_str(), (int)(r.getline(p, n, nl) ? n : 0), p);
+        exit(1);
+    }
+    return p[0] == '@' ? 1 : 0;
+}
+
+static std::string out_name(const std::string& od, const std::string& in, int type) {  // Reads.h:138-157
+    std::string stem = rcxio::output_stem(in);
+    std::string s = od + "/" + stem + (type == 1 ? ".cor.fq" : ".cor.fa");
+    if (rcxio::ends_with_gz(in)) s += ".gz";
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------- dump loading
+struct Dump {
+    std::vector<uint64_t> codes;   // every record, in file order (KmerCode::Append over the k-mer token)
+    std::vector<int32_t> counts;   // atoi(&token[1]); records with an invalid k-mer get count 0 (Store::Put ignores them)
+    int64_t stored = 0;            // the "Stored %d kmers" number (main.cpp:306)
+    uint64_t rate_records = 0;     // how many leading records the ERROR_RATE pass may use (validity quirk, main.cpp:323)
+};
+
+static inline int nuc(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+static void load_dump(const char* path, int k, Dump& d) {  // main.cpp:294-308 with a block reader instead of fscanf("%s")
+    FILE* fp = fopen(path, "r");
+    if (!fp) {
+        fprintf(stderr, "Could not open file %s\n", path);
+        exit(1);
+    }
+    const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    std::vector<char> buf(64u << 20);
+    size_t have = 0;
+    bool eof = false, want_count = true, rate_open = true;
+    int last_inv_state = -1;  // KmerCode::invalidPos left by the last STORED record of this loop
+    int cur_count = 0;
+    while (!eof || have) {
+        if (!eof) {
+            size_t got = fread(buf.data() + have, 1, buf.size() - have, fp);
+            if (got == 0) eof = true;
+            have += got;
+        }
+        size_t pos = 0, consumed = 0;
+        for (;;) {
+            while (pos < have && (unsigned char)buf[pos] <= ' ') ++pos;  // %s skips whitespace
+            size_t s = pos;
+            while (pos < have && (unsigned char)buf[pos] > ' ') ++pos;
+            if (pos == have && !eof) break;  // token may continue in the next block
+            if (s == pos) { consumed = have; break; }
+            if (want_count) {
+                // atoi(&buffer[1])
+                long v = 0;
+                size_t q = s + 1;
+                bool neg = false;
+                if (q < pos && (buf[q] == '-' || buf[q] == '+')) { neg = buf[q] == '-'; ++q; }
+                while (q < pos && buf[q] >= '0' && buf[q] <= '9') { v = v * 10 + (buf[q] - '0'); if (v > 2147483647L) v = 2147483647L; ++q; }
+                cur_count = (int)(neg ? -v : v);
+                want_count = false;
+            } else {
+                uint64_t code = 0;
+                int inv = -1;
+                for (size_t q = s; q < pos; ++q) {  // KmerCode::Append, KmerCode.cpp:7-21
+                    const int v = nuc(buf[q]);
+                    if (inv != -1) ++inv;
+                    code = ((code << 2) & mask) | (uint64_t)(v & 3);
+                    if (v < 0) inv = 0;
+                    if (inv >= k) inv = -1;
+                }
+                d.codes.push_back(code);
+                if (cur_count > 1) {
+                    ++d.stored;
+                    last_inv_state = inv;
+                    d.counts.push_back(inv == -1 ? cur_count : 0);
+                } else {
+                    d.counts.push_back(0);
+                }
+                // the ERROR_RATE pass stops being able to use records once one of them leaves the shared KmerCode
+                // invalid after the 4 last-base variants (an invalid character anywhere but the last position)
+                if (rate_open) {
+                    if (inv > 0) rate_open = false;
+                    else d.rate_records = d.codes.size();
+                }
+                want_count = true;
+            }
+            consumed = pos;
+        }
+        memmove(buf.data(), buf.data() + consumed, have - consumed);
+        have -= consumed;
+        if (eof && have && consumed == 0) break;
+    }
+    fclose(fp);
+    if (last_inv_state != -1) d.rate_records = 0;  // main.cpp:323 tests the state the load loop left behind
+}
+
+// ---------------------------------------------------------------------------------------------- per-file processing
+struct Gpu {
+    rcx_ctx* ctx = nullptr;
+};
+
+struct HostBatch {
+    char* seq = nullptr;
+    char* qual = nullptr;
+    uint32_t* off = nullptr;
+    int32_t *corr = nullptr, *l = nullptr, *m = nullptr, *h = nullptr;
+    size_t cap_bases = 0, cap_reads = 0;
+    size_t n = 0, bases = 0;
+    void alloc(size_t reads, size_t bases_) {
+        cap_reads = reads;
+        cap_bases = bases_;
+        seq = (char*)rcx_host_alloc(bases_ + 64);
+        qual = (char*)rcx_host_alloc(bases_ + 64);
+        off = (uint32_t*)rcx_host_alloc((reads + 1) * 4);
+        corr = (int32_t*)rcx_host_alloc(reads * 4);
+        l = (int32_t*)rcx_host_alloc(reads * 4);
+        m = (int32_t*)rcx_host_alloc(reads * 4);
+        h = (int32_t*)rcx_host_alloc(reads * 4);
+        if (!seq || !qual || !off || !corr || !l || !m || !h) die_rcx("pinned allocation failed");
+    }
+};
+
+// read one record into the batch; returns false at end of file
+static bool read_record(LineReader& r, int type, HostBatch& b, Chunk& c, const std::string& path) {
+    const char* p;
+    size_t n;
+    bool nl;
+    if (!r.getline(p, n, nl)) return false;
+    c.ids.insert(c.ids.end(), p, p + n);
+    c.id_off.push_back((uint32_t)c.ids.size());
+    size_t L = 0;
+    bool seq_nl = false;
+    if (r.getline(p, n, nl)) {
+        L = n;
+        seq_nl = nl;
+        if (L > RCX_MAX_READ_LENGTH) {
+            fprintf(stderr, "ERROR: a read in %s is longer than %d bases.\n", path.c_str(), RCX_MAX_READ_LENGTH);
+            exit(1);
+        }
+        memcpy(b.seq + b.bases, p, L);
+    }
+    if (type == 1) {
+        r.getline(p, n, nl);  // '+' line: dropped (Reads.h:246)
+        size_t qn = 0;
+        bool qnl = false;
+        const char* qp = nullptr;
+        if (r.getline(qp, qn, qnl)) {
+            // Reads.h:255-262: the newline is stripped at the SEQUENCE line's length
+            const size_t strip_at = L + (seq_nl ? 1 : 0) - 1;
+            if (qn == L || (qn == strip_at && qnl)) {
+                memcpy(b.qual + b.bases, qp, std::min(qn, L));
+                if (qn < L) memset(b.qual + b.bases + qn, 0, L - qn);
+            } else {
+                c.ragged_qual = true;
+                memcpy(b.qual + b.bases, qp, std::min(qn, L));
+                if (qn < L) memset(b.qual + b.bases + qn, 0, L - qn);
+            }
+            if (c.ragged_qual || qn != L) {
+                // keep verbatim text (with its newline if it was not stripped) for the writer
+                while (c.qual_text_off.size() < c.id_off.size() - 1) c.qual_text_off.push_back((uint32_t)c.qual_text.size());
+                c.qual_text.insert(c.qual_text.end(), qp, qp + qn);
+                if (qnl && qn != strip_at) c.qual_text.push_back('\n');
+                c.qual_text_off.push_back((uint32_t)c.qual_text.size());
+                c.ragged_qual = true;
+            }
+        } else {
+            memset(b.qual + b.bases, 0, L);
+        }
+    } else {
+        memset(b.qual + b.bases, 0, L);  // FASTA: qual[0] == '\0' (Reads.h:241)
+    }
+    b.bases += L;
+    b.off[++b.n] = (uint32_t)b.bases;
+    c.n = b.n;
+    return true;
+}
+
+// Reads.h:360-421 OutputBatch for records [lo, hi) of the batch (stride/start select one mate of an interleaved batch)
+static void format_records(const HostBatch& b, const Chunk& c, int type, size_t lo, size_t hi, size_t stride, std::string& out) {
+    out.clear();
+    char num[16];
+    for (size_t r = lo; r < hi; r += stride) {
+        out.append(c.ids.data() + c.id_off[r], c.id_off[r + 1] - c.id_off[r]);
+        out.append(" l:");
+        out.append(num, rcxio::format_int(num, b.l[r]));
+        out.append(" m:");
+        out.append(num, rcxio::format_int(num, b.m[r]));
+        out.append(" h:");
+        out.append(num, rcxio::format_int(num, b.h[r]));
+        if (b.corr[r] == -1) out.append(" unfixable_error");
+        else if (b.corr[r] > 0) out.append(" cor");
+        out.push_back('\n');
+        out.append(b.seq + b.off[r], b.off[r + 1] - b.off[r]);
+        out.push_back('\n');
+        if (type == 1) {
+            out.append("+\n");
+            if (c.ragged_qual && r + 1 < c.qual_text_off.size() && c.qual_text_off[r + 1] > c.qual_text_off[r])
+                out.append(c.qual_text.data() + c.qual_text_off[r], c.qual_text_off[r + 1] - c.qual_text_off[r]);
+            else
+                out.append(b.qual + b.off[r], b.off[r + 1] - b.off[r]);
+            out.push_back('\n');
+        }
+    }
+}
+
+static void correct_on_gpus(std::vector<Gpu>& gpus, int mode, HostBatch& b) {
+    const size_t n = b.n;
+    if (n == 0) return;
+    const size_t G = gpus.size();
+    if (G == 1) {
+        if (rcx_correct_batch(gpus[0].ctx, mode, (int64_t)n, b.seq, b.qual, b.off, b.seq, b.corr, b.l, b.m, b.h)) die_rcx("rcx_correct_batch");
+        return;
+    }
+    // contiguous record-index shards, both mates of a pair on the same GPU
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(G);
+    const size_t unit = mode == RCX_INTERLEAVED ? 2 : 1;
+    const size_t units = n / unit;
+    for (size_t g = 0; g < G; ++g) {
+        const size_t lo = units * g / G * unit, hi = units * (g + 1) / G * unit;
+        if (lo == hi) continue;
+        th.emplace_back([&, g, lo, hi]() {
+            std::vector<uint32_t> off(hi - lo + 1);
+            for (size_t i = lo; i <= hi; ++i) off[i - lo] = b.off[i] - b.off[lo];
+            if (rcx_correct_batch(gpus[g].ctx, mode, (int64_t)(hi - lo), b.seq + b.off[lo], b.qual + b.off[lo], off.data(), b.seq + b.off[lo],
+                                  b.corr + lo, b.l + lo, b.m + lo, b.h + lo))
+                errs[g] = rcx_last_error();
+        });
+    }
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (!e.empty()) {
+            fprintf(stderr, "rcx_correct_batch: %s\n", e.c_str());
+            exit(1);
+        }
+}
+
+int main(int argc, char* argv[]) {
+    int k = 23, threads = 1, max_fix_per_k = 4, ngpu = 1;
+    double wk = 0.95;
+    bool to_stdout = false;
+    const char* dump_path = nullptr;
+    std::string od = "./";
+    size_t batch_reads = 4u << 20;
+    if (const char* e = getenv("RCX_GPUS")) ngpu = atoi(e);
+    if (argc == 1) {
+        print_help();
+        exit(0);
+    }
+    for (int i = 1; i < argc; ++i) {  // first pass: options (main.cpp:165-247)
+        if (!strcmp("-r", argv[i])) { ++i; continue; }
+        else if (!strcmp("-p", argv[i])) { i += 2; continue; }
+        else if (!strcmp("-i", argv[i])) { ++i; continue; }
+        else if (!strcmp("-od", argv[i])) { mkdir(argv[i + 1], 0700); od = argv[i + 1]; ++i; }
+        else if (!strcmp("-c", argv[i])) { dump_path = argv[i + 1]; ++i; }
+        else if (!strcmp("-k", argv[i])) { k = atoi(argv[i + 1]); ++i; }
+        else if (!strcmp("-t", argv[i])) { threads = atoi(argv[i + 1]); ++i; }
+        else if (!strcmp("-maxcor", argv[i])) { ++i; }  // parsed and unused by the reference as well (dead parameter)
+        else if (!strcmp("-maxcorK", argv[i])) { max_fix_per_k = atoi(argv[i + 1]); ++i; }
+        else if (!strcmp("-wk", argv[i])) { wk = atof(argv[i + 1]); ++i; }
+        else if (!strcmp("-stdout", argv[i])) { to_stdout = true; }
+        else if (!strcmp("-verbose", argv[i])) { /* per-read trace to stdout: not produced */ }
+        else if (!strcmp("-gpus", argv[i])) { ngpu = atoi(argv[i + 1]); ++i; }
+        else if (!strcmp("-batch", argv[i])) { batch_reads = (size_t)atol(argv[i + 1]); ++i; }
+        else if (!strcmp("-h", argv[i])) { print_help(); exit(0); }
+        else { fprintf(stderr, "Unknown argument: %s\n", argv[i]); exit(0); }
+    }
+    if (!dump_path) {
+        fprintf(stderr, "Could not open file (no -c jf_dump given)\n");
+        exit(1);
+    }
+    {
+        FILE* t = fopen(dump_path, "r");
+        if (!t) {
+            fprintf(stderr, "Could not open file %s\n", dump_path);
+            exit(1);
+        }
+        fclose(t);
+    }
+    if (k < 2 || k > RCX_MAX_K) {
+        fprintf(stderr, "The kmer size must be between 2 and %d.\n", RCX_MAX_K);
+        exit(1);
+    }
+    if (threads < 1) threads = 1;
+    if (ngpu < 1) ngpu = 1;
+    if (batch_reads < 2) batch_reads = 2;
+    batch_reads &= ~(size_t)1;
+
+    std::vector<ReadFile> files;
+    std::vector<std::string> mates;
+    for (int i = 1; i < argc; ++i) {  // second pass: read files in argv order (main.cpp:250-268)
+        if (!strcmp("-r", argv[i])) { ReadFile f; f.path = argv[i + 1]; files.push_back(f); ++i; }
+        else if (!strcmp("-p", argv[i])) { ReadFile f; f.path = argv[i + 1]; f.paired = true; files.push_back(f); mates.push_back(argv[i + 2]); i += 2; }
+        else if (!strcmp("-i", argv[i])) { ReadFile f; f.path = argv[i + 1]; f.interleaved = true; files.push_back(f); ++i; }
+        else if (!strcmp("-od", argv[i]) || !strcmp("-c", argv[i]) || !strcmp("-k", argv[i]) || !strcmp("-t", argv[i]) || !strcmp("-maxcor", argv[i]) ||
+                 !strcmp("-maxcorK", argv[i]) || !strcmp("-wk", argv[i]) || !strcmp("-gpus", argv[i]) || !strcmp("-batch", argv[i]))
+            ++i;
+    }
+    if (files.size() > 100 || mates.size() > 100) {  // MAX_READ_FILE, Reads.h:11,110-114
+        fprintf(stderr, "The number of read files exceeds the limit %d.\n", 100);
+        exit(1);
+    }
+    {
+        size_t mi = 0;
+        for (auto& f : files) {
+            f.type = sniff_type(f.path);
+            f.out_path = out_name(od, f.path, f.type);
+            if (f.paired) {
+                f.mate_path = mates[mi++];
+                const int t2 = sniff_type(f.mate_path);
+                f.mate_out_path = out_name(od, f.mate_path, t2);
+            }
+        }
+    }
+    // the reference opens (truncates) every output when the file is added (Reads.h:159-160)
+    std::vector<Writer> out1(files.size()), out2(files.size());
+    for (size_t i = 0; i < files.size(); ++i) {
+        if (!out1[i].open(files[i].out_path, to_stdout) || (files[i].paired && !out2[i].open(files[i].mate_out_path, to_stdout))) {
+            fprintf(stderr, "ERROR: Could not open file %s\n", files[i].out_path.c_str());
+            exit(1);
+        }
+    }
+
+    // ---- GPUs and table
+    std::vector<Gpu> gpus(ngpu);
+    for (int g = 0; g < ngpu; ++g)
+        if (rcx_create(g, &gpus[g].ctx)) die_rcx("rcx_create");
+    Dump dump;
+    load_dump(dump_path, k, dump);
+    {
+        std::vector<std::thread> th;
+        std::vector<int> rc(ngpu, 0);
+        for (int g = 0; g < ngpu; ++g)
+            th.emplace_back([&, g]() { rc[g] = rcx_table_build(gpus[g].ctx, k, dump.codes.data(), dump.counts.data(), dump.codes.size(), 0); });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < ngpu; ++g)
+            if (rc[g]) { fprintf(stderr, "rcx_table_build failed on GPU %d\n", g); exit(1); }
+    }
+    fprintf(stderr, "Stored %d kmers\n", (int)dump.stored);
+
+    // ---- ERROR_RATE (main.cpp:310-358)
+    double error_rate = 0.01;
+    if (rcx_estimate_error_rate(gpus[0].ctx, dump.codes.data(), dump.rate_records, wk, &error_rate)) die_rcx("rcx_estimate_error_rate");
+    fprintf(stderr, "Weak kmer threshold rate: %lf (estimated from %.3lf/1 of the chosen kmers)\n", error_rate, wk);
+    if (getenv("RCX_DEBUG_SCALARS")) fprintf(stderr, "RCX_DEBUG error_rate=%.17g\n", error_rate);
+    { std::vector<uint64_t>().swap(dump.codes); std::vector<int32_t>().swap(dump.counts); }
+
+    // ---- badQualityThreshold (main.cpp:88-128): first 1e6 records of the first Reads object
+    int bad_qual = 0;
+    if (!files.empty() && files[0].type == 1) {
+        int first[300], last[300];
+        memset(first, 0, sizeof first);
+        memset(last, 0, sizeof last);
+        long total = 0;
+        for (size_t fi = 0; fi < files.size() && total < 1000000; ++fi) {
+            LineReader r;
+            if (!r.open(files[fi].path)) continue;
+            const char* p;
+            size_t n;
+            bool nl;
+            const int per = files[fi].type == 1 ? 4 : 2;
+            std::string seq;
+            while (total < 1000000 && r.getline(p, n, nl)) {
+                size_t L = 0;
+                if (r.getline(p, n, nl)) L = n;
+                if (per == 4) {
+                    r.getline(p, n, nl);
+                    if (r.getline(p, n, nl) && L > 0 && n > 0) {
+                        ++last[(unsigned char)(L - 1 < n ? p[L - 1] : 0)];
+                        ++first[(unsigned char)p[0]];
+                    }
+                }
+                ++total;
+            }
+        }
+        int i, cnt = 0, t1, t2;
+        for (i = 0; i < 300; ++i) { cnt += first[i]; if (cnt > total * 0.05) break; }
+        t1 = i - 1;
+        cnt = 0;
+        for (i = 0; i < 300; ++i) { cnt += last[i]; if (cnt > total * 0.05) break; }
+        t2 = i;
+        bad_qual = (int)(char)(t2 < t1 ? t2 : t1);
+    }
+    fprintf(stderr, "Bad quality threshold is '%c'\n", bad_qual);
+
+    rcx_params params;
+    params.k = k;
+    params.max_fix_per_k = max_fix_per_k;
+    params.error_rate = error_rate;
+    params.bad_qual = bad_qual;
+    for (auto& g : gpus)
+        if (rcx_set_params(g.ctx, &params)) die_rcx("rcx_set_params");
+
+    // ---- correction loop (replaces main.cpp:368-523)
+    uint64_t total_reads = 0, total_corrections = 0;
+    HostBatch b;
+    b.alloc(batch_reads, batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u);
+    Chunk c;
+    const int nfmt = std::min(threads, 32);
+    std::vector<std::string> pieces;
+    for (size_t fi = 0; fi < files.size(); ++fi) {
+        const ReadFile& f = files[fi];
+        LineReader r1, r2;
+        if (!r1.open(f.path) || (f.paired && !r2.open(f.mate_path))) {
+            fprintf(stderr, "ERROR: Could not open file %s\n", f.path.c_str());
+            exit(1);
+        }
+        const int mode = (f.paired || f.interleaved) ? RCX_INTERLEAVED : RCX_SINGLE;
+        bool more = true;
+        while (more) {
+            b.n = 0;
+            b.bases = 0;
+            b.off[0] = 0;
+            c.clear();
+            while (b.n + 2 <= b.cap_reads && b.bases + 2 * (RCX_MAX_READ_LENGTH + 1) <= b.cap_bases) {
+                if (!read_record(r1, f.type, b, c, f.path)) { more = false; break; }
+                if (f.paired) {
+                    if (!read_record(r2, f.type, b, c, f.mate_path)) {
+                        fprintf(stderr, "ERROR: The files are not paired!\n");  // main.cpp:463-466
+                        exit(1);
+                    }
+                } else if (f.interleaved) {
+                    if (!read_record(r1, f.type, b, c, f.path)) {
+                        // odd record count in an interleaved file: the reference pairs it with a stale buffer; treat the
+                        // last record as its own mate-less pair by duplicating nothing and correcting it single-end
+                        more = false;
+                        break;
+                    }
+                }
+            }
+            if (f.paired && !more) {
+                const char* p; size_t n; bool nl;
+                if (r2.getline(p, n, nl)) { fprintf(stderr, "ERROR: The files are not paired!\n"); exit(1); }
+            }
+            if (b.n == 0) break;
+            int m = mode;
+            size_t odd_tail = 0;
+            if (m == RCX_INTERLEAVED && (b.n & 1)) odd_tail = 1;
+            if (odd_tail) {
+                // correct the even prefix as pairs, the dangling record single-end
+                HostBatch t = b;
+                t.n = b.n - 1;
+                correct_on_gpus(gpus, RCX_INTERLEAVED, t);
+                HostBatch s = b;
+                s.seq = b.seq + b.off[b.n - 1]; s.qual = b.qual + b.off[b.n - 1];
+                uint32_t so[2] = {0, b.off[b.n] - b.off[b.n - 1]};
+                s.off = so; s.corr = b.corr + b.n - 1; s.l = b.l + b.n - 1; s.m = b.m + b.n - 1; s.h = b.h + b.n - 1; s.n = 1;
+                correct_on_gpus(gpus, RCX_SINGLE, s);
+            } else {
+                correct_on_gpus(gpus, m, b);
+            }
+            for (size_t r = 0; r < b.n; ++r) {  // UpdateSummary, main.cpp:73-79
+                ++total_reads;
+                if (b.corr[r] > 0) total_corrections += (uint64_t)b.corr[r];
+            }
+            // ---- output in input order (main.cpp:485-516); -stdout interleaves the mates of a -p pair
+            auto emit = [&](Writer& w, size_t start, size_t stride) {
+                const size_t recs = (b.n - start + stride - 1) / stride;
+                const int parts = (int)std::min<size_t>((size_t)nfmt, std::max<size_t>(1, recs / 4096));
+                pieces.resize(parts);
+                std::vector<std::thread> th;
+                for (int t = 0; t < parts; ++t) {
+                    const size_t lo = start + stride * (recs * t / parts), hi = start + stride * (recs * (t + 1) / parts);
+                    th.emplace_back([&, t, lo, hi]() { format_records(b, c, f.type, lo, std::min(hi, b.n), stride, pieces[t]); });
+                }
+                for (auto& t : th) t.join();
+                for (int t = 0; t < parts; ++t) w.write(pieces[t].data(), pieces[t].size());
+            };
+            if (f.paired && !to_stdout) {
+                emit(out1[fi], 0, 2);
+                emit(out2[fi], 1, 2);
+            } else {
+                emit(out1[fi], 0, 1);  // single, interleaved, or paired to stdout (mate1, mate2, mate1, ...)
+            }
+        }
+    }
+    for (auto& w : out1) w.close();
+    for (auto& w : out2) w.close();
+    for (auto& g : gpus) rcx_destroy(g.ctx);
+    fprintf(stderr, "Processed %" PRIu64 " reads\n\tCorrected %" PRIu64 " bases.\n", total_reads, total_corrections);
+    return 0;
+}

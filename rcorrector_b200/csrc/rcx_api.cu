@@ -66,6 +66,9 @@ struct rcx_ctx {
     DevBuf<uint32_t> d_off;
     DevBuf<int32_t> d_counts, d_thr, d_corr, d_l, d_m, d_h;
     DevBuf<uint8_t> d_flags;
+    DevBuf<uint32_t> d_worklist;
+    DevBuf<int32_t> d_meta;
+    DevBuf<signed char> d_fixbuf;
     unsigned long long* d_counters = nullptr;
     cudaEvent_t ev[6]{};
     rcx_stats stats{};
@@ -103,7 +106,7 @@ extern "C" void rcx_destroy(rcx_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->buckets) cudaFree(c->buckets);
     c->d_seq.release(); c->d_qual.release(); c->d_off.release(); c->d_counts.release(); c->d_thr.release();
-    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release();
+    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_meta.release(); c->d_fixbuf.release();
     if (c->d_counters) cudaFree(c->d_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -140,19 +143,23 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     if (n >= 0xffffffffull) return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^32-2 records in one table");
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->buckets) { cudaFree(c->buckets); c->buckets = nullptr; }
-    // two slots per bucket, load factor <= 0.5 over slots => nbuckets >= n, rounded up to a power of two
-    unsigned long long nb = 1024;
-    while (nb < n) nb <<= 1;
+    // 5 slots per 64-byte bucket at ~1.33 keys per bucket on average (48 B of HBM per k-mer): fewer than 0.3 % of the
+    // buckets overflow, so nearly every probe -- hit or miss -- is a single 64-byte access
+    unsigned long long nb = (n * 3 + 3) / 4;
+    if (nb < 1024) nb = 1024;
     CUDA_TRY(cudaMalloc(&c->buckets, nb * sizeof(RcxBucket)));
     c->nbuckets = nb;
     c->k = k;
     c->entries = 0;
     CUDA_TRY(rcx_launch_table_init(c->buckets, nb, c->stream));
     unsigned long long* d_new = nullptr;
+    unsigned long long* d_vals = nullptr;  // build-time {tag:count} per slot
     CUDA_TRY(cudaMalloc(&d_new, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(d_new, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaMalloc(&d_vals, nb * RCX_SLOTS * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_vals, 0, nb * RCX_SLOTS * sizeof(unsigned long long), c->stream));
     if (src_on_device) {
-        CUDA_TRY(rcx_launch_table_insert(c->buckets, nb - 1, k, (const unsigned long long*)fwd_codes, counts, n, 0, d_new, c->stream));
+        CUDA_TRY(rcx_launch_table_insert(c->buckets, nb, d_vals, k, (const unsigned long long*)fwd_codes, counts, n, 0, d_new, c->stream));
     } else {
         // stream the records through a bounded device staging area
         const uint64_t chunk = 1ull << 24;
@@ -165,16 +172,18 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
             const uint64_t len = std::min<uint64_t>(chunk, n - s);
             CUDA_TRY(cudaMemcpyAsync(d_codes, fwd_codes + s, len * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaMemcpyAsync(d_cnt, counts + s, len * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(rcx_launch_table_insert(c->buckets, nb - 1, k, d_codes, d_cnt, len, s, d_new, c->stream));
+            CUDA_TRY(rcx_launch_table_insert(c->buckets, nb, d_vals, k, d_codes, d_cnt, len, s, d_new, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
         }
         cudaFree(d_codes);
         cudaFree(d_cnt);
     }
+    CUDA_TRY(rcx_launch_table_finalize(c->buckets, nb, d_vals, c->stream));
     unsigned long long h_new = 0;
     CUDA_TRY(cudaMemcpyAsync(&h_new, d_new, sizeof h_new, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(d_new);
+    cudaFree(d_vals);
     c->entries = h_new;
     return RCX_OK;
 }
@@ -182,7 +191,7 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
 static RcxTable table_of(const rcx_ctx* c) {
     RcxTable t;
     t.buckets = c->buckets;
-    t.bucket_mask = c->nbuckets - 1;
+    t.nbuckets = c->nbuckets;
     t.k = c->k;
     return t;
 }
@@ -213,7 +222,7 @@ extern "C" int rcx_table_lookup(rcx_ctx* c, const uint64_t* fwd_codes, int32_t* 
 extern "C" int rcx_table_info(rcx_ctx* c, uint64_t* entries, uint64_t* slots, uint64_t* bytes) {
     if (!c) return fail(RCX_ERR_ARG, "rcx_table_info: null context");
     if (entries) *entries = c->entries;
-    if (slots) *slots = c->nbuckets * 2;
+    if (slots) *slots = c->nbuckets * RCX_SLOTS;
     if (bytes) *bytes = c->nbuckets * sizeof(RcxBucket);
     return RCX_OK;
 }
@@ -243,6 +252,11 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
     CUDA_TRY(c->d_counts.ensure(total_bases + 1));
     CUDA_TRY(c->d_thr.ensure((size_t)n + 2));
     CUDA_TRY(c->d_flags.ensure((size_t)n + 2));
+    if (correct) {
+        CUDA_TRY(c->d_worklist.ensure((size_t)n + 2));
+        CUDA_TRY(c->d_meta.ensure(3 * (size_t)n + 4));
+        CUDA_TRY(c->d_fixbuf.ensure(total_bases + 64));
+    }
     CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, c->stream));
     RcxScanArgs sa;
     sa.t = table_of(c);
@@ -259,8 +273,9 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
         ca.max_fix_per_k = c->params.max_fix_per_k; ca.error_rate = c->params.error_rate; ca.bad_qual = c->params.bad_qual;
         ca.counts = c->d_counts.p; ca.thr = c->d_thr.p; ca.flags = c->d_flags.p;
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = c->d_counters;
+        ca.worklist = c->d_worklist.p; ca.meta = c->d_meta.p; ca.fixbuf = c->d_fixbuf.p;
         CUDA_TRY(rcx_launch_correct(ca, c->sm_count, c->stream));
-        c->stats.kernel_launches = 2;
+        c->stats.kernel_launches = 4;  // scan + triage + search + finalize
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     c->stats.reads = (uint64_t)n;
@@ -388,6 +403,17 @@ extern "C" int rcx_get_stats(rcx_ctx* c, rcx_stats* out) {
     c->stats.ms_d2h = ms(4, 5);
     c->stats.ms_total = ms(0, 5);
     *out = c->stats;
+    return RCX_OK;
+}
+
+// raw device counters of the last call (debug / profiling builds: search breakdown and per-phase cycles)
+extern "C" int rcx_debug_counters(rcx_ctx* c, uint64_t* out, int n) {
+    if (!c || !out) return fail(RCX_ERR_ARG, "rcx_debug_counters: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    unsigned long long h[RCX_C_COUNT];
+    CUDA_TRY(cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) out[i] = i < RCX_C_COUNT ? h[i] : 0;
     return RCX_OK;
 }
 

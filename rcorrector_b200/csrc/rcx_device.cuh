@@ -18,21 +18,29 @@
 #define RCX_MAX_TRIAL 1025                   // ErrorCorrection.cpp:7
 
 // ----------------------------------------------------------------------------- table
-// Open-addressed, bucketed: one bucket = one 32-byte DRAM sector = two 16-byte
-// slots {u64 canonical key, u32 count, u32 insertion tag}.  Linear probing over
-// buckets; slots fill in order, so the first empty slot terminates a probe.
-struct RcxSlot {
-    unsigned long long key;
-    unsigned int count;
-    unsigned int tag;  // (record index + 1) of the writer: resolves "last writer wins" at build time
+// Open-addressed, bucketed.  One bucket = 64 bytes = one DRAM burst (the L2 fetches two adjacent 32-byte sectors
+// per miss on this part: measured ~64 B of dram__bytes_read per probed 32 B bucket in round 1, profiles/):
+//     u64 key[5] | u32 count[5] | u32 meta          (40 + 20 + 4 bytes)
+// key = canonical code, empty = ~0 (never canonical for k <= 32: revcomp of T..T is 0); slots fill in order.
+// meta bit 0 = "overflow": some key whose HOME bucket this is lives in a later bucket.  A probe therefore ends
+// at its home bucket unless that bit is set (Poisson(1.33) >= 6 keys: < 0.3 % of buckets) -- hits AND misses cost
+// exactly one dependent memory round trip, which is what the latency-bound correction search needs.  Overflowing
+// keys continue linearly; away from home a bucket with a free slot terminates the probe.
+struct __align__(64) RcxBucket {
+    unsigned long long key[5];
+    unsigned int count[5];
+    unsigned int meta;
 };
-struct __align__(32) RcxBucket {
-    RcxSlot s[2];
-};
+#define RCX_SLOTS 5
 struct RcxTable {
     const RcxBucket* buckets;
-    unsigned long long bucket_mask;  // nbuckets - 1 (power of two)
+    unsigned long long nbuckets;
     int k;
+};
+// a bucket held in registers (two 256-bit loads)
+struct RcxBucketRegs {
+    unsigned long long a0, a1, a2, a3;  // key[0..3]
+    unsigned long long b0, b1, b2, b3;  // key[4], count[0..1], count[2..3], count[4] | meta << 32
 };
 
 __device__ __forceinline__ unsigned long long rcx_hash(unsigned long long x) {
@@ -42,6 +50,9 @@ __device__ __forceinline__ unsigned long long rcx_hash(unsigned long long x) {
     x *= 0xD6E8FEB86659FD93ull;
     x ^= x >> 32;
     return x;
+}
+__device__ __forceinline__ unsigned long long rcx_home(const RcxTable& t, unsigned long long canon) {
+    return __umul64hi(rcx_hash(canon), t.nbuckets);  // uniform over [0, nbuckets) without a power-of-two table
 }
 
 // reverse complement of a k-mer code (A0 C1 G2 T3 => complement is 3-x = ~x on 2 bits)
@@ -55,26 +66,39 @@ __device__ __forceinline__ unsigned long long rcx_canonical(unsigned long long c
     return rc < code ? rc : code;
 }
 
-__device__ __forceinline__ void rcx_load_bucket(const RcxBucket* p, unsigned long long& k0, unsigned long long& v0,
-                                                unsigned long long& k1, unsigned long long& v1) {
-    // one 256-bit load = exactly one DRAM sector (LDG.E.256 on sm_100a)
+// issue the two 256-bit loads of one bucket (LDG.E.256 x2 on sm_100a; read-only path, no L1 allocation)
+__device__ __forceinline__ void rcx_issue(const RcxTable& t, unsigned long long b, RcxBucketRegs& d) {
+    const RcxBucket* p = t.buckets + b;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(k0), "=l"(v0), "=l"(k1), "=l"(v1)
+                 : "=l"(d.a0), "=l"(d.a1), "=l"(d.a2), "=l"(d.a3)
+                 : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4+32];"
+                 : "=l"(d.b0), "=l"(d.b1), "=l"(d.b2), "=l"(d.b3)
                  : "l"(p));
 }
-
+// consume a loaded HOME bucket: Store::GetCount for a canonical key (follows the overflow chain if needed)
+__device__ __forceinline__ int rcx_resolve(const RcxTable& t, unsigned long long canon, unsigned long long home, RcxBucketRegs& d) {
+    unsigned long long b = home;
+    bool at_home = true;
+    for (;;) {
+        if (d.a0 == canon) return (int)(unsigned int)d.b1;
+        if (d.a1 == canon) return (int)(unsigned int)(d.b1 >> 32);
+        if (d.a2 == canon) return (int)(unsigned int)d.b2;
+        if (d.a3 == canon) return (int)(unsigned int)(d.b2 >> 32);
+        if (d.b0 == canon) return (int)(unsigned int)d.b3;
+        const bool more = at_home ? ((d.b3 >> 32) & 1ull) != 0 : d.b0 != RCX_EMPTY_KEY;
+        if (!more) return 0;
+        at_home = false;
+        b = b + 1 == t.nbuckets ? 0 : b + 1;
+        rcx_issue(t, b, d);
+    }
+}
 // Store::GetCount for a canonical key.
 __device__ __forceinline__ int rcx_probe(const RcxTable& t, unsigned long long canon) {
-    unsigned long long b = rcx_hash(canon) & t.bucket_mask;
-    for (;;) {
-        unsigned long long k0, v0, k1, v1;
-        rcx_load_bucket(t.buckets + b, k0, v0, k1, v1);
-        if (k0 == canon) return (int)(unsigned int)v0;
-        if (k0 == RCX_EMPTY_KEY) return 0;
-        if (k1 == canon) return (int)(unsigned int)v1;
-        if (k1 == RCX_EMPTY_KEY) return 0;
-        b = (b + 1) & t.bucket_mask;
-    }
+    const unsigned long long home = rcx_home(t, canon);
+    RcxBucketRegs d;
+    rcx_issue(t, home, d);
+    return rcx_resolve(t, canon, home, d);
 }
 
 // ----------------------------------------------------------------------------- KmerCode state machine
@@ -114,6 +138,11 @@ __device__ __forceinline__ int rcx_bound_i(int c, double er) {
     if (c < 0) return (int)0x80000000;
     return __double2int_rz(rcx_bound_d(c, er));
 }
+
+// out-of-line copies for the (large) correction kernel: its hot loops must stay inside the instruction cache
+static __device__ __noinline__ int rcx_bound_i_ool(int c, double er) { return rcx_bound_i(c, er); }
+static __device__ __noinline__ double rcx_bound_d_ool(int c, double er) { return rcx_bound_d(c, er); }
+static __device__ __noinline__ int rcx_probe_ool(const RcxTable& t, unsigned long long canon) { return rcx_probe(t, canon); }
 
 // ----------------------------------------------------------------------------- per-read bit planes
 // A warp turns one read into bit planes in shared memory:

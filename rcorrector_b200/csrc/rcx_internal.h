@@ -11,7 +11,11 @@
 #define RCX_F_REJECT 4    // too short / too many N / A / T (ErrorCorrection.cpp:713,735-755)
 
 // device counters (unsigned long long each)
-enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK, RCX_C_COUNT };
+enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
+       RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
+       RCX_C_ROUNDS, RCX_C_FF, RCX_C_REGULAR,  // search breakdown (only with -DRCX_PHASE_TIMERS)
+       RCX_C_PHASE0,                            // 8 phase cycle counters (only with -DRCX_PHASE_TIMERS)
+       RCX_C_COUNT = RCX_C_PHASE0 + 8 + 5 };  // + jumps, jump cycles, rescue steps, round cycles, round levels
 
 struct RcxScanArgs {
     RcxTable t;
@@ -44,13 +48,18 @@ struct RcxCorrectArgs {
     int32_t* m;
     int32_t* h;
     unsigned long long* counters;
+    // hand-over between the triage / search / finalize kernels
+    uint32_t* worklist;    // [n] indices of reads that need the search
+    int32_t* meta;         // [3 * n] per work item: status (-2 = post-filters), totalFix, badSegmentCnt
+    signed char* fixbuf;   // [off[n]] fix[] of reads that reach the post-filters
 };
 
 // table (rcx_table.cu)
 cudaError_t rcx_launch_table_init(RcxBucket* buckets, unsigned long long nbuckets, cudaStream_t s);
-cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long bucket_mask, int k, const unsigned long long* codes,
-                                    const int32_t* counts, unsigned long long n, unsigned long long first_index,
-                                    unsigned long long* new_keys, cudaStream_t s);
+cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long nbuckets, unsigned long long* vals, int k,
+                                    const unsigned long long* codes, const int32_t* counts, unsigned long long n,
+                                    unsigned long long first_index, unsigned long long* new_keys, cudaStream_t s);
+cudaError_t rcx_launch_table_finalize(RcxBucket* buckets, unsigned long long nbuckets, const unsigned long long* vals, cudaStream_t s);
 cudaError_t rcx_launch_table_lookup(RcxTable t, const unsigned long long* codes, int32_t* out, unsigned long long n,
                                     cudaStream_t s);
 // scan (rcx_scan.cu)

@@ -10,13 +10,12 @@
 //
 // Data flow per warp: coalesced byte loads of the read -> bit planes in shared
 // memory (rcx_build_planes) -> every lane funnel-shifts its own k-windows out
-// of the packed plane, canonicalises and issues up to 4 independent 32-byte
-// bucket loads before consuming any (a 150 bp read = 128 windows = 4 sectors
-// in flight per lane) -> counts to shared + HBM -> warp bitonic sort.
+// of the packed plane, canonicalises and issues SCAN_ILP independent 64-byte
+// bucket loads before consuming any -> counts to shared + HBM -> warp bitonic sort.
 #include "rcx_internal.h"
 
 #define SCAN_WARPS 8
-#define SCAN_ILP 4
+#define SCAN_ILP 2
 
 size_t rcx_scan_smem_per_warp(int max_len, int k) {
     int kcnt = max_len - k + 1;
@@ -57,7 +56,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a
 
         // ---- probes: SCAN_ILP windows per lane in flight
         for (int j0 = 0; j0 < kcnt; j0 += 32 * SCAN_ILP) {
-            unsigned long long canon[SCAN_ILP], bkt[SCAN_ILP], k0[SCAN_ILP], v0[SCAN_ILP], k1[SCAN_ILP], v1[SCAN_ILP];
+            unsigned long long canon[SCAN_ILP], home[SCAN_ILP];
+            RcxBucketRegs d[SCAN_ILP];
             bool live[SCAN_ILP];
 #pragma unroll
             for (int u = 0; u < SCAN_ILP; ++u) {
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a
                 live[u] = j < kcnt && (rcx_bits(P.inv, j < kcnt ? j : 0) & kmask32) == 0;
                 if (live[u]) {
                     canon[u] = rcx_canonical(rcx_window(P.pk, j, k), k);
-                    bkt[u] = rcx_hash(canon[u]) & a.t.bucket_mask;
-                    rcx_load_bucket(a.t.buckets + bkt[u], k0[u], v0[u], k1[u], v1[u]);
+                    home[u] = rcx_home(a.t, canon[u]);
+                    rcx_issue(a.t, home[u], d[u]);
                 }
             }
 #pragma unroll
@@ -75,14 +75,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a
                 int c = 0;
                 if (live[u]) {
                     ++probes;
-                    for (;;) {
-                        if (k0[u] == canon[u]) { c = (int)(unsigned int)v0[u]; break; }
-                        if (k0[u] == RCX_EMPTY_KEY) break;
-                        if (k1[u] == canon[u]) { c = (int)(unsigned int)v1[u]; break; }
-                        if (k1[u] == RCX_EMPTY_KEY) break;
-                        bkt[u] = (bkt[u] + 1) & a.t.bucket_mask;
-                        rcx_load_bucket(a.t.buckets + bkt[u], k0[u], v0[u], k1[u], v1[u]);
-                    }
+                    c = rcx_resolve(a.t, canon[u], home[u], d[u]);
                 }
                 if (j < kcnt) {
                     a.counts[o + j] = c;

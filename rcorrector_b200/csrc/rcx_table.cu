@@ -2,45 +2,69 @@
 //
 // Replaces Store::Put / Store::GetCount (Store.h:51-66) and the load loop of
 // main.cpp:295-307: canonicalise, skip count <= 1, last record of a duplicate
-// canonical key wins (resolved with a 64-bit atomicMax on {tag:count}, tag =
-// record index + 1, so the result is independent of thread scheduling).
+// canonical key wins.  "Last" is resolved with a 64-bit atomicMax on
+// {record index + 1 : count} in a build-time side array (one u64 per slot),
+// so the result does not depend on thread scheduling; a finalize pass then
+// writes the winning counts into the buckets and the side array is freed.
 #include "rcx_internal.h"
 
-__global__ void __launch_bounds__(256) rcx_table_init_kernel(uint4* p, unsigned long long nslots) {
+__global__ void __launch_bounds__(256) rcx_table_init_kernel(uint4* p, unsigned long long nbuckets) {
+    // bucket = 4 x 16 bytes: keys (40 B) all ones, counts + meta (24 B) zero
+    const unsigned long long n = nbuckets * 4;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += stride)
-        p[i] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);  // key = EMPTY, count = 0, tag = 0
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned int q = (unsigned int)(i & 3);
+        uint4 v;
+        if (q < 2) v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        else if (q == 2) v = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+        else v = make_uint4(0u, 0u, 0u, 0u);
+        p[i] = v;
+    }
 }
 
 __global__ void __launch_bounds__(256)
-rcx_table_insert_kernel(RcxBucket* buckets, unsigned long long bucket_mask, int k, const unsigned long long* __restrict__ codes,
-                        const int32_t* __restrict__ counts, unsigned long long n, unsigned long long first_index,
-                        unsigned long long* new_keys) {
+rcx_table_insert_kernel(RcxBucket* buckets, unsigned long long nbuckets, unsigned long long* vals, int k,
+                        const unsigned long long* __restrict__ codes, const int32_t* __restrict__ counts, unsigned long long n,
+                        unsigned long long first_index, unsigned long long* new_keys) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    RcxTable t;
+    t.buckets = buckets; t.nbuckets = nbuckets; t.k = k;
     unsigned long long fresh = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = counts[i];
         if (c <= 1) continue;  // main.cpp:299
         const unsigned long long key = rcx_canonical(codes[i] & kmask, k);
-        unsigned long long b = rcx_hash(key) & bucket_mask;
-        RcxSlot* slot = nullptr;
-        while (!slot) {
-            for (int s = 0; s < 2 && !slot; ++s) {
-                RcxSlot* cand = &buckets[b].s[s];
-                unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&cand->key);
+        const unsigned long long home = rcx_home(t, key);
+        unsigned long long b = home;
+        long long slot = -1;
+        while (slot < 0) {
+            for (int s = 0; s < RCX_SLOTS && slot < 0; ++s) {
+                unsigned long long* kp = &buckets[b].key[s];
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
                 if (cur == RCX_EMPTY_KEY) {
-                    cur = atomicCAS(&cand->key, RCX_EMPTY_KEY, key);
+                    cur = atomicCAS(kp, RCX_EMPTY_KEY, key);
                     if (cur == RCX_EMPTY_KEY) { ++fresh; cur = key; }
                 }
-                if (cur == key) slot = cand;
+                if (cur == key) slot = (long long)(b * RCX_SLOTS + s);
             }
-            b = (b + 1) & bucket_mask;
+            if (slot < 0) {
+                if (b == home) atomicOr(&buckets[home].meta, 1u);  // the key lives past its home bucket
+                b = b + 1 == nbuckets ? 0 : b + 1;
+            }
         }
         const unsigned long long packed = ((first_index + i + 1) << 32) | (unsigned int)c;
-        atomicMax(reinterpret_cast<unsigned long long*>(&slot->count), packed);
+        atomicMax(&vals[slot], packed);
     }
     if (fresh) atomicAdd(new_keys, fresh);
+}
+
+__global__ void __launch_bounds__(256)
+rcx_table_finalize_kernel(RcxBucket* buckets, unsigned long long nbuckets, const unsigned long long* __restrict__ vals) {
+    const unsigned long long n = nbuckets * RCX_SLOTS;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        buckets[i / RCX_SLOTS].count[i % RCX_SLOTS] = (unsigned int)vals[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -59,17 +83,21 @@ static inline int grid_for(unsigned long long n, int block, int cap) {
 }
 
 cudaError_t rcx_launch_table_init(RcxBucket* buckets, unsigned long long nbuckets, cudaStream_t s) {
-    const unsigned long long nslots = nbuckets * 2;
-    rcx_table_init_kernel<<<grid_for(nslots, 256, 148 * 16), 256, 0, s>>>(reinterpret_cast<uint4*>(buckets), nslots);
+    rcx_table_init_kernel<<<grid_for(nbuckets * 4, 256, 148 * 16), 256, 0, s>>>(reinterpret_cast<uint4*>(buckets), nbuckets);
     return cudaGetLastError();
 }
 
-cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long bucket_mask, int k, const unsigned long long* codes,
-                                    const int32_t* counts, unsigned long long n, unsigned long long first_index,
-                                    unsigned long long* new_keys, cudaStream_t s) {
+cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long nbuckets, unsigned long long* vals, int k,
+                                    const unsigned long long* codes, const int32_t* counts, unsigned long long n,
+                                    unsigned long long first_index, unsigned long long* new_keys, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    rcx_table_insert_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, s>>>(buckets, bucket_mask, k, codes, counts, n, first_index,
+    rcx_table_insert_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, s>>>(buckets, nbuckets, vals, k, codes, counts, n, first_index,
                                                                       new_keys);
+    return cudaGetLastError();
+}
+
+cudaError_t rcx_launch_table_finalize(RcxBucket* buckets, unsigned long long nbuckets, const unsigned long long* vals, cudaStream_t s) {
+    rcx_table_finalize_kernel<<<grid_for(nbuckets * RCX_SLOTS, 256, 148 * 16), 256, 0, s>>>(buckets, nbuckets, vals);
     return cudaGetLastError();
 }
 
