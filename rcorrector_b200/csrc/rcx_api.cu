@@ -66,8 +66,8 @@ struct rcx_ctx {
     DevBuf<uint32_t> d_off;
     DevBuf<int32_t> d_counts, d_thr, d_corr, d_l, d_m, d_h;
     DevBuf<uint8_t> d_flags;
-    DevBuf<uint32_t> d_worklist;
-    DevBuf<int32_t> d_meta;
+    DevBuf<uint32_t> d_worklist, d_worklist2;
+    DevBuf<int32_t> d_state;
     DevBuf<signed char> d_fixbuf;
     unsigned long long* d_counters = nullptr;
     cudaEvent_t ev[6]{};
@@ -106,7 +106,7 @@ extern "C" void rcx_destroy(rcx_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->buckets) cudaFree(c->buckets);
     c->d_seq.release(); c->d_qual.release(); c->d_off.release(); c->d_counts.release(); c->d_thr.release();
-    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_meta.release(); c->d_fixbuf.release();
+    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_worklist2.release(); c->d_state.release(); c->d_fixbuf.release();
     if (c->d_counters) cudaFree(c->d_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -254,7 +254,8 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
     CUDA_TRY(c->d_flags.ensure((size_t)n + 2));
     if (correct) {
         CUDA_TRY(c->d_worklist.ensure((size_t)n + 2));
-        CUDA_TRY(c->d_meta.ensure(3 * (size_t)n + 4));
+        CUDA_TRY(c->d_worklist2.ensure((size_t)n + 2));
+        CUDA_TRY(c->d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
         CUDA_TRY(c->d_fixbuf.ensure(total_bases + 64));
     }
     CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, c->stream));
@@ -273,9 +274,9 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
         ca.max_fix_per_k = c->params.max_fix_per_k; ca.error_rate = c->params.error_rate; ca.bad_qual = c->params.bad_qual;
         ca.counts = c->d_counts.p; ca.thr = c->d_thr.p; ca.flags = c->d_flags.p;
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = c->d_counters;
-        ca.worklist = c->d_worklist.p; ca.meta = c->d_meta.p; ca.fixbuf = c->d_fixbuf.p;
+        ca.worklist = c->d_worklist.p; ca.worklist2 = c->d_worklist2.p; ca.state = c->d_state.p; ca.fixbuf = c->d_fixbuf.p; ca.pass = 0;
         CUDA_TRY(rcx_launch_correct(ca, c->sm_count, c->stream));
-        c->stats.kernel_launches = 4;  // scan + triage + search + finalize
+        c->stats.kernel_launches = 7;  // scan, triage, 2 x (prep, search), finalize
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     c->stats.reads = (uint64_t)n;

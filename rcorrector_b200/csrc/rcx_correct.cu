@@ -744,6 +744,152 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_triage_kernel(RcxCorrectAr
     }
 }
 
+// per-work-item state in HBM (int32 words): header, isStrongTrusted plane, strict poly-A plane, segment list
+#define ST_STATUS 0      // -2 = go to the post-filters, -1 / 0 = final result, -3 = second pass of A.4 requested
+#define ST_TOTALFIX 1
+#define ST_BADSEG 2
+#define ST_STRONG 3
+#define ST_TRUST 4
+#define ST_NSEG 5
+#define ST_HDR 8
+__host__ __device__ inline int state_stride(int max_len, int k) { return ST_HDR + 2 * rcx_mask_words(max_len) + 2 * (max_len / k + 4); }
+
+// work-item fetch shared by the persistent kernels: pass 0 walks the triage work list, pass 1 the (short) list of
+// items whose first pass asked for a second one (forceNextRound, ErrorCorrection.cpp:1195-1211; at most two passes
+// can happen because forceNextRound needs iter == 0 and `unfixable` is never set)
+__device__ __forceinline__ bool fetch_item(const RcxCorrectArgs& a, int counter, int lane, long long& item) {
+    const long long n = (long long)a.counters[a.pass == 0 ? RCX_C_NWORK : RCX_C_NWORK2];
+    long long w = 0;
+    if (lane == 0) w = (long long)atomicAdd(&a.counters[counter], 1ull);
+    w = __shfl_sync(RCX_FULL, w, 0);
+    if (w >= n) return false;
+    item = a.pass == 0 ? w : (long long)a.worklist2[w];
+    return true;
+}
+
+// A.4 steps 1-4 (:863-1046): trusted k-mers -> islands -> trusted positions -> segments, written to the item state.
+__global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs a) {
+    extern __shared__ unsigned int smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = a.t.k;
+    const CorLayout L = cor_layout(a.max_len, k);
+    const int mw = L.mw;
+    WarpMem M;
+    setup_warpmem(M, smem, warp, L);
+    const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
+    const int stride = state_stride(a.max_len, k);
+    for (;;) {
+        long long item;
+        if (!fetch_item(a, a.pass == 0 ? RCX_C_WORKX0 : RCX_C_WORKX2, lane, item)) break;
+        const long long r = a.worklist[item];
+        int* st = a.state + item * stride;
+        const uint32_t o = a.off[r];
+        const int len = (int)(a.off[r + 1] - o);
+        const int kcnt = len - k + 1;
+        int nN, nA, nT;
+        build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
+        #pragma unroll 1
+        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
+        int strong, trust;
+        if (a.pass == 0) initial_thresholds(a, r, a.flags[r], a.error_rate, strong, trust);
+        else { strong = st[ST_STRONG]; trust = st[ST_TRUST]; }
+        #pragma unroll 1
+        for (int c = lane; c < mw; c += 32) { M.pstrict[c] = 0; M.strong[c] = 0; M.trusted[c] = 0; }
+        __syncwarp();
+        #pragma unroll 1
+        for (int c = 0; (c << 5) < kcnt; ++c) {
+            const int j = (c << 5) + lane;
+            const bool pa = j < kcnt && rcx_polya(M.P, j, k, kmask32, 2);
+            const unsigned int bp = __ballot_sync(RCX_FULL, pa);
+            const unsigned int bt = __ballot_sync(RCX_FULL, j < kcnt && M.counts[j] >= strong && !pa);  // :875
+            if (lane == 0) { M.pstrict[c] = bp; M.trusted[c] = bt; }
+        }
+        __syncwarp();
+        int status = -2, nseg = 0;
+        if (next_bit(M.trusted, 0, kcnt, false, lane) >= kcnt) {
+            status = 0;  // longestTrustedLength == kcnt (:1110)
+        } else {
+            // runs of trusted k-mers -> longest run, islands (runs >= 2), boundary adjustment, trusted positions
+            int longest = 0, tstart = 0, tend = -1;
+            {
+                int pf = 0, pt = -1;
+                bool have = false;
+                int p = 0;
+                #pragma unroll 1
+                while (p < kcnt) {
+                    const int s = next_bit(M.trusted, p, kcnt, true, lane);
+                    if (s >= kcnt) break;
+                    const int e = next_bit(M.trusted, s, kcnt, false, lane);
+                    const int rl = e - s;
+                    if (rl > longest) { longest = rl; tstart = s; tend = e - 1; }
+                    if (rl >= 2) {
+                        int cf = s, ct = e - 1;
+                        if (have) {
+                            if (cf <= pt + k) {  // :936-964
+                                const int len1 = pt - pf, len2 = ct - cf, overlap = pt + k - cf;
+                                const int j = pt + 1 + lane;
+                                const bool low = j < cf && M.counts[j] <= 2 && M.counts[j] < trust;
+                                if (__any_sync(RCX_FULL, low) && overlap <= 3) {
+                                    if (len1 < len2) pt -= overlap + 1; else cf += overlap + 1;
+                                }
+                            }
+                            if (pf <= pt) set_range(M.strong, pf, pt + k - 1, mw, lane);
+                            __syncwarp();
+                        }
+                        pf = cf; pt = ct; have = true;
+                    }
+                    p = e;
+                }
+                if (have && pf <= pt) set_range(M.strong, pf, pt + k - 1, mw, lane);
+                __syncwarp();
+            }
+            // islands that define the segments (:977-1007)
+            #pragma unroll 1
+            for (int c = lane; c < mw; c += 32) M.island[c] = M.strong[c];
+            __syncwarp();
+            if (next_bit(M.strong, 0, len, true, lane) >= len) {
+                set_range(M.island, tstart, tend + k - 1, mw, lane);
+                __syncwarp();
+            }
+            // segments (:1009-1046): prefix, gaps between islands, suffix; packed (from | to << 16), (lanchor | ranchor << 16)
+            int* segs = st + ST_HDR + 2 * mw;
+            int ifrom = next_bit(M.island, 0, len, true, lane);
+            int ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
+            int prev_to = -1, prev_len = 0;
+            bool first = true;
+            for (;;) {
+                int sf, sto, la, ra;
+                bool is_seg;
+                if (ifrom < len) {
+                    sf = prev_to + 1; sto = ifrom - 1;
+                    la = first ? 0 : prev_len; ra = ito - ifrom + 1;
+                    is_seg = first ? ifrom > 0 : true;
+                } else {
+                    sf = prev_to + 1; sto = len; la = prev_len; ra = 0;
+                    is_seg = prev_to < len - 1;
+                }
+                if (is_seg) {
+                    if (lane == 0 && nseg < L.nseg) { segs[2 * nseg] = sf | (sto << 16); segs[2 * nseg + 1] = la | (ra << 16); }
+                    ++nseg;
+                }
+                if (ifrom >= len) break;
+                prev_to = ito; prev_len = ito - ifrom + 1; first = false;
+                ifrom = next_bit(M.island, ito + 1, len, true, lane);
+                ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
+            }
+        }
+        #pragma unroll 1
+        for (int c = lane; c < mw; c += 32) { st[ST_HDR + c] = (int)M.strong[c]; st[ST_HDR + mw + c] = (int)M.pstrict[c]; }
+        if (lane == 0) {
+            st[ST_STATUS] = status; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
+            st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < L.nseg ? nseg : L.nseg;
+        }
+        __syncwarp();
+    }
+}
+
+// A.4 steps 6-9 (:1113-1289): the ordered searches over the segments of one read, then the ambiguity / forceNextRound
+// decisions and, when a second pass is due, the re-threshold.
 __global__ void __launch_bounds__(COR_WARPS * 32, 4) rcx_search_kernel(RcxCorrectArgs a) {
     extern __shared__ unsigned int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -754,7 +900,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32, 4) rcx_search_kernel(RcxCorrec
     WarpMem M;
     setup_warpmem(M, smem, warp, L);
     const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
-    const int loose = (k / 2 > 7) ? k / 2 : 7;
+    const int stride = state_stride(a.max_len, k);
     unsigned long long n_nodes = 0, n_sprobes = 0;
     unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #ifdef RCX_PHASE_TIMERS
@@ -762,207 +908,120 @@ __global__ void __launch_bounds__(COR_WARPS * 32, 4) rcx_search_kernel(RcxCorrec
     long long ph_last = clock64();
     int ph_cur = 0;
 #endif
-    const long long nwork = (long long)a.counters[RCX_C_NWORK];
-
     for (;;) {
         PH(0);  // work fetch
-        long long w = 0;
-        if (lane == 0) w = (long long)atomicAdd(&a.counters[RCX_C_WORK], 1ull);
-        w = __shfl_sync(RCX_FULL, w, 0);
-        if (w >= nwork) break;
-        const long long r = a.worklist[w];
+        long long item;
+        if (!fetch_item(a, a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3, lane, item)) break;
+        int* st = a.state + item * stride;
+        if (st[ST_STATUS] != -2) continue;  // decided by the prep kernel (all k-mers trusted on the second pass)
+        const long long r = a.worklist[item];
         const uint32_t o = a.off[r];
         const int len = (int)(a.off[r + 1] - o);
         const int kcnt = len - k + 1;
-        int result;
-        int nN = 0, nA = 0, nT = 0;
-        PH(1);  // planes + input loads
+        PH(1);  // planes + state loads
+        int nN, nA, nT;
         build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
         #pragma unroll 1
-        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
-        const uint8_t fl = a.flags[r];
+        for (int c = lane; c < mw; c += 32) { M.strong[c] = (unsigned int)st[ST_HDR + c]; M.pstrict[c] = (unsigned int)st[ST_HDR + mw + c]; }
+        #pragma unroll 1
+        for (int i = lane; i < len; i += 32) { M.fix[i] = -1; M.path[i] = -1; }  // :868-869, :1113-1114
+        const int strong = st[ST_STRONG], trust = st[ST_TRUST], nseg = st[ST_NSEG];
+        const int* segs = st + ST_HDR + 2 * mw;
         __syncwarp();
-        int total_fix = 0, bad_segments = 0;
-        {
-            PH(2);  // thresholds, masks, islands
-            int strong, trust;
-            initial_thresholds(a, r, fl, er, strong, trust);
-            #pragma unroll 1
-            for (int c = lane; c < mw; c += 32) M.pstrict[c] = 0;
-            __syncwarp();
-            #pragma unroll 1
-            for (int c = 0; (c << 5) < kcnt; ++c) {
-                const int j = (c << 5) + lane;
-                const unsigned int b = __ballot_sync(RCX_FULL, j < kcnt && rcx_polya(M.P, j, k, kmask32, 2));
-                if (lane == 0) M.pstrict[c] = b;
+        PH(3);  // searches
+        int result = -2, total_fix = 0, bad_segments = 0, best_bn = RCX_INF;
+        bool abort_read = false;
+        #pragma unroll 1
+        for (int g = 0; g < nseg && !abort_read; ++g) {  // :1125-1175
+            const int w0 = segs[2 * g], w1 = segs[2 * g + 1];
+            const int sf = w0 & 0xffff, sto = w0 >> 16, la = w1 & 0xffff, ra = w1 >> 16;
+            SearchState S;
+            S.trial = 0;
+            S.max_fix = (sto - sf + 1) * K / k * 2 + 1;
+            if (S.max_fix < K) S.max_fix = K;
+            S.best_bn = -1; S.best_cnt = -1; S.top2a = -1; S.top2b = -1;
+            {
+                const bool right = la >= ra;  // :1136
+                const int extend = right ? (sto == len ? 0 : k - 1) : (sf == 0 ? 0 : k - 1);
+                const RcxKmer kc = seed_kmer(M.P, right ? sf - k : sto + 1, k, kmask32);
+                search_segment(a.t, M, S, right, right ? sf : sto, right ? sto + extend : sf - extend, trust, kc, len, er, lane,
+                               n_nodes, n_sprobes, dbg);
             }
-            __syncwarp();
-            int iter = 0;
-            result = -2;  // -2 = fall through to the post-filters
-            for (;;) {    // ---------------- A.4 (:853-1291)
-                bool unfixable = false, force_next = false;
-                total_fix = 0;
-                // trusted k-mers of this pass (:875)
-                #pragma unroll 1
-                for (int c = lane; c < mw; c += 32) { M.strong[c] = 0; M.trusted[c] = 0; }
-                __syncwarp();
-                #pragma unroll 1
-                for (int c = 0; (c << 5) < kcnt; ++c) {
-                    const int j = (c << 5) + lane;
-                    const unsigned int b = __ballot_sync(RCX_FULL, j < kcnt && M.counts[j] >= strong && !getbit(M.pstrict, j));
-                    if (lane == 0) M.trusted[c] = b;
-                }
-                __syncwarp();
-                if (next_bit(M.trusted, 0, kcnt, false, lane) >= kcnt) { result = 0; break; }  // longest == kcnt, :1110
-                // runs of trusted k-mers -> longest run, islands (runs >= 2), boundary adjustment, trusted positions
-                int longest = 0, tstart = 0, tend = -1;
-                {
-                    int pf = 0, pt = -1;
-                    bool have = false;
-                    int p = 0;
-                    #pragma unroll 1
-                    while (p < kcnt) {
-                        const int s = next_bit(M.trusted, p, kcnt, true, lane);
-                        if (s >= kcnt) break;
-                        const int e = next_bit(M.trusted, s, kcnt, false, lane);
-                        const int rl = e - s;
-                        if (rl > longest) { longest = rl; tstart = s; tend = e - 1; }
-                        if (rl >= 2) {
-                            int cf = s, ct = e - 1;
-                            if (have) {
-                                if (cf <= pt + k) {  // :936-964
-                                    const int len1 = pt - pf, len2 = ct - cf, overlap = pt + k - cf;
-                                    const int j = pt + 1 + lane;
-                                    const bool low = j < cf && M.counts[j] <= 2 && M.counts[j] < trust;
-                                    if (__any_sync(RCX_FULL, low) && overlap <= 3) {
-                                        if (len1 < len2) pt -= overlap + 1; else cf += overlap + 1;
-                                    }
-                                }
-                                if (pf <= pt) set_range(M.strong, pf, pt + k - 1, mw, lane);
-                                __syncwarp();
-                            }
-                            pf = cf; pt = ct; have = true;
-                        }
-                        p = e;
-                    }
-                    if (have && pf <= pt) set_range(M.strong, pf, pt + k - 1, mw, lane);
-                    __syncwarp();
-                }
-                // islands that define the segments (:977-1007)
-                #pragma unroll 1
-                for (int c = lane; c < mw; c += 32) M.island[c] = M.strong[c];
-                __syncwarp();
-                if (next_bit(M.strong, 0, len, true, lane) >= len) {
-                    set_range(M.island, tstart, tend + k - 1, mw, lane);
-                    __syncwarp();
-                }
-                if (longest == kcnt) { result = 0; break; }  // :1110
-                #pragma unroll 1
-                for (int i = lane; i < len; i += 32) { M.fix[i] = -1; M.path[i] = -1; }
-                __syncwarp();
-                // ---------------- segments and searches (:1009-1046, :1118-1175)
-                bad_segments = 0;
-                int best_bn = RCX_INF, nseg = 0;
-                bool abort_read = false;
-                {
-                    int ifrom = next_bit(M.island, 0, len, true, lane);   // first island
-                    int ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
-                    int prev_to = -1, prev_len = 0;
-                    bool first = true;
-                    #pragma unroll 1
-                    while (!abort_read) {
-                        // segment before island [ifrom, ito] (or the suffix segment when ifrom >= len)
-                        int sf, st, la, ra;
-                        bool is_seg;
-                        if (ifrom < len) {
-                            sf = prev_to + 1; st = ifrom - 1;
-                            la = first ? 0 : prev_len; ra = ito - ifrom + 1;
-                            is_seg = first ? ifrom > 0 : true;
-                        } else {
-                            sf = prev_to + 1; st = len; la = prev_len; ra = 0;
-                            is_seg = prev_to < len - 1;
-                        }
-                        if (is_seg) {
-                            SearchState S;
-                            S.trial = 0;
-                            S.max_fix = (st - sf + 1) * K / k * 2 + 1;
-                            if (S.max_fix < K) S.max_fix = K;
-                            S.best_bn = -1; S.best_cnt = -1; S.top2a = -1; S.top2b = -1;
-                            {
-                                const bool right = la >= ra;  // :1136
-                                const int extend = right ? (st == len ? 0 : k - 1) : (sf == 0 ? 0 : k - 1);
-                                const RcxKmer kc = seed_kmer(M.P, right ? sf - k : st + 1, k, kmask32);
-                                search_segment(a.t, M, S, right, right ? sf : st, right ? st + extend : sf - extend, trust, kc, len, er,
-                                               lane, n_nodes, n_sprobes, dbg);
-                            }
-                            if (lane == 0 && nseg < L.nseg) M.segtop[nseg] = S.top2b;
-                            ++nseg;
-                            if (S.best_bn == -1) {
-                                ++bad_segments;
-                            } else {
-                                if (S.best_bn < best_bn) best_bn = S.best_bn;
-                                if (S.trial > RCX_MAX_TRIAL) abort_read = true;  // :1172
-                                else total_fix += S.max_fix;
-                            }
-                        }
-                        if (ifrom >= len) break;
-                        prev_to = ito; prev_len = ito - ifrom + 1; first = false;
-                        ifrom = next_bit(M.island, ito + 1, len, true, lane);
-                        ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
-                    }
-                }
-                if (abort_read) { result = -1; break; }
-                __syncwarp();
-                if (nseg > 0) {  // :1176-1230
-                    int best_fix_cnt = 1;
-                    #pragma unroll 1
-                    for (int g = 0; g < nseg && g < L.nseg; ++g)
-                        if (M.segtop[g] >= best_bn) best_fix_cnt *= 2;
-                    if (iter == 0 && (double)best_bn < rcx_bound_d_ool(strong, er)) force_next = true;  // :1195 FP64 compare
-                    if (best_fix_cnt >= 2) { result = -1; break; }
-                }
-                if (total_fix == 0 && force_next) { result = 0; break; }  // :1231
-                if (total_fix > len) unfixable = true;
-                if (!unfixable && !force_next) break;
-                if (trust < 10 && !force_next) { result = -1; break; }
-                // ---------------- re-threshold (:1247-1289)
-                const int n2 = rcx_pow2_at_least(kcnt);
-                #pragma unroll 1
-                for (int j = lane; j < n2; j += 32)
-                    M.sbuf[j] = j < kcnt ? (rcx_polya(M.P, j, k, kmask32, loose) ? -1 : M.counts[j]) : 0x7fffffff;
-                __syncwarp();
-                warp_sort_ool(M.sbuf, n2, lane);
-                int ibreak = 0;
-                bool any_drop = false;
-                #pragma unroll 1
-                for (int i = 1 + lane; i < kcnt; i += 32) {
-                    const int v = M.sbuf[i], pv = M.sbuf[i - 1];
-                    if (v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5)) && v < strong) ibreak = i;
-                }
-                ibreak = __reduce_max_sync(RCX_FULL, ibreak);
-                #pragma unroll 1
-                for (int i = 1 + lane; i < kcnt; i += 32) {
-                    const int v = M.sbuf[i], pv = M.sbuf[i - 1];
-                    if (i >= ibreak && v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5))) any_drop = true;
-                }
-                any_drop = __any_sync(RCX_FULL, any_drop);
-                if (!any_drop) break;
-                ++iter;
-                const int nv = M.sbuf[ibreak];
-                trust = rcx_bound_i_ool(nv, er);
-                strong = nv;
-                __syncwarp();
+            if (lane == 0) M.segtop[g] = S.top2b;
+            if (S.best_bn == -1) {
+                ++bad_segments;
+            } else {
+                if (S.best_bn < best_bn) best_bn = S.best_bn;
+                if (S.trial > RCX_MAX_TRIAL) abort_read = true;  // :1172
+                else total_fix += S.max_fix;
             }
         }
-        PH(5);  // hand-over to the finalize kernel
-        if (result == -2) {
-            #pragma unroll 1
-            for (int i = lane; i < len; i += 32) a.fixbuf[o + i] = M.fix[i];
+        __syncwarp();
+        PH(4);  // decisions, re-threshold
+        bool second_pass = false;
+        int new_strong = strong, new_trust = trust;
+        if (abort_read) {
+            result = -1;
+        } else {
+            bool force_next = false;
+            if (nseg > 0) {  // :1176-1230
+                int best_fix_cnt = 1;
+                #pragma unroll 1
+                for (int g = 0; g < nseg; ++g)
+                    if (M.segtop[g] >= best_bn) best_fix_cnt *= 2;
+                if (a.pass == 0 && (double)best_bn < rcx_bound_d_ool(strong, er)) force_next = true;  // :1195 FP64 compare
+                if (best_fix_cnt >= 2) result = -1;
+            }
+            if (result == -2) {
+                const bool unfixable = total_fix > len;  // :1234 (never true in practice)
+                if (total_fix == 0 && force_next) result = 0;  // :1231
+                else if (!unfixable && !force_next) { /* leave the loop: post-filters */ }
+                else if (trust < 10 && !force_next) result = -1;
+                else {
+                    // ---------------- re-threshold (:1247-1289)
+                    const int loose = (k / 2 > 7) ? k / 2 : 7;
+                    const int n2 = rcx_pow2_at_least(kcnt);
+                    #pragma unroll 1
+                    for (int j = lane; j < n2; j += 32)
+                        M.sbuf[j] = j < kcnt ? (rcx_polya(M.P, j, k, kmask32, loose) ? -1 : a.counts[o + j]) : 0x7fffffff;
+                    __syncwarp();
+                    warp_sort_ool(M.sbuf, n2, lane);
+                    int ibreak = 0;
+                    bool any_drop = false;
+                    #pragma unroll 1
+                    for (int i = 1 + lane; i < kcnt; i += 32) {
+                        const int v = M.sbuf[i], pv = M.sbuf[i - 1];
+                        if (v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5)) && v < strong) ibreak = i;
+                    }
+                    ibreak = __reduce_max_sync(RCX_FULL, ibreak);
+                    #pragma unroll 1
+                    for (int i = 1 + lane; i < kcnt; i += 32) {
+                        const int v = M.sbuf[i], pv = M.sbuf[i - 1];
+                        if (i >= ibreak && v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5))) any_drop = true;
+                    }
+                    any_drop = __any_sync(RCX_FULL, any_drop);
+                    if (any_drop) {
+                        const int nv = M.sbuf[ibreak];
+                        new_trust = rcx_bound_i_ool(nv, er);
+                        new_strong = nv;
+                        second_pass = a.pass == 0;  // a second pass never asks for a third (forceNextRound needs iter == 0)
+                    }
+                    __syncwarp();
+                }
+            }
         }
-        if (lane == 0) {
-            a.meta[3 * w] = result;
-            a.meta[3 * w + 1] = total_fix;
-            a.meta[3 * w + 2] = bad_segments;
+        PH(5);  // hand-over
+        if (second_pass) {
+            if (lane == 0) {
+                st[ST_STATUS] = -3; st[ST_STRONG] = new_strong; st[ST_TRUST] = new_trust;
+                a.worklist2[atomicAdd(&a.counters[RCX_C_NWORK2], 1ull)] = (uint32_t)item;
+            }
+        } else {
+            if (result == -2) {
+                #pragma unroll 1
+                for (int i = lane; i < len; i += 32) a.fixbuf[o + i] = M.fix[i];
+            }
+            if (lane == 0) { st[ST_STATUS] = result; st[ST_TOTALFIX] = total_fix; st[ST_BADSEG] = bad_segments; }
         }
         __syncwarp();
     }
@@ -1004,8 +1063,9 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
         const uint32_t o = a.off[r];
         const int len = (int)(a.off[r + 1] - o);
         const int kcnt = len - k + 1;
-        int result = a.meta[3 * w];
-        const int total_fix = a.meta[3 * w + 1], bad_segments = a.meta[3 * w + 2];
+        const int* st = a.state + w * state_stride(a.max_len, k);
+        int result = st[ST_STATUS];
+        const int total_fix = st[ST_TOTALFIX], bad_segments = st[ST_BADSEG];
         bool changed = false;
         int nN = 0, nA = 0, nT = 0;
         build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
@@ -1190,13 +1250,22 @@ static cudaError_t launch_one(void (*kern)(RcxCorrectArgs), const RcxCorrectArgs
     return cudaGetLastError();
 }
 
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, cudaStream_t s) {
-    if (a.n <= 0) return cudaSuccess;
+size_t rcx_state_words(int max_len, int k) { return (size_t)state_stride(max_len, k); }
+
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, cudaStream_t s) {
+    if (a0.n <= 0) return cudaSuccess;
+    RcxCorrectArgs a = a0;
     const size_t smem = rcx_correct_smem_per_warp(a.max_len, a.t.k) * COR_WARPS;
+    a.pass = 0;
     cudaError_t e = launch_one(rcx_triage_kernel, a, sm_count, a.n, smem, s);
     if (e != cudaSuccess) return e;
-    // the work-list length lives on the device: the two persistent kernels read it there (no host round trip)
-    e = launch_one(rcx_search_kernel, a, sm_count, a.n, smem, s);
-    if (e != cudaSuccess) return e;
+    // the work-list lengths live on the device: the persistent kernels read them there (no host round trip)
+    for (int pass = 0; pass < 2; ++pass) {
+        a.pass = pass;
+        e = launch_one(rcx_prep_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
+        if (e != cudaSuccess) return e;
+        e = launch_one(rcx_search_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
+        if (e != cudaSuccess) return e;
+    }
     return launch_one(rcx_finalize_kernel, a, sm_count, a.n, smem, s);
 }

@@ -13,6 +13,7 @@
 // device counters (unsigned long long each)
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
+       RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_WORKX4,  // second-pass list, per-kernel fetch counters
        RCX_C_ROUNDS, RCX_C_FF, RCX_C_REGULAR,  // search breakdown (only with -DRCX_PHASE_TIMERS)
        RCX_C_PHASE0,                            // 8 phase cycle counters (only with -DRCX_PHASE_TIMERS)
        RCX_C_COUNT = RCX_C_PHASE0 + 8 + 5 };  // + jumps, jump cycles, rescue steps, round cycles, round levels
@@ -50,7 +51,9 @@ struct RcxCorrectArgs {
     unsigned long long* counters;
     // hand-over between the triage / search / finalize kernels
     uint32_t* worklist;    // [n] indices of reads that need the search
-    int32_t* meta;         // [3 * n] per work item: status (-2 = post-filters), totalFix, badSegmentCnt
+    uint32_t* worklist2;   // [n] work items that asked for a second pass of A.4
+    int32_t* state;        // [n * rcx_state_words()] per work item: header, masks, segment list
+    int pass;              // 0 / 1 (set by the launcher)
     signed char* fixbuf;   // [off[n]] fix[] of reads that reach the post-filters
 };
 
@@ -67,4 +70,5 @@ size_t rcx_scan_smem_per_warp(int max_len, int k);
 cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s);
 // correction (rcx_correct.cu)
 size_t rcx_correct_smem_per_warp(int max_len, int k);
+size_t rcx_state_words(int max_len, int k);
 cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);

@@ -11,7 +11,7 @@ seq=np.fromfile(d+'/reads.seq',dtype=np.uint8); qual=np.fromfile(d+'/reads.qual'
 for i in range(2):
     c.correct(SINGLE, seq, qual, off)
 st=c.stats(); print(st)
-dc=c.debug_counters(23)
-names=['scan_probes','search_probes','rescan_probes','nodes','work','nwork','work2','rounds','ff','regular','ph0 fetch','ph1 planes+loads','ph2 thr/masks/islands','ph3 search','ph4 after-search','ph5 postfilter','ph6 lmh','ph7 tail','jumps','jump cycles','rescue steps','round cycles','round levels']
-tot=float(sum(dc[10:18]))
+dc=c.debug_counters(29)
+names=['scan_probes','search_probes','rescan_probes','nodes','work','nwork','work2','nwork2','wx0','wx1','wx2','wx3','wx4','rounds','ff','regular','ph0 fetch','ph1 planes+loads','ph2 thr/masks/islands','ph3 search','ph4 after-search','ph5 postfilter','ph6 lmh','ph7 tail','jumps','jump cycles','rescue steps','round cycles','round levels']
+tot=float(sum(dc[16:24]))
 for n,v in zip(names,dc): print('%-24s %15d %s'%(n,v, '%.1f%%'%(100*v/tot) if (n.startswith('ph') or 'cycles' in n) else ''))
