@@ -53,7 +53,7 @@ __host__ __device__ inline CorLayout cor_layout(int max_len, int k) {
     L.depth = kc + 3;
     int un = L.depth * FRAME_WORDS;
     if (un < L.n2) un = L.n2;
-    L.words = L.pkw + 10 * L.mw + L.lpad /*counts*/ + L.lpad / 2 /*path+fix as int8*/ + L.nseg + un;
+    L.words = L.pkw + 10 * L.mw + L.lpad /*counts*/ + 3 * L.lpad / 4 /*path, fix, posinfo as int8*/ + L.nseg + un;
     return L;
 }
 
@@ -69,6 +69,7 @@ struct WarpMem {
     int* counts;
     signed char* path;
     signed char* fix;
+    unsigned char* posinfo;  // per base: code (bits 0-1) | not-ACGT (bit 2) | substitution allowed in a Right search (bit 3) / Left search (bit 4)
     int* segtop;            // top2FixBottleNeck[1] per segment
     int* sbuf;              // sort buffer (aliases the search stack)
     unsigned int* stack;
@@ -349,8 +350,7 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
                         const unsigned int m = pos >= 31 ? rcx_bits(M.P.inv, pos - 31) : (M.P.inv[0] << (31 - pos));
                         run = m ? __clz(m) : 32;
                     }
-                    const int pidx0 = right ? pos - k + 1 : pos;
-                    const bool allowed0 = !getbit(M.strong, pos) && !(pidx0 >= 0 && getbit(M.pstrict, pidx0));
+                    const bool allowed0 = (M.posinfo[pos] & (right ? 8 : 16)) != 0;
                     spec_lite = !allowed0 && !force_full && t > 0 && run >= 1;
                     int D;
                     if (spec_lite) {
@@ -384,14 +384,9 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
                     const int i = lane;
                     const bool inr = i >= spec_lvl && i < spec_n;
                     const int p = right ? spec_pos0 + i : spec_pos0 - i;
-                    bool hok = false, allowed_i = false;
-                    int hb_i = 0;
-                    if (inr) {
-                        hok = !getbit(M.P.inv, p);
-                        hb_i = rcx_base(M.P.pk, p);
-                        const int pidx = right ? p - k + 1 : p;
-                        allowed_i = !getbit(M.strong, p) && !(pidx >= 0 && getbit(M.pstrict, pidx));
-                    }
+                    const int pi = inr ? M.posinfo[p] : 4;
+                    const bool hok = !(pi & 4), allowed_i = (pi & (right ? 8 : 16)) != 0;
+                    const int hb_i = pi & 3;
                     const int t_eff = t > 0 ? t : 0x7fffffff;
                     int thr_i = t_eff, keepc;
                     bool ok;
@@ -452,8 +447,9 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
                 DBG_INC(dbg[2]);
             }
         }
-        const bool here_ok = stage != ST_DONE && !getbit(M.P.inv, pos);
-        const int hb = stage != ST_DONE ? rcx_base(M.P.pk, pos) : 0;
+        const int pinfo = stage != ST_DONE ? M.posinfo[pos] : 4;
+        const bool here_ok = !(pinfo & 4);
+        const int hb = pinfo & 3;
         if (stage == ST_KEEP) {
             stage = ST_ALT0;
             if (here_ok) {  // :294-339 / :532-574
@@ -471,8 +467,9 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
                     #pragma unroll 1
                     for (; c < thr && steps < k; ++steps) {
                         if (right) { ++i; if (i >= to) break; } else { --i; if (i < to) break; }
-                        const bool bad = getbit(M.P.inv, i);
-                        const int b = rcx_base(M.P.pk, i);
+                        const int qi = M.posinfo[i];
+                        const bool bad = (qi & 4) != 0;
+                        const int b = qi & 3;
                         if (right) rcx_k_append(x, b, bad, k, mask); else rcx_k_prepend(x, b, bad, k, mask);
                         c = x.inv != -1 ? 0 : rcx_probe_ool(tab, rcx_canonical(x.code, k));
                         n_probes += 1;
@@ -490,8 +487,7 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
             }
         }
         if (stage >= ST_ALT0 && stage < ST_JUMP) {  // :343-372 / :577-608
-            const int pidx = right ? pos - k + 1 : pos;
-            const bool allowed = !getbit(M.strong, pos) && !(pidx >= 0 && getbit(M.pstrict, pidx));
+            const bool allowed = (pinfo & (right ? 8 : 16)) != 0;
             bool pushed = false;
             if (allowed) {
                 #pragma unroll 1
@@ -530,8 +526,9 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
                         probe4(tab, x, true, mask, lane, d0, d1, d2, d3);
                         n_probes += 4;
                         th = infer_thr(d0, d1, d2, d3, t, er);
-                        const bool bad = getbit(M.P.inv, i);
-                        const int b = rcx_base(M.P.pk, i);
+                        const int qi = M.posinfo[i];
+                        const bool bad = (qi & 4) != 0;
+                        const int b = qi & 3;
                         rcx_k_append(x, b, bad, k, mask);
                         const int c = bad ? 0 : sel4(b, d0, d1, d2, d3);
                         if (lane == 0) M.path[i] = -1;
@@ -548,8 +545,9 @@ __device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMe
                         probe4(tab, x, false, mask, lane, d0, d1, d2, d3);
                         n_probes += 4;
                         th = infer_thr(d0, d1, d2, d3, t, er);
-                        const bool bad = getbit(M.P.inv, i);
-                        const int b = rcx_base(M.P.pk, i);
+                        const int qi = M.posinfo[i];
+                        const bool bad = (qi & 4) != 0;
+                        const int b = qi & 3;
                         rcx_k_prepend(x, b, bad, k, mask);
                         const int c = bad ? 0 : sel4(b, d0, d1, d2, d3);
                         if (lane == 0) M.path[i] = -1;
@@ -635,7 +633,8 @@ __device__ __forceinline__ void setup_warpmem(WarpMem& M, unsigned int* smem, in
     M.counts = reinterpret_cast<int*>(p); p += L.lpad;
     M.path = reinterpret_cast<signed char*>(p);
     M.fix = M.path + L.lpad;
-    p += L.lpad / 2;
+    M.posinfo = reinterpret_cast<unsigned char*>(M.fix + L.lpad);
+    p += 3 * L.lpad / 4;
     M.segtop = reinterpret_cast<int*>(p); p += L.nseg;
     M.sbuf = reinterpret_cast<int*>(p);
     M.stack = p;
@@ -923,8 +922,15 @@ __global__ void __launch_bounds__(COR_WARPS * 32, 4) rcx_search_kernel(RcxCorrec
         build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
         #pragma unroll 1
         for (int c = lane; c < mw; c += 32) { M.strong[c] = (unsigned int)st[ST_HDR + c]; M.pstrict[c] = (unsigned int)st[ST_HDR + mw + c]; }
+        __syncwarp();
         #pragma unroll 1
-        for (int i = lane; i < len; i += 32) { M.fix[i] = -1; M.path[i] = -1; }  // :868-869, :1113-1114
+        for (int i = lane; i < len; i += 32) {
+            M.fix[i] = -1; M.path[i] = -1;  // :868-869, :1113-1114
+            const bool free_pos = !getbit(M.strong, i);
+            const bool pr = i - k + 1 >= 0 && getbit(M.pstrict, i - k + 1), pl = getbit(M.pstrict, i);  // :343 / :577
+            M.posinfo[i] = (unsigned char)(rcx_base(M.P.pk, i) | (getbit(M.P.inv, i) << 2) | ((free_pos && !pr) ? 8 : 0) |
+                                           ((free_pos && !pl) ? 16 : 0));
+        }
         const int strong = st[ST_STRONG], trust = st[ST_TRUST], nseg = st[ST_NSEG];
         const int* segs = st + ST_HDR + 2 * mw;
         __syncwarp();
