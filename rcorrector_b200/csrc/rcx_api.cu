@@ -68,7 +68,9 @@ struct rcx_ctx {
     DevBuf<uint8_t> d_flags;
     DevBuf<uint32_t> d_worklist, d_worklist2;
     DevBuf<int32_t> d_state;
-    DevBuf<signed char> d_fixbuf;
+    DevBuf<signed char> d_fixbuf, d_dfs_path;
+    DevBuf<unsigned char> d_posbuf;
+    DevBuf<unsigned int> d_dfs_stack;
     unsigned long long* d_counters = nullptr;
     cudaEvent_t ev[6]{};
     rcx_stats stats{};
@@ -106,7 +108,7 @@ extern "C" void rcx_destroy(rcx_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->buckets) cudaFree(c->buckets);
     c->d_seq.release(); c->d_qual.release(); c->d_off.release(); c->d_counts.release(); c->d_thr.release();
-    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_worklist2.release(); c->d_state.release(); c->d_fixbuf.release();
+    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_worklist2.release(); c->d_state.release(); c->d_fixbuf.release(); c->d_dfs_path.release(); c->d_posbuf.release(); c->d_dfs_stack.release();
     if (c->d_counters) cudaFree(c->d_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -257,6 +259,7 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
         CUDA_TRY(c->d_worklist2.ensure((size_t)n + 2));
         CUDA_TRY(c->d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
         CUDA_TRY(c->d_fixbuf.ensure(total_bases + 64));
+        CUDA_TRY(c->d_posbuf.ensure(total_bases + 64));
     }
     CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, c->stream));
     RcxScanArgs sa;
@@ -275,7 +278,12 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
         ca.counts = c->d_counts.p; ca.thr = c->d_thr.p; ca.flags = c->d_flags.p;
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = c->d_counters;
         ca.worklist = c->d_worklist.p; ca.worklist2 = c->d_worklist2.p; ca.state = c->d_state.p; ca.fixbuf = c->d_fixbuf.p; ca.pass = 0;
-        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, c->stream));
+        int dfs_grid = 0;
+        rcx_dfs_geometry(c->sm_count, max_len, c->k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
+        CUDA_TRY(c->d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
+        CUDA_TRY(c->d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
+        ca.posbuf = c->d_posbuf.p; ca.dfs_stack = c->d_dfs_stack.p; ca.dfs_path = c->d_dfs_path.p;
+        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, c->stream));
         c->stats.kernel_launches = 7;  // scan, triage, 2 x (prep, search), finalize
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));

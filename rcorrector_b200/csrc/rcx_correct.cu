@@ -120,470 +120,6 @@ __device__ __noinline__ void set_range(unsigned int* m, int a, int b, int mw, in
     }
 }
 
-__device__ __forceinline__ int sel4(int b, int c0, int c1, int c2, int c3) { return b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3; }
-
-// counts of the four one-base extensions of kc (lanes 0..3 probe, everyone receives)
-__device__ __noinline__ void probe4(const RcxTable& t, const RcxKmer& kc, bool right, unsigned long long mask, int lane, int& c0,
-                                       int& c1, int& c2, int& c3) {
-    int mine = 0;
-    if (lane < 4) {
-        RcxKmer x = kc;
-        if (right) rcx_k_append(x, lane, false, t.k, mask);
-        else rcx_k_prepend(x, lane, false, t.k, mask);
-        mine = x.inv != -1 ? 0 : rcx_probe_ool(t, rcx_canonical(x.code, t.k));
-    }
-    __syncwarp();
-    c0 = __shfl_sync(RCX_FULL, mine, 0);
-    c1 = __shfl_sync(RCX_FULL, mine, 1);
-    c2 = __shfl_sync(RCX_FULL, mine, 2);
-    c3 = __shfl_sync(RCX_FULL, mine, 3);
-}
-
-// InferPosThreshold (:144-173) given the four extension counts
-__device__ __forceinline__ int infer_thr(int c0, int c1, int c2, int c3, int upper, double er) {
-    int mx = c0 > c1 ? c0 : c1;
-    int my = c2 > c3 ? c2 : c3;
-    mx = mx > my ? mx : my;
-    if (mx < 0) mx = 0;
-    int r = rcx_bound_i_ool(mx, er);
-    if (r < 1) r = 1;
-    return (upper > r || upper <= 0) ? r : upper;
-}
-
-// ---------------------------------------------------------------------------------------------- speculative frontier
-// A search node needs the counts of its 4 one-base extensions, and the next node's k-mer depends on which child is
-// taken, so a literal translation pays one dependent DRAM round trip per node.  Almost every node, however, is a
-// "keep the read's base" step (after a substitution the search walks k-1 more positions to re-validate the
-// following k-mers).  So one ROUND probes, in a single batch of independent loads, nodes along the read's own bases:
-//   * FULL round: the 4 extensions of the current node and of the next 8*SPEC_U-1 nodes (lane 4*g+b probes base b of
-//     level 8*u+g); results are transposed to one level per lane (4 counts + the InferPosThreshold bound, so
-//     GetBound's FP64 sqrt runs once per round, not once per node);
-//   * LITE round (node on a position where substitutions are not allowed: strong-trusted base or poly-A k-mer):
-//     only the keep-base k-mer of up to 32 levels, one per lane.  A level passes without the other three counts when
-//     keep >= t and (int)GetBound(keep) >= t: GetBound is monotone, so InferPosThreshold returns exactly t.
-// Runs of nodes whose only viable child is the keep-base child are then consumed in one warp-parallel step
-// ("fast-forward").  Results, order of side effects and tie-breaking are those of the node-by-node recursion.
-#define SPEC_U 2
-#define SPEC_LEVELS (8 * SPEC_U)
-
-struct SpecRegs {
-    int c0, c1, c2, c3;  // full round: counts of the 4 extensions of level `lane`; lite round: c0 = keep-base count
-    int r;               // full: max(1, (int)GetBound(max of the 4)); lite: (int)GetBound(keep)
-};
-
-__device__ __noinline__ RcxKmer advance_kmer(const RcxPlanes& P, const RcxKmer& kc, bool right, int pos, int n, int k,
-                                                unsigned long long mask) {
-    // kc after n keep-base steps over VALID read bases starting at pos (n < k)
-    if (n == 0) return kc;
-    RcxKmer x;
-    if (right) {
-        const unsigned long long W = rcx_window(P.pk, pos, n);
-        x.code = ((kc.code << (2 * n)) | W) & mask;
-        x.inv = kc.inv == -1 ? -1 : (kc.inv + n >= k ? -1 : kc.inv + n);
-    } else {
-        const unsigned long long W = rcx_window(P.pk, pos - n + 1, n);
-        x.code = (kc.code >> (2 * n)) | (W << (2 * (k - n)));
-        x.inv = kc.inv == -1 ? -1 : (kc.inv - n < 0 ? -1 : kc.inv - n);
-    }
-    return x;
-}
-
-__device__ __noinline__ void spec_round_full(const RcxTable& tab, const RcxPlanes& P, const RcxKmer& kc, bool right, int pos, int D,
-                                                unsigned long long mask, double er, int lane, SpecRegs& R,
-                                                unsigned long long& n_probes) {
-    const int k = tab.k;
-    const int g = lane >> 2, b = lane & 3;
-    unsigned long long canon[SPEC_U], home[SPEC_U];
-    RcxBucketRegs d[SPEC_U];
-    bool live[SPEC_U];
-    int cnt[SPEC_U];
-#pragma unroll
-    for (int u = 0; u < SPEC_U; ++u) {
-        const int lvl = u * 8 + g;
-        live[u] = false;
-        cnt[u] = 0;
-        if (u * 8 < D) {  // warp-uniform: skip whole groups of levels that are not wanted
-            if (lvl < D) {
-                RcxKmer x = advance_kmer(P, kc, right, pos, lvl, k, mask);
-                if (right) rcx_k_append(x, b, false, k, mask);
-                else rcx_k_prepend(x, b, false, k, mask);
-                if (x.inv == -1) {
-                    live[u] = true;
-                    canon[u] = rcx_canonical(x.code, k);
-                    home[u] = rcx_home(tab, canon[u]);
-                    rcx_issue(tab, home[u], d[u]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < SPEC_U; ++u) {
-        if (u * 8 < D) {
-            if (live[u]) cnt[u] = rcx_resolve(tab, canon[u], home[u], d[u]);
-            n_probes += __popc(__ballot_sync(RCX_FULL, live[u]));
-        }
-    }
-    __syncwarp();
-    // transpose: lane i gathers the 4 counts of level i from lanes 4*(i&7)+b of register u = i>>3
-    const int src = 4 * (lane & 7), myu = lane >> 3;
-    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-    for (int u = 0; u < SPEC_U; ++u) {
-        if (u * 8 < D) {
-            const int x0 = __shfl_sync(RCX_FULL, cnt[u], src), x1 = __shfl_sync(RCX_FULL, cnt[u], src + 1);
-            const int x2 = __shfl_sync(RCX_FULL, cnt[u], src + 2), x3 = __shfl_sync(RCX_FULL, cnt[u], src + 3);
-            if (myu == u) { a0 = x0; a1 = x1; a2 = x2; a3 = x3; }
-        }
-    }
-    R.c0 = a0; R.c1 = a1; R.c2 = a2; R.c3 = a3;
-    int mx = a0 > a1 ? a0 : a1;
-    const int my = a2 > a3 ? a2 : a3;
-    mx = mx > my ? mx : my;
-    int r = rcx_bound_i_ool(mx < 0 ? 0 : mx, er);
-    R.r = r < 1 ? 1 : r;
-}
-
-__device__ __noinline__ void spec_round_lite(const RcxTable& tab, const RcxPlanes& P, const RcxKmer& kc, bool right, int pos, int D,
-                                                unsigned long long mask, double er, int lane, SpecRegs& R,
-                                                unsigned long long& n_probes) {
-    const int k = tab.k;
-    int c = 0;
-    bool live = false;
-    if (lane < D) {  // level `lane`: the k-mer after keeping the read's bases pos .. pos+lane (all valid)
-        const RcxKmer x = advance_kmer(P, kc, right, pos, lane + 1, k, mask);
-        if (x.inv == -1) {
-            live = true;
-            c = rcx_probe_ool(tab, rcx_canonical(x.code, k));
-        }
-    }
-    n_probes += __popc(__ballot_sync(RCX_FULL, live));
-    R.c0 = c; R.c1 = 0; R.c2 = 0; R.c3 = 0;
-    R.r = rcx_bound_i_ool(c < 0 ? 0 : c, er);
-}
-
-// One whole SearchPaths_Right (right = true) or SearchPaths_Left call tree.
-__device__ __forceinline__ void search_segment(const RcxTable& tab, const WarpMem& M, SearchState& S, const bool right, const int start,
-                               const int to, const int t0, RcxKmer kc, const int len, const double er, const int lane,
-                               unsigned long long& n_nodes, unsigned long long& n_probes, unsigned long long* dbg) {
-    const int k = tab.k;
-    const unsigned long long mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
-    (void)dbg;
-    int pos = start, t = t0, fix_cnt = 0, bn = RCX_INF, thr = 0, ext = 0, stage = ST_ENTER;
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    int sp = 0;
-    // speculation state (warp-uniform) + per-lane results
-    SpecRegs R;
-    R.c0 = R.c1 = R.c2 = R.c3 = 0; R.r = 1;
-    int spec_lvl = -1, spec_n = 0, spec_pos0 = 0;
-    bool first = true, spec_lite = false, force_full = false;
-
-#define PUSH_CHILD(npos, nt, nfix, nbn, nkc, nlvl)                                                    \
-    do {                                                                                              \
-        if (lane == 0) {                                                                              \
-            unsigned int* f = M.stack + sp * FRAME_WORDS;                                             \
-            f[0] = (unsigned int)kc.code;                                                             \
-            f[1] = (unsigned int)(kc.code >> 32);                                                     \
-            f[2] = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)stage << 20) | \
-                   ((unsigned int)(ext != 0) << 24);                                                  \
-            f[3] = (unsigned int)t; f[4] = (unsigned int)fix_cnt; f[5] = (unsigned int)bn; f[6] = (unsigned int)thr; \
-            f[7] = (unsigned int)c0; f[8] = (unsigned int)c1; f[9] = (unsigned int)c2; f[10] = (unsigned int)c3; \
-        }                                                                                             \
-        ++sp;                                                                                         \
-        { const int _p = (npos), _t = (nt), _f = (nfix), _b = (nbn), _l = (nlvl); const RcxKmer _k = (nkc); \
-          pos = _p; t = _t; fix_cnt = _f; bn = _b; kc = _k; spec_lvl = _l; }                          \
-        stage = ST_ENTER;                                                                             \
-        __syncwarp();                                                                                 \
-    } while (0)
-    // the jump child is always the last child of its node, so the parent frame is not needed again: no push.
-    // (This also bounds the stack: a Left jump can re-enter the same position, ErrorCorrection.cpp:672-676.)
-#define TAIL_CHILD(npos, nt, nfix, nkc)                                                               \
-    do {                                                                                              \
-        { const int _p = (npos), _t = (nt), _f = (nfix); const RcxKmer _k = (nkc);                    \
-          pos = _p; t = _t; fix_cnt = _f; kc = _k; spec_lvl = -1; }                                   \
-        stage = ST_ENTER;                                                                             \
-        __syncwarp();                                                                                 \
-    } while (0)
-
-    for (;;) {
-        if (stage == ST_ENTER) {
-            ++n_nodes;
-            bool leave = false;
-            // step 0 (:211-224 / :453-467)
-            if (S.trial > RCX_MAX_TRIAL) {
-                if (S.max_fix > 2) { --S.max_fix; S.best_cnt = 0; S.best_bn = -1; S.trial = 0; }
-                else leave = true;
-            }
-            if (!leave && fix_cnt > S.max_fix) leave = true;
-            if (!leave && (right ? pos >= to : pos < to)) {
-                // terminal (:228-285 / :468-524)
-                int fc = fix_cnt;
-                if (bn < t) ++fc;
-                if (fc < S.max_fix) { S.top2a = bn; S.top2b = -1; }
-                else if (fc == S.max_fix) {
-                    if (bn > S.top2a) { S.top2b = S.top2a; S.top2a = bn; }
-                    else if (bn > S.top2b) S.top2b = bn;
-                }
-                if (fc < S.max_fix || (fc == S.max_fix && bn > S.best_bn)) {
-                    if (fc < S.max_fix) S.trial = -(S.max_fix - fc + 1) * RCX_MAX_TRIAL;
-                    const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
-                    __syncwarp();
-                    #pragma unroll 1
-                    for (int i = lo + lane; i <= hi; i += 32) M.fix[i] = M.path[i];
-                    __syncwarp();
-                    S.max_fix = fc; S.best_bn = bn; S.best_cnt = 1;
-                } else if (fc == S.max_fix && bn == S.best_bn) {
-                    S.best_cnt += 1;
-                }
-                leave = true;
-            }
-            if (leave) {
-                stage = ST_DONE;
-            } else {
-                if (!(spec_lvl >= 0 && spec_lvl < spec_n)) {
-                    // new round from this node
-                    const int remaining = right ? to - pos : pos - to + 1;
-                    int run;  // consecutive valid read bases from pos in the search direction
-                    if (right) {
-                        const unsigned int m = rcx_bits(M.P.inv, pos);
-                        run = m ? __ffs(m) - 1 : 32;
-                    } else {
-                        const unsigned int m = pos >= 31 ? rcx_bits(M.P.inv, pos - 31) : (M.P.inv[0] << (31 - pos));
-                        run = m ? __clz(m) : 32;
-                    }
-                    const bool allowed0 = (M.posinfo[pos] & (right ? 8 : 16)) != 0;
-                    spec_lite = !allowed0 && !force_full && t > 0 && run >= 1;
-                    int D;
-                    if (spec_lite) {
-                        D = remaining < 32 ? remaining : 32;
-                        if (D > k - 1) D = k - 1;
-                        if (D > run) D = run;
-                    } else {
-                        // 1 level at the root of the search (its keep-base child usually fails: the root sits on the first
-                        // untrusted position), full depth afterwards
-                        D = first ? 1 : SPEC_LEVELS;
-                        if (D > remaining) D = remaining;
-                        if (D > k) D = k;
-                        if (D > run + 1) D = run + 1;
-                    }
-#ifdef RCX_PHASE_TIMERS
-                    const long long rt0 = clock64();
-#endif
-                    if (spec_lite) spec_round_lite(tab, M.P, kc, right, pos, D, mask, er, lane, R, n_probes);
-                    else spec_round_full(tab, M.P, kc, right, pos, D, mask, er, lane, R, n_probes);
-#ifdef RCX_PHASE_TIMERS
-                    dbg[6] += (unsigned long long)(clock64() - rt0);
-                    dbg[7] += D;
-#endif
-                    DBG_INC(dbg[0]);
-                    spec_lvl = 0; spec_n = D; spec_pos0 = pos;
-                    first = false;
-                    force_full = false;
-                }
-                // ---- fast-forward over nodes whose only viable child is the keep-base child (lane i = level i)
-                {
-                    const int i = lane;
-                    const bool inr = i >= spec_lvl && i < spec_n;
-                    const int p = right ? spec_pos0 + i : spec_pos0 - i;
-                    const int pi = inr ? M.posinfo[p] : 4;
-                    const bool hok = !(pi & 4), allowed_i = (pi & (right ? 8 : 16)) != 0;
-                    const int hb_i = pi & 3;
-                    const int t_eff = t > 0 ? t : 0x7fffffff;
-                    int thr_i = t_eff, keepc;
-                    bool ok;
-                    if (spec_lite) {
-                        keepc = R.c0;
-                        ok = inr && hok && !allowed_i && keepc >= t_eff && R.r >= t_eff;
-                    } else {
-                        if (right) {
-                            thr_i = t_eff < R.r ? t_eff : R.r;
-                        } else {  // Left hands its threshold down: prefix minimum from the current level
-                            int v = inr ? R.r : 0x7fffffff;
-#pragma unroll
-                            for (int o = 1; o < SPEC_LEVELS; o <<= 1) {
-                                const int u = __shfl_up_sync(RCX_FULL, v, o);
-                                if (lane >= o && u < v) v = u;
-                            }
-                            thr_i = t_eff < v ? t_eff : v;
-                        }
-                        keepc = sel4(hb_i, R.c0, R.c1, R.c2, R.c3);
-                        const bool alt_any = (R.c0 >= thr_i && !(hok && hb_i == 0)) || (R.c1 >= thr_i && !(hok && hb_i == 1)) ||
-                                             (R.c2 >= thr_i && !(hok && hb_i == 2)) || (R.c3 >= thr_i && !(hok && hb_i == 3));
-                        ok = inr && hok && keepc >= thr_i && !(allowed_i && alt_any);
-                    }
-                    const unsigned int okmask = __ballot_sync(RCX_FULL, ok);
-                    const int n_ff = __ffs(~(okmask >> spec_lvl)) - 1;
-                    if (n_ff > 0) {
-                        const bool mine = i >= spec_lvl && i < spec_lvl + n_ff;
-                        const int mn = __reduce_min_sync(RCX_FULL, mine ? keepc : 0x7fffffff);
-                        if (mn < bn) bn = mn;
-                        if (mine) M.path[p] = -1;
-                        if (!right) t = __shfl_sync(RCX_FULL, thr_i, spec_lvl + n_ff - 1);
-                        kc = advance_kmer(M.P, kc, right, pos, n_ff, k, mask);
-                        pos += right ? n_ff : -n_ff;
-                        spec_lvl += n_ff;
-                        n_nodes += n_ff - 1;
-                        DBG_INC(dbg[1]);
-                    }
-                    if (spec_lite && spec_lvl < spec_n) {  // a level failed the keep-only test: this node needs a full round
-                        spec_lvl = -1;
-                        force_full = true;
-                    }
-                    if (n_ff > 0 || spec_lite) {
-                        if (n_ff == 0) --n_nodes;  // the same node is entered again
-                        __syncwarp();
-                        continue;  // enter the node the run stopped at (gate and terminal test are re-evaluated)
-                    }
-                }
-                c0 = __shfl_sync(RCX_FULL, R.c0, spec_lvl);
-                c1 = __shfl_sync(RCX_FULL, R.c1, spec_lvl);
-                c2 = __shfl_sync(RCX_FULL, R.c2, spec_lvl);
-                c3 = __shfl_sync(RCX_FULL, R.c3, spec_lvl);
-                {
-                    const int r = __shfl_sync(RCX_FULL, R.r, spec_lvl);
-                    thr = (t > r || t <= 0) ? r : t;  // InferPosThreshold (:169-172)
-                }
-                ext = 0;
-                stage = ST_KEEP;
-                DBG_INC(dbg[2]);
-            }
-        }
-        const int pinfo = stage != ST_DONE ? M.posinfo[pos] : 4;
-        const bool here_ok = !(pinfo & 4);
-        const int hb = pinfo & 3;
-        if (stage == ST_KEEP) {
-            stage = ST_ALT0;
-            if (here_ok) {  // :294-339 / :532-574
-                int c = sel4(hb, c0, c1, c2, c3);
-                RcxKmer x = kc;
-                if (right) rcx_k_append(x, hb, false, k, mask); else rcx_k_prepend(x, hb, false, k, mask);
-                if (c >= thr) {
-                    if (lane == 0) M.path[pos] = -1;
-                    ext = 1;
-                    PUSH_CHILD(right ? pos + 1 : pos - 1, right ? t : thr, fix_cnt, c < bn ? c : bn, x, spec_lvl + 1);
-                    continue;
-                } else if (thr == 1 && t <= 2) {
-                    // "accidentally below the threshold" rescue (:313-338 / :550-573)
-                    int i = pos, steps = 0;
-                    #pragma unroll 1
-                    for (; c < thr && steps < k; ++steps) {
-                        if (right) { ++i; if (i >= to) break; } else { --i; if (i < to) break; }
-                        const int qi = M.posinfo[i];
-                        const bool bad = (qi & 4) != 0;
-                        const int b = qi & 3;
-                        if (right) rcx_k_append(x, b, bad, k, mask); else rcx_k_prepend(x, b, bad, k, mask);
-                        c = x.inv != -1 ? 0 : rcx_probe_ool(tab, rcx_canonical(x.code, k));
-                        n_probes += 1;
-                        DBG_INC(dbg[5]);
-                    }
-                    if (steps < k && (right ? i < to : i >= to)) {
-                        const int lo = right ? pos : i, hi = right ? i : pos;
-                        #pragma unroll 1
-                        for (int j = lo + lane; j <= hi; j += 32) M.path[j] = -1;
-                        ext = 1;
-                        PUSH_CHILD(right ? i + 1 : i - 1, right ? t : thr, fix_cnt + 1, bn, x, -1);
-                        continue;
-                    }
-                }
-            }
-        }
-        if (stage >= ST_ALT0 && stage < ST_JUMP) {  // :343-372 / :577-608
-            const bool allowed = (pinfo & (right ? 8 : 16)) != 0;
-            bool pushed = false;
-            if (allowed) {
-                #pragma unroll 1
-                for (int b = stage - ST_ALT0; b < 4; ++b) {
-                    if (here_ok && b == hb) continue;
-                    const int c = sel4(b, c0, c1, c2, c3);
-                    if (c >= thr) {
-                        if (lane == 0) M.path[pos] = (signed char)b;
-                        ++S.trial;
-                        ext = 1;
-                        RcxKmer x = kc;
-                        if (right) rcx_k_append(x, b, false, k, mask); else rcx_k_prepend(x, b, false, k, mask);
-                        stage = ST_ALT0 + b + 1;
-                        PUSH_CHILD(right ? pos + 1 : pos - 1, right ? t : thr, fix_cnt + (here_ok ? 1 : 0), c < bn ? c : bn, x, -1);
-                        pushed = true;
-                        break;
-                    }
-                }
-            }
-            if (pushed) continue;
-            stage = ST_JUMP;
-        }
-        if (stage == ST_JUMP) {
-            stage = ST_DONE;
-            if (ext == 0) {  // jump through an unfixable region (:393-441 / :629-677)
-                RcxKmer x = kc;
-                int i, th = thr;
-#ifdef RCX_PHASE_TIMERS
-                const long long jt0 = clock64();
-                dbg[3] += 1;
-#endif
-                if (right) {
-                    #pragma unroll 1
-                    for (i = pos; i < to; ++i) {
-                        int d0, d1, d2, d3;
-                        probe4(tab, x, true, mask, lane, d0, d1, d2, d3);
-                        n_probes += 4;
-                        th = infer_thr(d0, d1, d2, d3, t, er);
-                        const int qi = M.posinfo[i];
-                        const bool bad = (qi & 4) != 0;
-                        const int b = qi & 3;
-                        rcx_k_append(x, b, bad, k, mask);
-                        const int c = bad ? 0 : sel4(b, d0, d1, d2, d3);
-                        if (lane == 0) M.path[i] = -1;
-                        if (c >= th) break;
-                    }
-                    int kk = (i < len) ? i - pos - k + 1 : (i - pos) / 2;
-                    if (kk <= 0) kk = 1;
-                    if (i >= to) i -= 1;
-                    TAIL_CHILD(i + 1, t, fix_cnt + kk, x);
-                } else {
-                    #pragma unroll 1
-                    for (i = pos; i >= to; --i) {
-                        int d0, d1, d2, d3;
-                        probe4(tab, x, false, mask, lane, d0, d1, d2, d3);
-                        n_probes += 4;
-                        th = infer_thr(d0, d1, d2, d3, t, er);
-                        const int qi = M.posinfo[i];
-                        const bool bad = (qi & 4) != 0;
-                        const int b = qi & 3;
-                        rcx_k_prepend(x, b, bad, k, mask);
-                        const int c = bad ? 0 : sel4(b, d0, d1, d2, d3);
-                        if (lane == 0) M.path[i] = -1;
-                        if (c >= th) break;
-                    }
-                    int kk = (i >= 0) ? pos - i - k + 1 : pos - 1;
-                    if (kk <= 0) kk = 1;
-                    if (i <= to) ++i;
-                    TAIL_CHILD(i - 1, th, fix_cnt + kk, x);
-                }
-#ifdef RCX_PHASE_TIMERS
-                dbg[4] += (unsigned long long)(clock64() - jt0);
-#endif
-                continue;
-            }
-        }
-        // ST_DONE: return to the parent frame
-        if (sp == 0) break;
-        --sp;
-        spec_lvl = -1;
-        {
-            const unsigned int* f = M.stack + sp * FRAME_WORDS;
-            kc.code = (unsigned long long)f[0] | ((unsigned long long)f[1] << 32);
-            const unsigned int w = f[2];
-            pos = (int)(w & 0xfff) - 1;
-            kc.inv = (int)((w >> 12) & 0xff) - 1;
-            stage = (int)((w >> 20) & 0xf);
-            ext = (int)((w >> 24) & 1);
-            t = (int)f[3]; fix_cnt = (int)f[4]; bn = (int)f[5]; thr = (int)f[6];
-            c0 = (int)f[7]; c1 = (int)f[8]; c2 = (int)f[9]; c3 = (int)f[10];
-        }
-    }
-#undef PUSH_CHILD
-#undef TAIL_CHILD
-}
-
 // window code / state for a seed k-mer built by Restart + k Appends of seq[j .. j+k) (j may be -1)
 __device__ __forceinline__ RcxKmer seed_kmer(const RcxPlanes& P, int j, int k, unsigned int kmask32) {
     RcxKmer x;
@@ -743,19 +279,9 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_triage_kernel(RcxCorrectAr
     }
 }
 
-// per-work-item state in HBM (int32 words): header, isStrongTrusted plane, strict poly-A plane, segment list
-#define ST_STATUS 0      // -2 = go to the post-filters, -1 / 0 = final result, -3 = second pass of A.4 requested
-#define ST_TOTALFIX 1
-#define ST_BADSEG 2
-#define ST_STRONG 3
-#define ST_TRUST 4
-#define ST_NSEG 5
-#define ST_HDR 8
-__host__ __device__ inline int state_stride(int max_len, int k) { return ST_HDR + 2 * rcx_mask_words(max_len) + 2 * (max_len / k + 4); }
-
-// work-item fetch shared by the persistent kernels: pass 0 walks the triage work list, pass 1 the (short) list of
-// items whose first pass asked for a second one (forceNextRound, ErrorCorrection.cpp:1195-1211; at most two passes
-// can happen because forceNextRound needs iter == 0 and `unfixable` is never set)
+// work-item fetch shared by the persistent warp-per-read kernels: pass 0 walks the triage work list, pass 1 the
+// (short) list of items whose first pass asked for a second one (forceNextRound, ErrorCorrection.cpp:1195-1211; at
+// most two passes can happen because forceNextRound needs iter == 0 and `unfixable` is never set)
 __device__ __forceinline__ bool fetch_item(const RcxCorrectArgs& a, int counter, int lane, long long& item) {
     const long long n = (long long)a.counters[a.pass == 0 ? RCX_C_NWORK : RCX_C_NWORK2];
     long long w = 0;
@@ -766,17 +292,18 @@ __device__ __forceinline__ bool fetch_item(const RcxCorrectArgs& a, int counter,
     return true;
 }
 
-// A.4 steps 1-4 (:863-1046): trusted k-mers -> islands -> trusted positions -> segments, written to the item state.
+// A.4 steps 1-4 (:863-1046): trusted k-mers -> islands -> trusted positions -> segments (+ their seed k-mers and
+// maxFixCnt), written to the item state for the search kernel; on the second pass the re-threshold of :1247-1289 first.
 __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs a) {
     extern __shared__ unsigned int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = a.t.k;
+    const int k = a.t.k, K = a.max_fix_per_k;
     const CorLayout L = cor_layout(a.max_len, k);
     const int mw = L.mw;
     WarpMem M;
     setup_warpmem(M, smem, warp, L);
     const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
-    const int stride = state_stride(a.max_len, k);
+    const int stride = rcx_state_stride(a.max_len, k);
     for (;;) {
         long long item;
         if (!fetch_item(a, a.pass == 0 ? RCX_C_WORKX0 : RCX_C_WORKX2, lane, item)) break;
@@ -789,9 +316,44 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
         build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
         #pragma unroll 1
         for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
+        __syncwarp();
         int strong, trust;
-        if (a.pass == 0) initial_thresholds(a, r, a.flags[r], a.error_rate, strong, trust);
-        else { strong = st[ST_STRONG]; trust = st[ST_TRUST]; }
+        if (a.pass == 0) {
+            initial_thresholds(a, r, a.flags[r], a.error_rate, strong, trust);
+        } else {
+            // ---------------- re-threshold (:1247-1289)
+            strong = st[ST_STRONG]; trust = st[ST_TRUST];
+            const int loose = (k / 2 > 7) ? k / 2 : 7;
+            const int n2 = rcx_pow2_at_least(kcnt);
+            #pragma unroll 1
+            for (int j = lane; j < n2; j += 32)
+                M.sbuf[j] = j < kcnt ? (rcx_polya(M.P, j, k, kmask32, loose) ? -1 : M.counts[j]) : 0x7fffffff;
+            __syncwarp();
+            warp_sort_ool(M.sbuf, n2, lane);
+            int ibreak = 0;
+            bool any_drop = false;
+            #pragma unroll 1
+            for (int i = 1 + lane; i < kcnt; i += 32) {
+                const int v = M.sbuf[i], pv = M.sbuf[i - 1];
+                if (v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5)) && v < strong) ibreak = i;
+            }
+            ibreak = __reduce_max_sync(RCX_FULL, ibreak);
+            #pragma unroll 1
+            for (int i = 1 + lane; i < kcnt; i += 32) {
+                const int v = M.sbuf[i], pv = M.sbuf[i - 1];
+                if (i >= ibreak && v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5))) any_drop = true;
+            }
+            any_drop = __any_sync(RCX_FULL, any_drop);
+            if (!any_drop) {  // no lower plateau: keep the first pass' result and go to the post-filters (:1288-1289)
+                if (lane == 0) st[ST_STATUS] = RCX_ST_POSTFILTER;
+                __syncwarp();
+                continue;
+            }
+            const int nv = M.sbuf[ibreak];
+            trust = rcx_bound_i_ool(nv, a.error_rate);  // no clamp to 2 here (:1282)
+            strong = nv;
+            __syncwarp();
+        }
         #pragma unroll 1
         for (int c = lane; c < mw; c += 32) { M.pstrict[c] = 0; M.strong[c] = 0; M.trusted[c] = 0; }
         __syncwarp();
@@ -804,7 +366,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
             if (lane == 0) { M.pstrict[c] = bp; M.trusted[c] = bt; }
         }
         __syncwarp();
-        int status = -2, nseg = 0;
+        int status = RCX_ST_SEARCH, nseg = 0;
         if (next_bit(M.trusted, 0, kcnt, false, lane) >= kcnt) {
             status = 0;  // longestTrustedLength == kcnt (:1110)
         } else {
@@ -850,8 +412,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
                 set_range(M.island, tstart, tend + k - 1, mw, lane);
                 __syncwarp();
             }
-            // segments (:1009-1046): prefix, gaps between islands, suffix; packed (from | to << 16), (lanchor | ranchor << 16)
-            int* segs = st + ST_HDR + 2 * mw;
+            // segments (:1009-1046, :1125-1160): prefix, gaps between islands, suffix
             int ifrom = next_bit(M.island, 0, len, true, lane);
             int ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
             int prev_to = -1, prev_len = 0;
@@ -868,7 +429,22 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
                     is_seg = prev_to < len - 1;
                 }
                 if (is_seg) {
-                    if (lane == 0 && nseg < L.nseg) { segs[2 * nseg] = sf | (sto << 16); segs[2 * nseg + 1] = la | (ra << 16); }
+                    if (nseg < L.nseg) {
+                        const bool right = la >= ra;  // :1136
+                        const int extend = right ? (sto == len ? 0 : k - 1) : (sf == 0 ? 0 : k - 1);
+                        const RcxKmer kc = seed_kmer(M.P, right ? sf - k : sto + 1, k, kmask32);
+                        int max_fix = (sto - sf + 1) * K / k * 2 + 1;  // :1128-1131
+                        if (max_fix < K) max_fix = K;
+                        if (lane == 0) {
+                            int* sg = st + ST_HDR + ST_SEGW * nseg;
+                            sg[0] = (right ? sf : sto) | ((right ? sto + extend : sf - extend) << 16);
+                            sg[1] = (right ? 1 : 0) | (max_fix << 1);
+                            sg[2] = (int)(unsigned int)kc.code;
+                            sg[3] = (int)(unsigned int)(kc.code >> 32);
+                            sg[4] = kc.inv;
+                            sg[5] = -1;  // top2FixBottleNeck[1], filled by the search
+                        }
+                    }
                     ++nseg;
                 }
                 if (ifrom >= len) break;
@@ -876,176 +452,21 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
                 ifrom = next_bit(M.island, ito + 1, len, true, lane);
                 ito = ifrom < len ? next_bit(M.island, ifrom, len, false, lane) - 1 : len - 1;
             }
+            // per-base info for the search and a clean fix[] (:1113-1114)
+            #pragma unroll 1
+            for (int i = lane; i < len; i += 32) {
+                const bool free_pos = !getbit(M.strong, i);
+                const bool pr = i - k + 1 >= 0 && getbit(M.pstrict, i - k + 1), pl = getbit(M.pstrict, i);  // :343 / :577
+                a.posbuf[o + i] = (unsigned char)(rcx_base(M.P.pk, i) | (getbit(M.P.inv, i) << 2) | ((free_pos && !pr) ? 8 : 0) |
+                                                  ((free_pos && !pl) ? 16 : 0));
+                a.fixbuf[o + i] = -1;
+            }
         }
-        #pragma unroll 1
-        for (int c = lane; c < mw; c += 32) { st[ST_HDR + c] = (int)M.strong[c]; st[ST_HDR + mw + c] = (int)M.pstrict[c]; }
         if (lane == 0) {
             st[ST_STATUS] = status; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
             st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < L.nseg ? nseg : L.nseg;
         }
         __syncwarp();
-    }
-}
-
-// A.4 steps 6-9 (:1113-1289): the ordered searches over the segments of one read, then the ambiguity / forceNextRound
-// decisions and, when a second pass is due, the re-threshold.
-__global__ void __launch_bounds__(COR_WARPS * 32, 4) rcx_search_kernel(RcxCorrectArgs a) {
-    extern __shared__ unsigned int smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = a.t.k, K = a.max_fix_per_k;
-    const double er = a.error_rate;
-    const CorLayout L = cor_layout(a.max_len, k);
-    const int mw = L.mw;
-    WarpMem M;
-    setup_warpmem(M, smem, warp, L);
-    const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
-    const int stride = state_stride(a.max_len, k);
-    unsigned long long n_nodes = 0, n_sprobes = 0;
-    unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#ifdef RCX_PHASE_TIMERS
-    unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long ph_last = clock64();
-    int ph_cur = 0;
-#endif
-    for (;;) {
-        PH(0);  // work fetch
-        long long item;
-        if (!fetch_item(a, a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3, lane, item)) break;
-        int* st = a.state + item * stride;
-        if (st[ST_STATUS] != -2) continue;  // decided by the prep kernel (all k-mers trusted on the second pass)
-        const long long r = a.worklist[item];
-        const uint32_t o = a.off[r];
-        const int len = (int)(a.off[r + 1] - o);
-        const int kcnt = len - k + 1;
-        PH(1);  // planes + state loads
-        int nN, nA, nT;
-        build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
-        #pragma unroll 1
-        for (int c = lane; c < mw; c += 32) { M.strong[c] = (unsigned int)st[ST_HDR + c]; M.pstrict[c] = (unsigned int)st[ST_HDR + mw + c]; }
-        __syncwarp();
-        #pragma unroll 1
-        for (int i = lane; i < len; i += 32) {
-            M.fix[i] = -1; M.path[i] = -1;  // :868-869, :1113-1114
-            const bool free_pos = !getbit(M.strong, i);
-            const bool pr = i - k + 1 >= 0 && getbit(M.pstrict, i - k + 1), pl = getbit(M.pstrict, i);  // :343 / :577
-            M.posinfo[i] = (unsigned char)(rcx_base(M.P.pk, i) | (getbit(M.P.inv, i) << 2) | ((free_pos && !pr) ? 8 : 0) |
-                                           ((free_pos && !pl) ? 16 : 0));
-        }
-        const int strong = st[ST_STRONG], trust = st[ST_TRUST], nseg = st[ST_NSEG];
-        const int* segs = st + ST_HDR + 2 * mw;
-        __syncwarp();
-        PH(3);  // searches
-        int result = -2, total_fix = 0, bad_segments = 0, best_bn = RCX_INF;
-        bool abort_read = false;
-        #pragma unroll 1
-        for (int g = 0; g < nseg && !abort_read; ++g) {  // :1125-1175
-            const int w0 = segs[2 * g], w1 = segs[2 * g + 1];
-            const int sf = w0 & 0xffff, sto = w0 >> 16, la = w1 & 0xffff, ra = w1 >> 16;
-            SearchState S;
-            S.trial = 0;
-            S.max_fix = (sto - sf + 1) * K / k * 2 + 1;
-            if (S.max_fix < K) S.max_fix = K;
-            S.best_bn = -1; S.best_cnt = -1; S.top2a = -1; S.top2b = -1;
-            {
-                const bool right = la >= ra;  // :1136
-                const int extend = right ? (sto == len ? 0 : k - 1) : (sf == 0 ? 0 : k - 1);
-                const RcxKmer kc = seed_kmer(M.P, right ? sf - k : sto + 1, k, kmask32);
-                search_segment(a.t, M, S, right, right ? sf : sto, right ? sto + extend : sf - extend, trust, kc, len, er, lane,
-                               n_nodes, n_sprobes, dbg);
-            }
-            if (lane == 0) M.segtop[g] = S.top2b;
-            if (S.best_bn == -1) {
-                ++bad_segments;
-            } else {
-                if (S.best_bn < best_bn) best_bn = S.best_bn;
-                if (S.trial > RCX_MAX_TRIAL) abort_read = true;  // :1172
-                else total_fix += S.max_fix;
-            }
-        }
-        __syncwarp();
-        PH(4);  // decisions, re-threshold
-        bool second_pass = false;
-        int new_strong = strong, new_trust = trust;
-        if (abort_read) {
-            result = -1;
-        } else {
-            bool force_next = false;
-            if (nseg > 0) {  // :1176-1230
-                int best_fix_cnt = 1;
-                #pragma unroll 1
-                for (int g = 0; g < nseg; ++g)
-                    if (M.segtop[g] >= best_bn) best_fix_cnt *= 2;
-                if (a.pass == 0 && (double)best_bn < rcx_bound_d_ool(strong, er)) force_next = true;  // :1195 FP64 compare
-                if (best_fix_cnt >= 2) result = -1;
-            }
-            if (result == -2) {
-                const bool unfixable = total_fix > len;  // :1234 (never true in practice)
-                if (total_fix == 0 && force_next) result = 0;  // :1231
-                else if (!unfixable && !force_next) { /* leave the loop: post-filters */ }
-                else if (trust < 10 && !force_next) result = -1;
-                else {
-                    // ---------------- re-threshold (:1247-1289)
-                    const int loose = (k / 2 > 7) ? k / 2 : 7;
-                    const int n2 = rcx_pow2_at_least(kcnt);
-                    #pragma unroll 1
-                    for (int j = lane; j < n2; j += 32)
-                        M.sbuf[j] = j < kcnt ? (rcx_polya(M.P, j, k, kmask32, loose) ? -1 : a.counts[o + j]) : 0x7fffffff;
-                    __syncwarp();
-                    warp_sort_ool(M.sbuf, n2, lane);
-                    int ibreak = 0;
-                    bool any_drop = false;
-                    #pragma unroll 1
-                    for (int i = 1 + lane; i < kcnt; i += 32) {
-                        const int v = M.sbuf[i], pv = M.sbuf[i - 1];
-                        if (v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5)) && v < strong) ibreak = i;
-                    }
-                    ibreak = __reduce_max_sync(RCX_FULL, ibreak);
-                    #pragma unroll 1
-                    for (int i = 1 + lane; i < kcnt; i += 32) {
-                        const int v = M.sbuf[i], pv = M.sbuf[i - 1];
-                        if (i >= ibreak && v <= strong && ((v > 2 * pv && v > 10) || (pv == 0 && v >= 5))) any_drop = true;
-                    }
-                    any_drop = __any_sync(RCX_FULL, any_drop);
-                    if (any_drop) {
-                        const int nv = M.sbuf[ibreak];
-                        new_trust = rcx_bound_i_ool(nv, er);
-                        new_strong = nv;
-                        second_pass = a.pass == 0;  // a second pass never asks for a third (forceNextRound needs iter == 0)
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-        PH(5);  // hand-over
-        if (second_pass) {
-            if (lane == 0) {
-                st[ST_STATUS] = -3; st[ST_STRONG] = new_strong; st[ST_TRUST] = new_trust;
-                a.worklist2[atomicAdd(&a.counters[RCX_C_NWORK2], 1ull)] = (uint32_t)item;
-            }
-        } else {
-            if (result == -2) {
-                #pragma unroll 1
-                for (int i = lane; i < len; i += 32) a.fixbuf[o + i] = M.fix[i];
-            }
-            if (lane == 0) { st[ST_STATUS] = result; st[ST_TOTALFIX] = total_fix; st[ST_BADSEG] = bad_segments; }
-        }
-        __syncwarp();
-    }
-#ifdef RCX_PHASE_TIMERS
-    PH(7);
-    if (lane == 0) {
-        for (int i = 0; i < 8; ++i) atomicAdd(&a.counters[RCX_C_PHASE0 + i], ph[i]);
-        atomicAdd(&a.counters[RCX_C_ROUNDS], dbg[0]);
-        atomicAdd(&a.counters[RCX_C_FF], dbg[1]);
-        atomicAdd(&a.counters[RCX_C_REGULAR], dbg[2]);
-        for (int i = 3; i < 8; ++i) atomicAdd(&a.counters[RCX_C_PHASE0 + 8 + i - 3], dbg[i]);
-    }
-#endif
-    n_nodes = warp_sum_u64(lane == 0 ? n_nodes : 0);
-    n_sprobes = warp_sum_u64(lane == 0 ? n_sprobes : 0);
-    if (lane == 0) {
-        if (n_nodes) atomicAdd(&a.counters[RCX_C_SEARCH_NODES], n_nodes);
-        if (n_sprobes) atomicAdd(&a.counters[RCX_C_SEARCH_PROBES], n_sprobes);
     }
 }
 
@@ -1069,7 +490,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
         const uint32_t o = a.off[r];
         const int len = (int)(a.off[r + 1] - o);
         const int kcnt = len - k + 1;
-        const int* st = a.state + w * state_stride(a.max_len, k);
+        const int* st = a.state + w * rcx_state_stride(a.max_len, k);
         int result = st[ST_STATUS];
         const int total_fix = st[ST_TOTALFIX], bad_segments = st[ST_BADSEG];
         bool changed = false;
@@ -1256,9 +677,9 @@ static cudaError_t launch_one(void (*kern)(RcxCorrectArgs), const RcxCorrectArgs
     return cudaGetLastError();
 }
 
-size_t rcx_state_words(int max_len, int k) { return (size_t)state_stride(max_len, k); }
+size_t rcx_state_words(int max_len, int k) { return (size_t)rcx_state_stride(max_len, k); }
 
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, cudaStream_t s) {
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, int dfs_grid, cudaStream_t s) {
     if (a0.n <= 0) return cudaSuccess;
     RcxCorrectArgs a = a0;
     const size_t smem = rcx_correct_smem_per_warp(a.max_len, a.t.k) * COR_WARPS;
@@ -1270,7 +691,7 @@ cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, cudaStrea
         a.pass = pass;
         e = launch_one(rcx_prep_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
         if (e != cudaSuccess) return e;
-        e = launch_one(rcx_search_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
+        e = rcx_launch_dfs(a, dfs_grid, s);
         if (e != cudaSuccess) return e;
     }
     return launch_one(rcx_finalize_kernel, a, sm_count, a.n, smem, s);

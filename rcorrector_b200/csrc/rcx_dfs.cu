@@ -1,0 +1,398 @@
+// rcx_dfs.cu — the ordered correction search: SearchPaths_Right / SearchPaths_Left
+// (ErrorCorrection.cpp:201-442 / 444-678), InferPosThreshold (:144-173) and the per-read
+// bookkeeping around them (:1118-1242), one THREAD per read.
+//
+// Why a thread, not a warp: the search is an order-dependent depth-first walk whose state
+// (maxFixCnt, trialCnt, best path, tie counts) is shared by the whole recursion, so the only
+// parallelism inside one read is the 4 one-base extensions of a node.  A warp-per-read version of
+// this kernel (round 1, profiles/) executed ~4 000 warp-instructions per read with 31 of 32 lanes
+// repeating the same scalar bookkeeping, ran at 16 warps/SM because of its register count, and
+// spent 40 % of its issue slots waiting for instructions (63 KB of straight-line SASS executed once
+// per read).  Here every lane walks its own read: the bookkeeping is SIMT-parallel across 32
+// reads, the 4 extension probes of a node are 4 independent 64-byte loads per lane (128 per warp in
+// flight), and lanes pull new work items on their own so that short searches do not wait for long
+// ones.  Reads are independent, so results do not depend on the mapping.
+//
+// The recursion becomes an explicit stack of 11-word frames per thread, interleaved by lane in a
+// global scratch buffer (same-depth accesses of a warp coalesce; depth <= kcnt + 2 because the jump
+// child is a tail call).  Children are visited in the reference's order: keep-base (or the
+// "accidentally below threshold" rescue), then A, C, G, T, then the jump through an unfixable
+// region.  The four extension k-mers of a node serve InferPosThreshold, the keep-base test and the
+// three alternatives at once (the CPU probes the same k-mers 8 times).
+#include "rcx_internal.h"
+
+#define DFS_THREADS 128
+#define DFS_FRAME 11
+#define DFS_LUT 1024
+
+enum { T_FETCH = 0, T_SEG = 1, T_ENTER = 2, T_ALT0 = 3 /* ..T_ALT0+3 */, T_JUMP = 7, T_POP = 8 };
+
+__device__ __forceinline__ int dfs_sel4(int b, int c0, int c1, int c2, int c3) { return b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3; }
+
+// counts of the 4 one-base extensions of kc: 4 independent bucket probes per thread, two in flight at a time
+__device__ __noinline__ void dfs_probe4(const RcxTable& t, const RcxKmer& kc, bool right, unsigned long long mask, int& c0, int& c1,
+                                           int& c2, int& c3) {
+    int c[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        unsigned long long canon[2], home[2];
+        RcxBucketRegs d[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            RcxKmer x = kc;
+            if (right) rcx_k_append(x, 2 * h + u, false, t.k, mask);
+            else rcx_k_prepend(x, 2 * h + u, false, t.k, mask);
+            live[u] = x.inv == -1;
+            if (live[u]) {
+                canon[u] = rcx_canonical(x.code, t.k);
+                home[u] = rcx_home(t, canon[u]);
+                rcx_issue(t, home[u], d[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) c[2 * h + u] = live[u] ? rcx_resolve(t, canon[u], home[u], d[u]) : 0;
+    }
+    c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3];
+}
+
+// InferPosThreshold (:144-173) given the four extension counts; lut[c] = max(1, (int)GetBound(c)) for small c
+__device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upper, double er, const int* lut) {
+    int mx = c0 > c1 ? c0 : c1;
+    const int my = c2 > c3 ? c2 : c3;
+    mx = mx > my ? mx : my;
+    if (mx < 0) mx = 0;
+    int r;
+    if (mx < DFS_LUT) r = lut[mx];
+    else { r = rcx_bound_i(mx, er); if (r < 1) r = 1; }
+    return (upper > r || upper <= 0) ? r : upper;
+}
+
+__global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs a) {
+    __shared__ int lut[DFS_LUT];
+    const int lane = threadIdx.x & 31;
+    const int k = a.t.k;
+    const double er = a.error_rate;
+    const unsigned long long mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    for (int c = threadIdx.x; c < DFS_LUT; c += DFS_THREADS) {
+        const int r = rcx_bound_i(c, er);
+        lut[c] = r < 1 ? 1 : r;
+    }
+    __syncthreads();
+    const int stride = rcx_state_stride(a.max_len, k);
+    const long long nitems = (long long)a.counters[a.pass == 0 ? RCX_C_NWORK : RCX_C_NWORK2];
+    const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
+    // per-thread scratch, interleaved by lane
+    const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
+    unsigned int* stack = a.dfs_stack + gwarp * (long long)a.dfs_depth * DFS_FRAME * 32 + lane;
+    signed char* path = a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;
+#define STK(f, w) stack[((f) * DFS_FRAME + (w)) * 32]
+#define PATH(p) path[(p) * 32]
+
+    unsigned long long n_nodes = 0, n_probes = 0;
+    // ---- per-item state
+    int* st = nullptr;
+    const unsigned char* pinfo = nullptr;
+    signed char* fix = nullptr;
+    int len = 0, nseg = 0, g = 0, trust = 0, strong = 0, total_fix = 0, bad_segments = 0, best_bn_all = RCX_INF;
+    bool abort_read = false;
+    long long item = 0;
+    // ---- per-segment state (the by-reference parameters of SearchPaths_*)
+    bool right = true;
+    int start = 0, to = 0;
+    int max_fix = 0, best_cnt = -1, best_bn = -1, trial = 0, top2a = -1, top2b = -1;
+    // ---- current node
+    int pos = 0, t = 0, fix_cnt = 0, bn = 0, thr = 0, ext = 0, sp = 0;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    RcxKmer kc;
+    kc.code = 0; kc.inv = -1;
+    int stage = T_FETCH;
+
+    for (;;) {
+        if (stage == T_FETCH) {
+            const long long w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
+            if (w >= nitems) break;
+            item = a.pass == 0 ? w : (long long)a.worklist2[w];
+            st = a.state + item * stride;
+            if (st[ST_STATUS] != RCX_ST_SEARCH) continue;  // decided by the prep kernel
+            const long long r = a.worklist[item];
+            const uint32_t o = a.off[r];
+            len = (int)(a.off[r + 1] - o);
+            pinfo = a.posbuf + o;
+            fix = a.fixbuf + o;
+            nseg = st[ST_NSEG]; trust = st[ST_TRUST]; strong = st[ST_STRONG];
+            g = 0; total_fix = 0; bad_segments = 0; best_bn_all = RCX_INF; abort_read = false;
+            stage = T_SEG;
+        }
+        if (stage == T_SEG) {
+            if (g >= nseg || abort_read) {
+                // ---------------- decisions after the searches (:1176-1242)
+                int result = RCX_ST_POSTFILTER;
+                bool rethreshold = false;
+                if (abort_read) {
+                    result = -1;  // :1172
+                } else {
+                    bool force_next = false;
+                    if (nseg > 0) {
+                        int best_fix_cnt = 1;
+                        for (int s = 0; s < nseg; ++s)
+                            if (st[ST_HDR + ST_SEGW * s + 5] >= best_bn_all) best_fix_cnt *= 2;
+                        if (a.pass == 0 && (double)best_bn_all < rcx_bound_d(strong, er)) force_next = true;  // :1195 FP64 compare
+                        if (best_fix_cnt >= 2) result = -1;
+                    }
+                    if (result == RCX_ST_POSTFILTER) {
+                        const bool unfixable = total_fix > len;  // :1234 (never true in practice)
+                        if (total_fix == 0 && force_next) result = 0;  // :1231
+                        else if (!unfixable && !force_next) { /* leave the loop: post-filters */ }
+                        else if (trust < 10 && !force_next) result = -1;
+                        else rethreshold = true;
+                    }
+                }
+                st[ST_TOTALFIX] = total_fix;
+                st[ST_BADSEG] = bad_segments;
+                if (rethreshold) {
+                    if (a.pass == 0) {
+                        st[ST_STATUS] = RCX_ST_RETHRESHOLD;  // the pass-1 prep kernel re-thresholds (:1247-1289)
+                        a.worklist2[atomicAdd(&a.counters[RCX_C_NWORK2], 1ull)] = (uint32_t)item;
+                    } else {
+                        // a third pass needs `unfixable`, i.e. totalFix > read length: cannot happen; flagged, not hidden
+                        atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);
+                        st[ST_STATUS] = -1;
+                    }
+                } else {
+                    st[ST_STATUS] = result;
+                }
+                stage = T_FETCH;
+                continue;
+            }
+            const int* sg = st + ST_HDR + ST_SEGW * g;
+            const int w0 = sg[0], w1 = sg[1];
+            start = w0 & 0xffff; to = (w0 >> 16) & 0xffff;
+            right = (w1 & 1) != 0;
+            max_fix = w1 >> 1;
+            kc.code = (unsigned long long)(unsigned int)sg[2] | ((unsigned long long)(unsigned int)sg[3] << 32);
+            kc.inv = sg[4];
+            best_cnt = -1; best_bn = -1; trial = 0; top2a = -1; top2b = -1;
+            pos = start; t = trust; fix_cnt = 0; bn = RCX_INF; sp = 0;
+            stage = T_ENTER;
+        }
+        if (stage == T_ENTER) {
+            ++n_nodes;
+            bool leave = false;
+            // step 0 (:211-224 / :453-467)
+            if (trial > RCX_MAX_TRIAL) {
+                if (max_fix > 2) { --max_fix; best_cnt = 0; best_bn = -1; trial = 0; }
+                else leave = true;
+            }
+            if (!leave && fix_cnt > max_fix) leave = true;
+            if (!leave && (right ? pos >= to : pos < to)) {
+                // terminal (:228-285 / :468-524)
+                int fc = fix_cnt;
+                if (bn < t) ++fc;
+                if (fc < max_fix) { top2a = bn; top2b = -1; }
+                else if (fc == max_fix) {
+                    if (bn > top2a) { top2b = top2a; top2a = bn; }
+                    else if (bn > top2b) top2b = bn;
+                }
+                if (fc < max_fix || (fc == max_fix && bn > best_bn)) {
+                    if (fc < max_fix) trial = -(max_fix - fc + 1) * RCX_MAX_TRIAL;
+                    const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
+                    for (int i = lo; i <= hi; ++i) fix[i] = PATH(i);
+                    max_fix = fc; best_bn = bn; best_cnt = 1;
+                } else if (fc == max_fix && bn == best_bn) {
+                    best_cnt += 1;
+                }
+                leave = true;
+            }
+            if (leave) {
+                stage = T_POP;
+            } else {
+                dfs_probe4(a.t, kc, right, mask, c0, c1, c2, c3);
+                n_probes += 4;
+                thr = dfs_infer(c0, c1, c2, c3, t, er, lut);
+                ext = 0;
+                stage = T_ALT0;
+                // ---- keep the read's base (:294-339 / :532-574)
+                const int pi = pinfo[pos];
+                if (!(pi & 4)) {
+                    const int hb = pi & 3;
+                    int c = dfs_sel4(hb, c0, c1, c2, c3);
+                    RcxKmer x = kc;
+                    if (right) rcx_k_append(x, hb, false, k, mask); else rcx_k_prepend(x, hb, false, k, mask);
+                    bool go = false;
+                    int npos = 0, nfix = fix_cnt, nbn = bn;
+                    if (c >= thr) {
+                        PATH(pos) = -1;
+                        go = true; npos = right ? pos + 1 : pos - 1; nbn = c < bn ? c : bn;
+                    } else if (thr == 1 && t <= 2) {
+                        // "accidentally below the threshold" rescue (:313-338 / :550-573)
+                        int i = pos, steps = 0;
+                        for (; c < thr && steps < k; ++steps) {
+                            if (right) { ++i; if (i >= to) break; } else { --i; if (i < to) break; }
+                            const int qi = pinfo[i];
+                            if (right) rcx_k_append(x, qi & 3, (qi & 4) != 0, k, mask); else rcx_k_prepend(x, qi & 3, (qi & 4) != 0, k, mask);
+                            c = rcx_k_count(a.t, x);
+                            ++n_probes;
+                        }
+                        if (steps < k && (right ? i < to : i >= to)) {
+                            const int lo = right ? pos : i, hi = right ? i : pos;
+                            for (int j = lo; j <= hi; ++j) PATH(j) = -1;
+                            go = true; npos = right ? i + 1 : i - 1; nfix = fix_cnt + 1;
+                        }
+                    }
+                    if (go) {
+                        ext = 1;
+                        // when no alternative base can pass, the parent has nothing left to do after this child
+                        // (ext != 0 rules out the jump): tail call, no frame
+                        const bool allowed = (pi & (right ? 8 : 16)) != 0;
+                        const bool alt_any = allowed && ((hb != 0 && c0 >= thr) || (hb != 1 && c1 >= thr) || (hb != 2 && c2 >= thr) ||
+                                                         (hb != 3 && c3 >= thr));
+                        if (alt_any) {
+                            STK(sp, 0) = (unsigned int)kc.code; STK(sp, 1) = (unsigned int)(kc.code >> 32);
+                            STK(sp, 2) = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)T_ALT0 << 20) | (1u << 24);
+                            STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt; STK(sp, 5) = (unsigned int)bn;
+                            STK(sp, 6) = (unsigned int)thr;
+                            STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
+                            ++sp;
+                        }
+                        if (!right) t = thr;  // Left hands its threshold down (:546,569)
+                        pos = npos; fix_cnt = nfix; bn = nbn; kc = x;
+                        stage = T_ENTER;
+                        continue;
+                    }
+                }
+            }
+        }
+        if (stage >= T_ALT0 && stage < T_JUMP) {  // alternatives in the order A, C, G, T (:343-372 / :577-608)
+            const int pi = pinfo[pos];
+            const bool here_ok = !(pi & 4);
+            const int hb = pi & 3;
+            bool pushed = false;
+            if (pi & (right ? 8 : 16)) {
+                for (int b = stage - T_ALT0; b < 4; ++b) {
+                    if (here_ok && b == hb) continue;
+                    const int c = dfs_sel4(b, c0, c1, c2, c3);
+                    if (c >= thr) {
+                        PATH(pos) = (signed char)b;
+                        ++trial;
+                        ext = 1;
+                        STK(sp, 0) = (unsigned int)kc.code; STK(sp, 1) = (unsigned int)(kc.code >> 32);
+                        STK(sp, 2) = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)(T_ALT0 + b + 1) << 20) | (1u << 24);
+                        STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt; STK(sp, 5) = (unsigned int)bn;
+                        STK(sp, 6) = (unsigned int)thr;
+                        STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
+                        ++sp;
+                        if (right) rcx_k_append(kc, b, false, k, mask); else rcx_k_prepend(kc, b, false, k, mask);
+                        if (!right) t = thr;
+                        pos = right ? pos + 1 : pos - 1;
+                        if (here_ok) ++fix_cnt;
+                        if (c < bn) bn = c;
+                        stage = T_ENTER;
+                        pushed = true;
+                        break;
+                    }
+                }
+            }
+            if (pushed) continue;
+            stage = T_JUMP;
+        }
+        if (stage == T_JUMP) {
+            stage = T_POP;
+            if (ext == 0) {  // jump through an unfixable region (:393-441 / :629-677); last child => tail call
+                RcxKmer x = kc;
+                int i, th = thr;
+                if (right) {
+                    for (i = pos; i < to; ++i) {
+                        int d0, d1, d2, d3;
+                        dfs_probe4(a.t, x, true, mask, d0, d1, d2, d3);
+                        n_probes += 4;
+                        th = dfs_infer(d0, d1, d2, d3, t, er, lut);
+                        const int qi = pinfo[i];
+                        const bool bad = (qi & 4) != 0;
+                        rcx_k_append(x, qi & 3, bad, k, mask);
+                        const int c = bad ? 0 : dfs_sel4(qi & 3, d0, d1, d2, d3);
+                        PATH(i) = -1;
+                        if (c >= th) break;
+                    }
+                    int kk = (i < len) ? i - pos - k + 1 : (i - pos) / 2;
+                    if (kk <= 0) kk = 1;
+                    if (i >= to) i -= 1;
+                    pos = i + 1; fix_cnt += kk; kc = x;
+                } else {
+                    for (i = pos; i >= to; --i) {
+                        int d0, d1, d2, d3;
+                        dfs_probe4(a.t, x, false, mask, d0, d1, d2, d3);
+                        n_probes += 4;
+                        th = dfs_infer(d0, d1, d2, d3, t, er, lut);
+                        const int qi = pinfo[i];
+                        const bool bad = (qi & 4) != 0;
+                        rcx_k_prepend(x, qi & 3, bad, k, mask);
+                        const int c = bad ? 0 : dfs_sel4(qi & 3, d0, d1, d2, d3);
+                        PATH(i) = -1;
+                        if (c >= th) break;
+                    }
+                    int kk = (i >= 0) ? pos - i - k + 1 : pos - 1;
+                    if (kk <= 0) kk = 1;
+                    if (i <= to) ++i;
+                    pos = i - 1; fix_cnt += kk; kc = x; t = th;
+                }
+                stage = T_ENTER;
+                continue;
+            }
+        }
+        if (stage == T_POP) {
+            if (sp == 0) {
+                // ---------------- segment finished (:1162-1174)
+                st[ST_HDR + ST_SEGW * g + 5] = top2b;
+                if (best_bn == -1) {
+                    ++bad_segments;
+                } else {
+                    if (best_bn < best_bn_all) best_bn_all = best_bn;
+                    if (trial > RCX_MAX_TRIAL) abort_read = true;
+                    else total_fix += max_fix;
+                }
+                ++g;
+                stage = T_SEG;
+                continue;
+            }
+            --sp;
+            kc.code = (unsigned long long)STK(sp, 0) | ((unsigned long long)STK(sp, 1) << 32);
+            const unsigned int w = STK(sp, 2);
+            pos = (int)(w & 0xfff) - 1;
+            kc.inv = (int)((w >> 12) & 0xff) - 1;
+            stage = (int)((w >> 20) & 0xf);
+            ext = (int)((w >> 24) & 1);
+            t = (int)STK(sp, 3); fix_cnt = (int)STK(sp, 4); bn = (int)STK(sp, 5); thr = (int)STK(sp, 6);
+            c0 = (int)STK(sp, 7); c1 = (int)STK(sp, 8); c2 = (int)STK(sp, 9); c3 = (int)STK(sp, 10);
+        }
+    }
+#undef STK
+#undef PATH
+    // counters: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        n_nodes += __shfl_xor_sync(RCX_FULL, n_nodes, o);
+        n_probes += __shfl_xor_sync(RCX_FULL, n_probes, o);
+    }
+    if (lane == 0) {
+        if (n_nodes) atomicAdd(&a.counters[RCX_C_SEARCH_NODES], n_nodes);
+        if (n_probes) atomicAdd(&a.counters[RCX_C_SEARCH_PROBES], n_probes);
+    }
+}
+
+// scratch requirements of one launch
+void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel, DFS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    *grid = sm_count * per_sm;
+    int kc = max_len - k + 1;
+    if (kc < 1) kc = 1;
+    *depth = kc + 3;
+    *lpad = max_len + 2;
+}
+size_t rcx_dfs_stack_words(int grid, int depth) { return (size_t)grid * (DFS_THREADS / 32) * depth * DFS_FRAME * 32; }
+size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREADS / 32) * lpad * 32; }
+
+cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s) {
+    rcx_dfs_kernel<<<grid, DFS_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}

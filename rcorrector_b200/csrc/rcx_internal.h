@@ -13,7 +13,7 @@
 // device counters (unsigned long long each)
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
-       RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_WORKX4,  // second-pass list, per-kernel fetch counters
+       RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
        RCX_C_ROUNDS, RCX_C_FF, RCX_C_REGULAR,  // search breakdown (only with -DRCX_PHASE_TIMERS)
        RCX_C_PHASE0,                            // 8 phase cycle counters (only with -DRCX_PHASE_TIMERS)
        RCX_C_COUNT = RCX_C_PHASE0 + 8 + 5 };  // + jumps, jump cycles, rescue steps, round cycles, round levels
@@ -54,8 +54,26 @@ struct RcxCorrectArgs {
     uint32_t* worklist2;   // [n] work items that asked for a second pass of A.4
     int32_t* state;        // [n * rcx_state_words()] per work item: header, masks, segment list
     int pass;              // 0 / 1 (set by the launcher)
-    signed char* fixbuf;   // [off[n]] fix[] of reads that reach the post-filters
+    signed char* fixbuf;   // [off[n]] fix[] (bestFix of the searches), -1 = no change
+    unsigned char* posbuf; // [off[n]] per base: code | not-ACGT << 2 | substitution allowed (Right search) << 3 | (Left search) << 4
+    unsigned int* dfs_stack; // search scratch: explicit recursion stacks, interleaved by lane
+    signed char* dfs_path;   // search scratch: path[] per thread, interleaved by lane
+    int dfs_depth, dfs_lpad;
 };
+
+// per-work-item state in HBM (int32 words): 8-word header, then ST_SEGW words per segment
+#define ST_STATUS 0
+#define ST_TOTALFIX 1
+#define ST_BADSEG 2
+#define ST_STRONG 3
+#define ST_TRUST 4
+#define ST_NSEG 5
+#define ST_HDR 8
+#define ST_SEGW 6   // start | to << 16, right | maxFixCnt << 1, seed code lo, hi, seed invalidPos, top2FixBottleNeck[1]
+#define RCX_ST_SEARCH (-4)       // waiting for the search kernel
+#define RCX_ST_RETHRESHOLD (-3)  // first pass asked for a second one (forceNextRound)
+#define RCX_ST_POSTFILTER (-2)   // searches done: post-filters decide
+__host__ __device__ inline int rcx_state_stride(int max_len, int k) { return ST_HDR + ST_SEGW * (max_len / k + 4); }
 
 // table (rcx_table.cu)
 cudaError_t rcx_launch_table_init(RcxBucket* buckets, unsigned long long nbuckets, cudaStream_t s);
@@ -71,4 +89,9 @@ cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s);
 // correction (rcx_correct.cu)
 size_t rcx_correct_smem_per_warp(int max_len, int k);
 size_t rcx_state_words(int max_len, int k);
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_grid, cudaStream_t s);
+// search (rcx_dfs.cu)
+void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad);
+size_t rcx_dfs_stack_words(int grid, int depth);
+size_t rcx_dfs_path_bytes(int grid, int lpad);
+cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s);
