@@ -264,3 +264,60 @@ def parse_ref_stderr(text):
     m = re.search(r"Processed (\d+) reads\s+Corrected (\d+) bases", text)
     d["reads"], d["bases"] = (int(m.group(1)), int(m.group(2))) if m else (None, None)
     return d
+
+
+# ----------------------------------------------------------------------------- golden fixtures (tests/golden/make_golden.py)
+def golden_cases():
+    out = []
+    if os.path.isdir(GOLDEN):
+        for name in sorted(os.listdir(GOLDEN)):
+            if os.path.exists(os.path.join(GOLDEN, name, "meta.json")):
+                out.append(name)
+    return out
+
+
+def load_golden(name, workdir):
+    """Unpack one fixture into workdir; returns (meta, fastq paths, dump path, expected output bytes list)."""
+    import gzip
+    import json
+
+    d = os.path.join(GOLDEN, name)
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    w = os.path.join(workdir, "golden_" + name)
+    os.makedirs(w, exist_ok=True)
+
+    def unz(fn):
+        dst = os.path.join(w, fn[:-3])
+        if not os.path.exists(dst):
+            with gzip.open(os.path.join(d, fn), "rb") as g, open(dst, "wb") as f:
+                f.write(g.read())
+        return dst
+
+    fq = [unz(f) for f in meta["inputs"]]
+    dump = unz("reads.dump.gz")
+    import gzip as _g
+
+    expected = [_g.open(os.path.join(d, f), "rb").read() for f in meta["outputs"]]
+    return meta, fq, dump, expected
+
+
+def dump_to_arrays(path, k):
+    """Parse a Jellyfish-style text dump like main.cpp:294-308 into (forward codes, counts) for rcx_table_build."""
+    codes, counts = [], []
+    mask = (1 << (2 * k)) - 1
+    val = {"A": 0, "C": 1, "G": 2, "T": 3}
+    with open(path) as f:
+        toks = f.read().split()
+    for i in range(0, len(toks) - 1, 2):
+        c = int(toks[i][1:])
+        code = 0
+        ok = True
+        for ch in toks[i + 1]:
+            v = val.get(ch, -1)
+            if v < 0:
+                ok = False
+                v = 3
+            code = ((code << 2) | v) & mask
+        codes.append(code)
+        counts.append(c if ok else 0)
+    return np.array(codes, dtype=np.uint64), np.array(counts, dtype=np.int32)

@@ -1,0 +1,126 @@
+"""GPU: the CUDA path through the C ABI against the committed golden fixtures (bytes written by the unmodified
+reference), and the drop-in `rcorrector` binary against the same fixtures (stderr lines included)."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import rcx_testlib as T
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "rcorrector_b200", "bin", "rcorrector")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from rcorrector_b200 import Corrector
+
+    c = Corrector(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", T.golden_cases())
+def test_c_abi_reproduces_reference_bytes(gpu, name, workdir):
+    meta, fq, dump, expected = T.load_golden(name, workdir)
+    k, paired = meta["k"], meta["paired"]
+    bs = [T.read_fastq(f) for f in fq]
+    b = T.interleave(*bs) if paired else bs[0]
+    codes, counts = T.dump_to_arrays(dump, k)
+    gpu.build_table(k, codes, counts)
+    er = gpu.estimate_error_rate(codes, meta["wk"])          # main.cpp:310-358 with GPU probes
+    assert repr(er) == meta["oracle_error_rate"]
+    gpu.set_params(k, er, meta["stderr"]["bad_qual"], meta["maxcorK"])
+    so, corr, l, m, h = gpu.correct(T.INTERLEAVED if paired else T.SINGLE, b.seq, b.qual, b.off)
+    assert int(corr[corr > 0].sum()) == meta["stderr"]["bases"]
+    for i, exp in enumerate(expected):
+        rows = range(i, b.n, 2) if paired else None
+        assert T.format_fastq(b, so, corr, l, m, h, rows=rows) == exp
+
+
+def _run(args, cwd=None):
+    return subprocess.run([EXE] + args, capture_output=True, cwd=cwd)
+
+
+@pytest.mark.parametrize("name", T.golden_cases())
+def test_binary_is_a_drop_in(name, workdir):
+    """Same argv grammar, same stderr lines, same output names and bytes as the reference binary."""
+    meta, fq, dump, expected = T.load_golden(name, workdir)
+    od = os.path.join(workdir, "bin_" + name)
+    args = (["-p"] + fq if meta["paired"] else ["-r", fq[0]]) + ["-c", dump, "-k", str(meta["k"]), "-od", od, "-t", "4"] + meta["extra"]
+    r = _run(args)
+    assert r.returncode == 0, r.stderr.decode()
+    info = T.parse_ref_stderr(r.stderr.decode())
+    assert info == meta["stderr"]
+    for f, exp in zip(meta["outputs"], expected):
+        got = open(os.path.join(od, f[:-3]), "rb").read()
+        assert got == exp, f
+
+
+def test_binary_modes_match(workdir):
+    """-i interleaved == -p outputs re-interleaved; -p -stdout == same stream; .gz in -> .gz out."""
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir)
+    k = str(meta["k"])
+    w = os.path.join(workdir, "modes")
+    os.makedirs(w, exist_ok=True)
+    # interleaved file
+    a = open(fq[0], "rb").read().split(b"\n")
+    b = open(fq[1], "rb").read().split(b"\n")
+    inter = []
+    for i in range(0, len(a) - 1, 4):
+        inter += a[i:i + 4] + b[i:i + 4]
+    ipath = os.path.join(w, "inter.fq")
+    open(ipath, "wb").write(b"\n".join(inter) + b"\n")
+    e1 = expected[0].split(b"\n")
+    e2 = expected[1].split(b"\n")
+    exp_inter = []
+    for i in range(0, len(e1) - 1, 4):
+        exp_inter += e1[i:i + 4] + e2[i:i + 4]
+    exp_inter = b"\n".join(exp_inter) + b"\n"
+    r = _run(["-i", ipath, "-c", dump, "-k", k, "-od", os.path.join(w, "o1")])
+    assert r.returncode == 0, r.stderr.decode()
+    assert open(os.path.join(w, "o1", "inter.cor.fq"), "rb").read() == exp_inter
+    r = _run(["-p", fq[0], fq[1], "-c", dump, "-k", k, "-stdout", "-od", os.path.join(w, "o2")])
+    assert r.returncode == 0 and r.stdout == exp_inter
+    # gz input -> gz output at the reference's name
+    gz1 = os.path.join(w, "g_1.fq.gz")
+    with open(fq[0], "rb") as f, gzip.open(gz1, "wb") as g:
+        shutil.copyfileobj(f, g)
+    r = _run(["-r", gz1, "-c", dump, "-k", k, "-od", os.path.join(w, "o3")])
+    assert r.returncode == 0, r.stderr.decode()
+    r2 = _run(["-r", fq[0], "-c", dump, "-k", k, "-od", os.path.join(w, "o4")])
+    assert r2.returncode == 0
+    assert gzip.open(os.path.join(w, "o3", "g_1.cor.fq.gz"), "rb").read() == open(os.path.join(w, "o4", "reads_1.cor.fq"), "rb").read()
+    # two GPUs' worth of sharding logic on one device is exercised by -batch (many small device batches)
+    r = _run(["-p", fq[0], fq[1], "-c", dump, "-k", k, "-od", os.path.join(w, "o5"), "-batch", "64"])
+    assert r.returncode == 0
+    assert open(os.path.join(w, "o5", "reads_1.cor.fq"), "rb").read() == expected[0]
+    assert open(os.path.join(w, "o5", "reads_2.cor.fq"), "rb").read() == expected[1]
+
+
+def test_perl_driver_stage3(workdir):
+    """run_rcorrector.pl ... -stage 3 finds our binary next to it and produces the reference's bytes.
+    The Perl driver is part of the reference: it is copied from /root/reference at test time, only where that exists."""
+    src = "/root/reference/run_rcorrector.pl"
+    if not os.path.exists(src) or shutil.which("perl") is None:
+        pytest.skip("reference Perl driver not available on this box")
+    import hashlib
+
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir)
+    w = os.path.join(workdir, "perl")
+    os.makedirs(os.path.join(w, "tmp"), exist_ok=True)
+    shutil.copy(src, os.path.join(w, "run_rcorrector.pl"))
+    shutil.copy(EXE, os.path.join(w, "rcorrector"))
+    shutil.copy(os.path.join(ROOT, "rcorrector_b200", "librcx.so"), os.path.join(w, "librcx.so"))
+    crc = hashlib.md5(("%s %s " % (fq[0], fq[1])).encode()).hexdigest()
+    shutil.copy(dump, os.path.join(w, "tmp", "tmp_%s.jf_dump" % crc))
+    env = dict(os.environ, LD_LIBRARY_PATH=w + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run(["perl", os.path.join(w, "run_rcorrector.pl"), "-1", fq[0], "-2", fq[1], "-k", str(meta["k"]), "-od",
+                        os.path.join(w, "out"), "-tmpd", os.path.join(w, "tmp"), "-stage", "3"], capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr.decode()
+    assert open(os.path.join(w, "out", "reads_1.cor.fq"), "rb").read() == expected[0]
+    assert open(os.path.join(w, "out", "reads_2.cor.fq"), "rb").read() == expected[1]
