@@ -56,7 +56,11 @@ typedef struct {
     uint64_t rescan_probes;  /* probes of the l/m/h re-scan of changed reads */
     uint64_t search_nodes;   /* SearchPaths_* node visits */
     uint64_t kernel_launches;/* CUDA kernels launched by the call */
-    float ms_scan, ms_correct, ms_total, ms_h2d, ms_d2h; /* CUDA-event times on the context's stream */
+    float ms_scan, ms_correct, ms_total, ms_h2d, ms_d2h; /* CUDA-event times on the context's stream; ms_correct = triage..finalize */
+    float ms_triage, ms_prep, ms_dfs, ms_finalize;       /* per-kernel split of ms_correct (both passes summed) */
+    uint64_t work_items;     /* reads that needed the search (not all-trusted, not rejected) */
+    uint64_t second_pass;    /* of those, reads that took the second pass of the A.4 loop */
+    uint64_t unsupported;    /* reads that would have needed a third pass (must be 0) */
 } rcx_stats;
 
 typedef struct rcx_ctx rcx_ctx;
@@ -112,6 +116,8 @@ int rcx_scan_batch(rcx_ctx* ctx, int64_t n, const char* seq, const uint32_t* off
                    int32_t* strong_threshold_out);
 
 int rcx_get_stats(rcx_ctx* ctx, rcx_stats* out);
+/* roofline denominator: measured GB/s of independent random `sector_bytes` (32 or 64) reads over the built table */
+int rcx_measure_random_read(rcx_ctx* ctx, int sector_bytes, double* gbps);
 /* raw device counters of the last call (profiling builds add a search breakdown and per-phase cycle sums) */
 int rcx_debug_counters(rcx_ctx* ctx, uint64_t* out, int n);
 /* raw CUDA stream handle (cudaStream_t) of the context, for callers that enqueue their own copies */

@@ -19,7 +19,7 @@ SINGLE, INTERLEAVED = 0, 1
 SYMBOLS = [
     "rcx_abi_version", "rcx_last_error", "rcx_create", "rcx_destroy", "rcx_table_build", "rcx_table_lookup",
     "rcx_table_info", "rcx_set_params", "rcx_correct_batch", "rcx_correct_batch_device", "rcx_sync",
-    "rcx_scan_batch", "rcx_get_stats", "rcx_debug_counters", "rcx_stream", "rcx_host_alloc", "rcx_host_free", "rcx_estimate_error_rate",
+    "rcx_scan_batch", "rcx_get_stats", "rcx_debug_counters", "rcx_measure_random_read", "rcx_stream", "rcx_host_alloc", "rcx_host_free", "rcx_estimate_error_rate",
 ]
 
 
@@ -31,7 +31,9 @@ class RcxStats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("bases", C.c_uint64), ("scan_probes", C.c_uint64),
                 ("search_probes", C.c_uint64), ("rescan_probes", C.c_uint64), ("search_nodes", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("ms_scan", C.c_float), ("ms_correct", C.c_float),
-                ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_triage", C.c_float), ("ms_prep", C.c_float), ("ms_dfs", C.c_float), ("ms_finalize", C.c_float),
+                ("work_items", C.c_uint64), ("second_pass", C.c_uint64), ("unsupported", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -68,6 +70,7 @@ def load_library():
     lib.rcx_scan_batch.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.rcx_get_stats.argtypes = [vp, C.POINTER(RcxStats)]
     lib.rcx_debug_counters.argtypes = [vp, vp, C.c_int]
+    lib.rcx_measure_random_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.rcx_stream.argtypes = [vp]
     lib.rcx_stream.restype = vp
     lib.rcx_host_alloc.argtypes = [u64]
@@ -179,6 +182,11 @@ class Corrector:
         s = RcxStats()
         self._check(self.lib.rcx_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def measure_random_read(self, sector_bytes=32):
+        out = C.c_double()
+        self._check(self.lib.rcx_measure_random_read(self.h, sector_bytes, C.byref(out)))
+        return out.value
 
     def debug_counters(self, n=16):
         out = np.zeros(n, dtype=np.uint64)

@@ -73,6 +73,8 @@ struct rcx_ctx {
     DevBuf<unsigned int> d_dfs_stack;
     unsigned long long* d_counters = nullptr;
     cudaEvent_t ev[6]{};
+    cudaEvent_t kev[7]{};  // per-kernel marks inside the correction pipeline
+    bool kev_valid = false;
     rcx_stats stats{};
 };
 
@@ -98,6 +100,7 @@ extern "C" int rcx_create(int device, rcx_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * RCX_C_COUNT));
     CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT));
     for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+    for (auto& ev : c->kev) CUDA_TRY(cudaEventCreate(&ev));
     *out = c;
     return RCX_OK;
 }
@@ -111,6 +114,7 @@ extern "C" void rcx_destroy(rcx_ctx* c) {
     c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_worklist2.release(); c->d_state.release(); c->d_fixbuf.release(); c->d_dfs_path.release(); c->d_posbuf.release(); c->d_dfs_stack.release();
     if (c->d_counters) cudaFree(c->d_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -270,6 +274,7 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
     CUDA_TRY(rcx_launch_scan(sa, c->sm_count, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     c->stats.kernel_launches = 1;
+    c->kev_valid = false;
     if (correct) {
         RcxCorrectArgs ca;
         ca.t = sa.t;
@@ -283,7 +288,8 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
         CUDA_TRY(c->d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
         CUDA_TRY(c->d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
         ca.posbuf = c->d_posbuf.p; ca.dfs_stack = c->d_dfs_stack.p; ca.dfs_path = c->d_dfs_path.p;
-        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, c->stream));
+        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, c->stream, c->kev));
+        c->kev_valid = true;
         c->stats.kernel_launches = 7;  // scan, triage, 2 x (prep, search), finalize
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -411,7 +417,46 @@ extern "C" int rcx_get_stats(rcx_ctx* c, rcx_stats* out) {
     c->stats.ms_correct = ms(2, 3);
     c->stats.ms_d2h = ms(4, 5);
     c->stats.ms_total = ms(0, 5);
+    c->stats.ms_triage = c->stats.ms_prep = c->stats.ms_dfs = c->stats.ms_finalize = 0;
+    if (c->kev_valid) {
+        auto kms = [&](int a, int b) {
+            float v = 0;
+            if (cudaEventElapsedTime(&v, c->kev[a], c->kev[b]) != cudaSuccess) { cudaGetLastError(); v = 0; }
+            return v;
+        };
+        c->stats.ms_triage = kms(0, 1);
+        c->stats.ms_prep = kms(1, 2) + kms(3, 4);
+        c->stats.ms_dfs = kms(2, 3) + kms(4, 5);
+        c->stats.ms_finalize = kms(5, 6);
+    }
+    c->stats.work_items = h[RCX_C_NWORK];
+    c->stats.second_pass = h[RCX_C_NWORK2];
+    c->stats.unsupported = h[RCX_C_UNSUPPORTED];
     *out = c->stats;
+    return RCX_OK;
+}
+
+// Measured random-access read ceiling of this GPU over the built table: GB/s of `sector_bytes`-sized (32 or 64)
+// independent random reads (SURVEY §8d roofline denominator).
+extern "C" int rcx_measure_random_read(rcx_ctx* c, int sector_bytes, double* gbps) {
+    if (!c || !gbps) return fail(RCX_ERR_ARG, "rcx_measure_random_read: null argument");
+    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_measure_random_read: no table built");
+    if (sector_bytes != 32 && sector_bytes != 64) return fail(RCX_ERR_ARG, "rcx_measure_random_read: sector_bytes must be 32 or 64");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int grid = c->sm_count * 8;
+    const unsigned long long iters = 256;
+    unsigned long long* sink = c->d_counters + RCX_C_COUNT - 1;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        CUDA_TRY(rcx_launch_random_read(table_of(c), sector_bytes, grid, iters, sink, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *gbps = (double)grid * 256.0 * (double)iters * 8.0 * sector_bytes / (best * 1e-3) / 1e9;
     return RCX_OK;
 }
 

@@ -679,20 +679,30 @@ static cudaError_t launch_one(void (*kern)(RcxCorrectArgs), const RcxCorrectArgs
 
 size_t rcx_state_words(int max_len, int k) { return (size_t)rcx_state_stride(max_len, k); }
 
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, int dfs_grid, cudaStream_t s) {
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev) {
     if (a0.n <= 0) return cudaSuccess;
     RcxCorrectArgs a = a0;
     const size_t smem = rcx_correct_smem_per_warp(a.max_len, a.t.k) * COR_WARPS;
+    int ke = 0;
+#define MARK() do { if (kev) { cudaError_t _e = cudaEventRecord(kev[ke++], s); if (_e != cudaSuccess) return _e; } } while (0)
     a.pass = 0;
+    MARK();
     cudaError_t e = launch_one(rcx_triage_kernel, a, sm_count, a.n, smem, s);
     if (e != cudaSuccess) return e;
     // the work-list lengths live on the device: the persistent kernels read them there (no host round trip)
     for (int pass = 0; pass < 2; ++pass) {
         a.pass = pass;
+        MARK();
         e = launch_one(rcx_prep_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
         if (e != cudaSuccess) return e;
+        MARK();
         e = rcx_launch_dfs(a, dfs_grid, s);
         if (e != cudaSuccess) return e;
     }
-    return launch_one(rcx_finalize_kernel, a, sm_count, a.n, smem, s);
+    MARK();
+    e = launch_one(rcx_finalize_kernel, a, sm_count, a.n, smem, s);
+    if (e != cudaSuccess) return e;
+    MARK();
+#undef MARK
+    return cudaSuccess;
 }

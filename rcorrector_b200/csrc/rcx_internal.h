@@ -83,13 +83,15 @@ cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long nbuck
 cudaError_t rcx_launch_table_finalize(RcxBucket* buckets, unsigned long long nbuckets, const unsigned long long* vals, cudaStream_t s);
 cudaError_t rcx_launch_table_lookup(RcxTable t, const unsigned long long* codes, int32_t* out, unsigned long long n,
                                     cudaStream_t s);
+cudaError_t rcx_launch_random_read(RcxTable t, int bytes, int grid, unsigned long long iters, unsigned long long* sink, cudaStream_t s);
 // scan (rcx_scan.cu)
 size_t rcx_scan_smem_per_warp(int max_len, int k);
 cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s);
 // correction (rcx_correct.cu)
 size_t rcx_correct_smem_per_warp(int max_len, int k);
 size_t rcx_state_words(int max_len, int k);
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_grid, cudaStream_t s);
+// kev: 7 events recorded before triage, prep0, dfs0, prep1, dfs1, finalize and after finalize (may be null)
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev);
 // search (rcx_dfs.cu)
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad);
 size_t rcx_dfs_stack_words(int grid, int depth);

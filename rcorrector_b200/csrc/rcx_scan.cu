@@ -23,6 +23,42 @@ size_t rcx_scan_smem_per_warp(int max_len, int k) {
     return sizeof(unsigned int) * (size_t)(rcx_pk_words(max_len) + 4 * rcx_mask_words(max_len) + rcx_pow2_at_least(kcnt));
 }
 
+// sort the kcnt masked counts of one read in registers and pull out what GetStrongTrustedThreshold needs:
+// di = largest index i >= 1 with s[i] > 2*s[i-1] && s[i] > 10 (0 if none), thr = s[di] or the median of the positive
+// entries, below = s[di-1]
+template <int R>
+__device__ __forceinline__ void scan_sorted_summary(const int* sbuf, int kcnt, int lane, int& di, int& nonpos, int& thr, int& below) {
+    int v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = (r << 5) | lane;
+        v[r] = j < kcnt ? sbuf[j] : 0x7fffffff;
+    }
+    rcx_regsort<R>(v, lane);
+    di = 0;
+    nonpos = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = (r << 5) | lane;
+        int pv = __shfl_up_sync(RCX_FULL, v[r], 1);
+        if (r > 0) {
+            const int pl = __shfl_sync(RCX_FULL, v[r - 1], 31);
+            if (lane == 0) pv = pl;
+        }
+        if (i >= 1 && i < kcnt && v[r] > 2 * pv && v[r] > 10) di = i;
+        nonpos += (i < kcnt && v[r] <= 0) ? 1 : 0;
+    }
+    di = __reduce_max_sync(RCX_FULL, di);
+    nonpos = __reduce_add_sync(RCX_FULL, nonpos);
+    below = 0;
+    if (di >= 1) {
+        thr = rcx_regsort_get<R>(v, di);
+        below = rcx_regsort_get<R>(v, di - 1);
+    } else {
+        thr = rcx_regsort_get<R>(v, (nonpos + kcnt - 1) / 2);
+    }
+}
+
 __global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a) {
     extern __shared__ unsigned int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -91,32 +127,32 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a
             continue;
         }
         // ---- masked sort + drop search (:1540-1563)
-        const int n2 = rcx_pow2_at_least(kcnt);
-        for (int j = kcnt + lane; j < n2; j += 32) sbuf[j] = 0x7fffffff;
-        __syncwarp();
-        rcx_warp_sort(sbuf, n2, lane);
-        int di = 0, nonpos = 0;
-        for (int i = lane; i < kcnt; i += 32) {
-            const int v = sbuf[i];
-            if (i >= 1) {
-                const int pv = sbuf[i - 1];
-                if (v > 2 * pv && v > 10) di = i;  // indices ascend per lane, so the last hit is the largest
+        int thr, di = 0, nonpos = 0, below = 0;
+        if (kcnt <= 128) {
+            scan_sorted_summary<4>(sbuf, kcnt, lane, di, nonpos, thr, below);
+        } else if (kcnt <= 256) {
+            scan_sorted_summary<8>(sbuf, kcnt, lane, di, nonpos, thr, below);
+        } else {
+            const int n2 = rcx_pow2_at_least(kcnt);
+            for (int j = kcnt + lane; j < n2; j += 32) sbuf[j] = 0x7fffffff;
+            __syncwarp();
+            rcx_warp_sort(sbuf, n2, lane);
+            for (int i = lane; i < kcnt; i += 32) {
+                const int v = sbuf[i];
+                if (i >= 1) {
+                    const int pv = sbuf[i - 1];
+                    if (v > 2 * pv && v > 10) di = i;  // indices ascend per lane, so the last hit is the largest
+                }
+                nonpos += v <= 0;
             }
-            nonpos += v <= 0;
+            di = __reduce_max_sync(RCX_FULL, di);
+            nonpos = __reduce_add_sync(RCX_FULL, nonpos);
+            if (di >= 1) { thr = sbuf[di]; below = sbuf[di - 1]; }
+            else thr = sbuf[(nonpos + kcnt - 1) / 2];  // first index with a positive value == number of entries <= 0
         }
-        di = __reduce_max_sync(RCX_FULL, di);
-        nonpos = __reduce_add_sync(RCX_FULL, nonpos);
         if (lane == 0) {
-            int thr;
-            uint8_t fl = 0;
-            if (di >= 1) {
-                thr = sbuf[di];
-                fl = RCX_F_DROP | (sbuf[di - 1] == 2 ? RCX_F_PREV2 : 0);
-            } else {
-                thr = sbuf[(nonpos + kcnt - 1) / 2];  // first index with a positive value == number of entries <= 0
-            }
             a.thr[r] = thr;
-            a.flags[r] = fl;
+            a.flags[r] = di >= 1 ? (uint8_t)(RCX_F_DROP | (below == 2 ? RCX_F_PREV2 : 0)) : (uint8_t)0;
         }
         __syncwarp();
     }

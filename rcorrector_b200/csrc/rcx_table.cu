@@ -75,6 +75,44 @@ rcx_table_lookup_kernel(RcxTable t, const unsigned long long* __restrict__ codes
         out[i] = rcx_probe(t, rcx_canonical(codes[i] & kmask, t.k));
 }
 
+// Roofline micro-benchmark: independent, uniformly random 32- or 64-byte reads over the table (8 in flight per thread).
+// This is the ceiling the lookup kernel is compared with ("the random-access ceiling must be measured on the box").
+template <int BYTES>
+__global__ void __launch_bounds__(256) rcx_random_read_kernel(RcxTable t, unsigned long long iters, unsigned long long seed,
+                                                              unsigned long long* sink) {
+    unsigned long long x = seed + ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+    unsigned long long acc = 0;
+    for (unsigned long long it = 0; it < iters; ++it) {
+        unsigned long long b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x = rcx_hash(x + u + 1);
+            b[u] = __umul64hi(x, t.nbuckets);
+        }
+        unsigned long long v[8][BYTES / 8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const RcxBucket* p = t.buckets + b[u];
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(v[u][0]), "=l"(v[u][1]), "=l"(v[u][2]), "=l"(v[u][3]) : "l"(p));
+            if (BYTES == 64)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4+32];"
+                             : "=l"(v[u][BYTES / 8 - 4]), "=l"(v[u][BYTES / 8 - 3]), "=l"(v[u][BYTES / 8 - 2]), "=l"(v[u][BYTES / 8 - 1]) : "l"(p));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int w = 0; w < BYTES / 8; ++w) acc ^= v[u][w];
+    }
+    if (acc == 0x1234567887654321ull) *sink = acc;  // keep the loads alive
+}
+
+cudaError_t rcx_launch_random_read(RcxTable t, int bytes, int grid, unsigned long long iters, unsigned long long* sink, cudaStream_t s) {
+    if (bytes == 64) rcx_random_read_kernel<64><<<grid, 256, 0, s>>>(t, iters, 12345, sink);
+    else rcx_random_read_kernel<32><<<grid, 256, 0, s>>>(t, iters, 12345, sink);
+    return cudaGetLastError();
+}
+
 static inline int grid_for(unsigned long long n, int block, int cap) {
     unsigned long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
