@@ -149,9 +149,9 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     if (n >= 0xffffffffull) return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^32-2 records in one table");
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->buckets) { cudaFree(c->buckets); c->buckets = nullptr; }
-    // 5 slots per 64-byte bucket at ~1.33 keys per bucket on average (48 B of HBM per k-mer): fewer than 0.3 % of the
-    // buckets overflow, so nearly every probe -- hit or miss -- is a single 64-byte access
-    unsigned long long nb = (n * 3 + 3) / 4;
+    // 2 slots per 32-byte bucket at 0.45 keys per bucket on average (71 B of HBM per k-mer): ~1 % of the buckets
+    // overflow, so nearly every probe -- hit or miss -- is a single 32-byte sector
+    unsigned long long nb = (n * 20 + 8) / 9;
     if (nb < 1024) nb = 1024;
     CUDA_TRY(cudaMalloc(&c->buckets, nb * sizeof(RcxBucket)));
     c->nbuckets = nb;
@@ -160,8 +160,8 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     CUDA_TRY(rcx_launch_table_init(c->buckets, nb, c->stream));
     unsigned long long* d_new = nullptr;
     unsigned long long* d_vals = nullptr;  // build-time {tag:count} per slot
-    CUDA_TRY(cudaMalloc(&d_new, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(d_new, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaMalloc(&d_new, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_new, 0, 2 * sizeof(unsigned long long), c->stream));
     CUDA_TRY(cudaMalloc(&d_vals, nb * RCX_SLOTS * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(d_vals, 0, nb * RCX_SLOTS * sizeof(unsigned long long), c->stream));
     if (src_on_device) {

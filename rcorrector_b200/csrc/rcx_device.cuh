@@ -18,29 +18,35 @@
 #define RCX_MAX_TRIAL 1025                   // ErrorCorrection.cpp:7
 
 // ----------------------------------------------------------------------------- table
-// Open-addressed, bucketed.  One bucket = 64 bytes = one DRAM burst (the L2 fetches two adjacent 32-byte sectors
-// per miss on this part: measured ~64 B of dram__bytes_read per probed 32 B bucket in round 1, profiles/):
-//     u64 key[5] | u32 count[5] | u32 meta          (40 + 20 + 4 bytes)
+// Open-addressed, bucketed.  One bucket = 32 bytes = ONE DRAM sector:
+//     u64 key[2] | u32 count[2] | u64 meta            (16 + 8 + 8 bytes)
 // key = canonical code, empty = ~0 (never canonical for k <= 32: revcomp of T..T is 0); slots fill in order.
-// meta bit 0 = "overflow": some key whose HOME bucket this is lives in a later bucket.  A probe therefore ends
-// at its home bucket unless that bit is set (Poisson(1.33) >= 6 keys: < 0.3 % of buckets) -- hits AND misses cost
-// exactly one dependent memory round trip, which is what the latency-bound correction search needs.  Overflowing
-// keys continue linearly; away from home a bucket with a free slot terminates the probe.
-struct __align__(64) RcxBucket {
-    unsigned long long key[5];
-    unsigned int count[5];
-    unsigned int meta;
+// meta bit 0 = "overflow": some key whose HOME bucket this is lives in a later bucket.  A probe therefore ends at
+// its home bucket unless that bit is set (0.45 keys per bucket on average: Poisson(0.45) >= 3 keys, 1.1 % of
+// buckets) -- hits AND misses cost exactly one dependent memory round trip of one sector.
+// Why this shape (round-1 measurements, profiles/): random reads on this part are limited to ~40 G sectors/s
+// whether a probe takes 32 or 64 bytes (rcx_measure_random_read: 1.28 TB/s in both cases), so sectors per probe is
+// what counts.  Tried and measured: (a) 16-byte slots, 2 per sector, linear probing at load 0.37: 30 % of miss
+// probes needed a second DEPENDENT load; (b) one 64-byte bucket of 5 slots + overflow bit: no dependency, but 2
+// sectors per probe; (c) three 10-byte slots with 16-bit saturated counts + a side table for big counts: RNA-seq
+// reads concentrate on highly expressed k-mers, so the side lookup was hot.  (d) = this layout: exact 32-bit
+// counts inline, one sector, 71 B of HBM per k-mer (1 G k-mers = 71 GB, fits one B200).
+struct __align__(32) RcxBucket {
+    unsigned long long key[2];
+    unsigned int count[2];
+    unsigned long long meta;
 };
-#define RCX_SLOTS 5
+#define RCX_SLOTS 2
 struct RcxTable {
     const RcxBucket* buckets;
     unsigned long long nbuckets;
     int k;
 };
-// a bucket held in registers (two 256-bit loads)
+// a bucket held in registers (one 256-bit load)
 struct RcxBucketRegs {
-    unsigned long long a0, a1, a2, a3;  // key[0..3]
-    unsigned long long b0, b1, b2, b3;  // key[4], count[0..1], count[2..3], count[4] | meta << 32
+    unsigned long long a0, a1;  // key[0..1]
+    unsigned long long w;       // count[0] | count[1] << 32
+    unsigned long long meta;
 };
 
 __device__ __forceinline__ unsigned long long rcx_hash(unsigned long long x) {
@@ -66,14 +72,11 @@ __device__ __forceinline__ unsigned long long rcx_canonical(unsigned long long c
     return rc < code ? rc : code;
 }
 
-// issue the two 256-bit loads of one bucket (LDG.E.256 x2 on sm_100a; read-only path, no L1 allocation)
+// issue the 256-bit load of one bucket (LDG.E.256 on sm_100a; read-only path, no L1 allocation)
 __device__ __forceinline__ void rcx_issue(const RcxTable& t, unsigned long long b, RcxBucketRegs& d) {
     const RcxBucket* p = t.buckets + b;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(d.a0), "=l"(d.a1), "=l"(d.a2), "=l"(d.a3)
-                 : "l"(p));
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4+32];"
-                 : "=l"(d.b0), "=l"(d.b1), "=l"(d.b2), "=l"(d.b3)
+                 : "=l"(d.a0), "=l"(d.a1), "=l"(d.w), "=l"(d.meta)
                  : "l"(p));
 }
 // consume a loaded HOME bucket: Store::GetCount for a canonical key (follows the overflow chain if needed)
@@ -81,12 +84,9 @@ __device__ __forceinline__ int rcx_resolve(const RcxTable& t, unsigned long long
     unsigned long long b = home;
     bool at_home = true;
     for (;;) {
-        if (d.a0 == canon) return (int)(unsigned int)d.b1;
-        if (d.a1 == canon) return (int)(unsigned int)(d.b1 >> 32);
-        if (d.a2 == canon) return (int)(unsigned int)d.b2;
-        if (d.a3 == canon) return (int)(unsigned int)(d.b2 >> 32);
-        if (d.b0 == canon) return (int)(unsigned int)d.b3;
-        const bool more = at_home ? ((d.b3 >> 32) & 1ull) != 0 : d.b0 != RCX_EMPTY_KEY;
+        if (d.a0 == canon) return (int)(unsigned int)d.w;
+        if (d.a1 == canon) return (int)(unsigned int)(d.w >> 32);
+        const bool more = at_home ? (d.meta & 1ull) != 0 : d.a1 != RCX_EMPTY_KEY;
         if (!more) return 0;
         at_home = false;
         b = b + 1 == t.nbuckets ? 0 : b + 1;

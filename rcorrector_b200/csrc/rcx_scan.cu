@@ -15,7 +15,7 @@
 #include "rcx_internal.h"
 
 #define SCAN_WARPS 8
-#define SCAN_ILP 2
+#define SCAN_ILP 4
 
 size_t rcx_scan_smem_per_warp(int max_len, int k) {
     int kcnt = max_len - k + 1;

@@ -9,17 +9,11 @@
 #include "rcx_internal.h"
 
 __global__ void __launch_bounds__(256) rcx_table_init_kernel(uint4* p, unsigned long long nbuckets) {
-    // bucket = 4 x 16 bytes: keys (40 B) all ones, counts + meta (24 B) zero
-    const unsigned long long n = nbuckets * 4;
+    // bucket = 2 x 16 bytes: keys (16 B) all ones, counts + meta (16 B) zero
+    const unsigned long long n = nbuckets * 2;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned int q = (unsigned int)(i & 3);
-        uint4 v;
-        if (q < 2) v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        else if (q == 2) v = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
-        else v = make_uint4(0u, 0u, 0u, 0u);
-        p[i] = v;
-    }
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        p[i] = (i & 1) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
 }
 
 __global__ void __launch_bounds__(256)
@@ -49,7 +43,7 @@ rcx_table_insert_kernel(RcxBucket* buckets, unsigned long long nbuckets, unsigne
                 if (cur == key) slot = (long long)(b * RCX_SLOTS + s);
             }
             if (slot < 0) {
-                if (b == home) atomicOr(&buckets[home].meta, 1u);  // the key lives past its home bucket
+                if (b == home) atomicOr(&buckets[home].meta, 1ull);  // the key lives past its home bucket
                 b = b + 1 == nbuckets ? 0 : b + 1;
             }
         }
@@ -87,7 +81,7 @@ __global__ void __launch_bounds__(256) rcx_random_read_kernel(RcxTable t, unsign
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             x = rcx_hash(x + u + 1);
-            b[u] = __umul64hi(x, t.nbuckets);
+            b[u] = __umul64hi(x, t.nbuckets - 1) & ~1ull;  // even bucket: a 64-byte read stays inside the table and 64-byte aligned
         }
         unsigned long long v[8][BYTES / 8];
 #pragma unroll
@@ -121,7 +115,7 @@ static inline int grid_for(unsigned long long n, int block, int cap) {
 }
 
 cudaError_t rcx_launch_table_init(RcxBucket* buckets, unsigned long long nbuckets, cudaStream_t s) {
-    rcx_table_init_kernel<<<grid_for(nbuckets * 4, 256, 148 * 16), 256, 0, s>>>(reinterpret_cast<uint4*>(buckets), nbuckets);
+    rcx_table_init_kernel<<<grid_for(nbuckets * 2, 256, 148 * 16), 256, 0, s>>>(reinterpret_cast<uint4*>(buckets), nbuckets);
     return cudaGetLastError();
 }
 
