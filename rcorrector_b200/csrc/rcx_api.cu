@@ -96,6 +96,14 @@ extern "C" int rcx_create(int device, rcx_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    // The table probes are independent random 32-byte sectors: ask the L2 not to fetch neighbouring sectors from HBM
+    // (default granularity fetched ~85 B per 32-B probe, profiles/r01_e).  RCX_L2_FETCH=64|128 overrides (a hint).
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("RCX_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * RCX_C_COUNT));
     CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT));

@@ -29,20 +29,23 @@ enum { T_FETCH = 0, T_SEG = 1, T_ENTER = 2, T_ALT0 = 3 /* ..T_ALT0+3 */, T_JUMP 
 
 __device__ __forceinline__ int dfs_sel4(int b, int c0, int c1, int c2, int c3) { return b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3; }
 
-// counts of the 4 one-base extensions of kc: 4 independent bucket probes per thread, two in flight at a time
+// counts of the 4 one-base extensions of kc: DFS_ILP independent one-sector bucket probes per thread in flight
+#ifndef DFS_ILP
+#define DFS_ILP 2
+#endif
 __device__ __noinline__ void dfs_probe4(const RcxTable& t, const RcxKmer& kc, bool right, unsigned long long mask, int& c0, int& c1,
-                                           int& c2, int& c3) {
+                                        int& c2, int& c3) {
     int c[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        unsigned long long canon[2], home[2];
-        RcxBucketRegs d[2];
-        bool live[2];
+    for (int h = 0; h < 4 / DFS_ILP; ++h) {
+        unsigned long long canon[DFS_ILP], home[DFS_ILP];
+        RcxBucketRegs d[DFS_ILP];
+        bool live[DFS_ILP];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < DFS_ILP; ++u) {
             RcxKmer x = kc;
-            if (right) rcx_k_append(x, 2 * h + u, false, t.k, mask);
-            else rcx_k_prepend(x, 2 * h + u, false, t.k, mask);
+            if (right) rcx_k_append(x, DFS_ILP * h + u, false, t.k, mask);
+            else rcx_k_prepend(x, DFS_ILP * h + u, false, t.k, mask);
             live[u] = x.inv == -1;
             if (live[u]) {
                 canon[u] = rcx_canonical(x.code, t.k);
@@ -51,7 +54,7 @@ __device__ __noinline__ void dfs_probe4(const RcxTable& t, const RcxKmer& kc, bo
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) c[2 * h + u] = live[u] ? rcx_resolve(t, canon[u], home[u], d[u]) : 0;
+        for (int u = 0; u < DFS_ILP; ++u) c[DFS_ILP * h + u] = live[u] ? rcx_resolve(t, canon[u], home[u], d[u]) : 0;
     }
     c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3];
 }

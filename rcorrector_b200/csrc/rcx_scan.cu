@@ -15,7 +15,7 @@
 #include "rcx_internal.h"
 
 #define SCAN_WARPS 8
-#define SCAN_ILP 4
+#define SCAN_ILP 2
 
 size_t rcx_scan_smem_per_warp(int max_len, int k) {
     int kcnt = max_len - k + 1;
@@ -59,7 +59,7 @@ __device__ __forceinline__ void scan_sorted_summary(const int* sbuf, int kcnt, i
     }
 }
 
-__global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a) {
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 4) rcx_scan_kernel(RcxScanArgs a) {
     extern __shared__ unsigned int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = a.t.k;
@@ -130,9 +130,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) rcx_scan_kernel(RcxScanArgs a
         int thr, di = 0, nonpos = 0, below = 0;
         if (kcnt <= 128) {
             scan_sorted_summary<4>(sbuf, kcnt, lane, di, nonpos, thr, below);
-        } else if (kcnt <= 256) {
-            scan_sorted_summary<8>(sbuf, kcnt, lane, di, nonpos, thr, below);
-        } else {
+        } else {  // longer reads: shared-memory network (keeps the common path at 4 sort registers per lane)
             const int n2 = rcx_pow2_at_least(kcnt);
             for (int j = kcnt + lane; j < n2; j += 32) sbuf[j] = 0x7fffffff;
             __syncwarp();
