@@ -54,9 +54,13 @@ struct rcx_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     // table
-    RcxBucket* buckets = nullptr;
-    unsigned long long nbuckets = 0;
-    unsigned long long entries = 0;
+    RcxEntry* entries_dev = nullptr;     // the table: nlines * 4 sectors of 32 bytes
+    unsigned long long nlines = 0;
+    unsigned long long entries = 0;      // distinct canonical k-mers stored
+    unsigned long long contexts = 0;     // distinct (k-1)-mer contexts = occupied sectors
+    unsigned long long* big_keys = nullptr;
+    unsigned int* big_counts = nullptr;
+    int nbig = 0;
     int k = 0;
     // params
     rcx_params params{};
@@ -113,11 +117,13 @@ extern "C" int rcx_create(int device, rcx_ctx** out) {
     return RCX_OK;
 }
 
+static void free_table(rcx_ctx* c);
+
 extern "C" void rcx_destroy(rcx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->buckets) cudaFree(c->buckets);
+    free_table(c);
     c->d_seq.release(); c->d_qual.release(); c->d_off.release(); c->d_counts.release(); c->d_thr.release();
     c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_worklist2.release(); c->d_state.release(); c->d_fixbuf.release(); c->d_dfs_path.release(); c->d_posbuf.release(); c->d_dfs_stack.release();
     if (c->d_counters) cudaFree(c->d_counters);
@@ -149,6 +155,15 @@ extern "C" int rcx_sync(rcx_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------------ table
+static void free_table(rcx_ctx* c) {
+    if (c->entries_dev) { cudaFree(c->entries_dev); c->entries_dev = nullptr; }
+    if (c->big_keys) { cudaFree(c->big_keys); c->big_keys = nullptr; }
+    if (c->big_counts) { cudaFree(c->big_counts); c->big_counts = nullptr; }
+    c->nbig = 0;
+    c->nlines = 0;
+    c->entries = 0;
+}
+
 extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, const int32_t* counts, uint64_t n,
                                int src_on_device) {
     if (!c) return fail(RCX_ERR_ARG, "rcx_table_build: null context");
@@ -156,63 +171,154 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     if (n && (!fwd_codes || !counts)) return fail(RCX_ERR_ARG, "rcx_table_build: null input arrays");
     if (n >= 0xffffffffull) return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^32-2 records in one table");
     CUDA_TRY(cudaSetDevice(c->device));
-    if (c->buckets) { cudaFree(c->buckets); c->buckets = nullptr; }
-    // 2 slots per 32-byte bucket at 0.45 keys per bucket on average (71 B of HBM per k-mer): ~1 % of the buckets
-    // overflow, so nearly every probe -- hit or miss -- is a single 32-byte sector
-    unsigned long long nb = (n * 20 + 8) / 9;
-    if (nb < 1024) nb = 1024;
-    CUDA_TRY(cudaMalloc(&c->buckets, nb * sizeof(RcxBucket)));
-    c->nbuckets = nb;
+    free_table(c);
     c->k = k;
-    c->entries = 0;
-    CUDA_TRY(rcx_launch_table_init(c->buckets, nb, c->stream));
-    unsigned long long* d_new = nullptr;
-    unsigned long long* d_vals = nullptr;  // build-time {tag:count} per slot
-    CUDA_TRY(cudaMalloc(&d_new, 2 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(d_new, 0, 2 * sizeof(unsigned long long), c->stream));
-    CUDA_TRY(cudaMalloc(&d_vals, nb * RCX_SLOTS * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(d_vals, 0, nb * RCX_SLOTS * sizeof(unsigned long long), c->stream));
+    // One 32-byte entry per distinct (k-1)-mer context.  A transcriptome / genome has about as many contexts as k-mers
+    // (the de Bruijn graph is mostly linear paths); unrelated random k-mers have two each.  Start from contexts ~ n at
+    // the target load and grow if the claim pass says otherwise.
+    double load = 0.40;  // entries per sector: ~82 % of the stored contexts sit in their home sector
+    if (const char* e = getenv("RCX_TABLE_LOAD")) load = atof(e);
+    if (!(load >= 0.05 && load <= 0.70)) load = 0.40;
+    unsigned long long nlines = (unsigned long long)((double)n * 1.02 / load / 4.0) + 64;
+
+    // records: device-resident if they are (or fit), else streamed through a bounded staging area for every pass
+    const unsigned long long* d_codes_all = nullptr;
+    const int32_t* d_counts_all = nullptr;
+    unsigned long long* own_codes = nullptr;
+    int32_t* own_counts = nullptr;
+    const uint64_t chunk = 1ull << 24;
     if (src_on_device) {
-        CUDA_TRY(rcx_launch_table_insert(c->buckets, nb, d_vals, k, (const unsigned long long*)fwd_codes, counts, n, 0, d_new, c->stream));
+        d_codes_all = (const unsigned long long*)fwd_codes;
+        d_counts_all = counts;
     } else {
-        // stream the records through a bounded device staging area
-        const uint64_t chunk = 1ull << 24;
-        unsigned long long* d_codes = nullptr;
-        int32_t* d_cnt = nullptr;
-        const uint64_t m = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
-        CUDA_TRY(cudaMalloc(&d_codes, m * sizeof(unsigned long long)));
-        CUDA_TRY(cudaMalloc(&d_cnt, m * sizeof(int32_t)));
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t m = (n * 12 <= free_b / 4) ? std::max<uint64_t>(n, 1) : std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
+        CUDA_TRY(cudaMalloc(&own_codes, m * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&own_counts, m * sizeof(int32_t)));
+        if (m >= n) {
+            CUDA_TRY(cudaMemcpyAsync(own_codes, fwd_codes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(own_counts, counts, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            d_codes_all = own_codes;
+            d_counts_all = own_counts;
+        }
+    }
+    // run `fn(codes, counts, len, first_index)` over all records
+    auto for_records = [&](auto fn) -> int {
+        if (d_codes_all) return fn(d_codes_all, d_counts_all, (unsigned long long)n, 0ull);
         for (uint64_t s = 0; s < n; s += chunk) {
             const uint64_t len = std::min<uint64_t>(chunk, n - s);
-            CUDA_TRY(cudaMemcpyAsync(d_codes, fwd_codes + s, len * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(d_cnt, counts + s, len * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(rcx_launch_table_insert(c->buckets, nb, d_vals, k, d_codes, d_cnt, len, s, d_new, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(own_codes, fwd_codes + s, len * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(own_counts, counts + s, len * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            int rc = fn(own_codes, own_counts, (unsigned long long)len, (unsigned long long)s);
+            if (rc) return rc;
             CUDA_TRY(cudaStreamSynchronize(c->stream));
         }
-        cudaFree(d_codes);
-        cudaFree(d_cnt);
+        return RCX_OK;
+    };
+    unsigned long long* d_stat = nullptr;  // [0] contexts claimed, [1] abort flag, [2] distinct k-mers, [3] saturated counts
+    CUDA_TRY(cudaMalloc(&d_stat, 4 * sizeof(unsigned long long)));
+    unsigned long long h_stat[4] = {0, 0, 0, 0};
+    RcxEntry* e = nullptr;
+    for (int attempt = 0;; ++attempt) {
+        CUDA_TRY(cudaMalloc(&e, nlines * 4 * sizeof(RcxEntry)));
+        CUDA_TRY(rcx_launch_table_init(e, nlines, c->stream));
+        CUDA_TRY(cudaMemsetAsync(d_stat, 0, 4 * sizeof(unsigned long long), c->stream));
+        const unsigned long long limit = (unsigned long long)(0.75 * 4.0 * (double)nlines);
+        for (int home_only = 1; home_only >= 0; --home_only) {
+            int rc = for_records([&](const unsigned long long* dc, const int32_t* dn, unsigned long long len, unsigned long long) -> int {
+                CUDA_TRY(rcx_launch_table_claim(e, nlines, k, dc, dn, len, home_only, d_stat, limit, c->stream));
+                return RCX_OK;
+            });
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h_stat, d_stat, sizeof h_stat, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const double fill = (double)h_stat[0] / (4.0 * (double)nlines);
+        if (!h_stat[1] && (fill <= load * 1.5 || attempt >= 3)) break;
+        // more contexts than assumed: size for what was seen (an aborted pass saw at least 75 % of the sectors)
+        cudaFree(e);
+        e = nullptr;
+        const unsigned long long seen = h_stat[1] ? std::max<unsigned long long>(h_stat[0], 2 * (unsigned long long)n) : h_stat[0];
+        nlines = (unsigned long long)((double)seen / load / 4.0) + 64;
+        if (attempt >= 4) return fail(RCX_ERR_NOMEM, "rcx_table_build: could not size the table");
     }
-    CUDA_TRY(rcx_launch_table_finalize(c->buckets, nb, d_vals, c->stream));
-    unsigned long long h_new = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h_new, d_new, sizeof h_new, cudaMemcpyDeviceToHost, c->stream));
+    // "last record wins" per count slot, one partition of the table at a time (the side array is as large as the
+    // sectors it covers, so it is cut to what is free)
+    const unsigned long long nsec = nlines * 4;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    unsigned long long part = nsec;
+    const unsigned long long afford = (unsigned long long)(free_b * 0.6) / 32;
+    if (part > afford) part = std::max<unsigned long long>(afford, 1ull << 16);
+    unsigned int* d_win = nullptr;
+    CUDA_TRY(cudaMalloc(&d_win, part * 32));
+    const unsigned long long big_cap = 1ull << 20;
+    unsigned long long* d_big_keys = nullptr;
+    unsigned int* d_big_counts = nullptr;
+    CUDA_TRY(cudaMalloc(&d_big_keys, big_cap * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d_big_counts, big_cap * sizeof(unsigned int)));
+    for (unsigned long long lo = 0; lo < nsec; lo += part) {
+        const unsigned long long hi = std::min(nsec, lo + part);
+        CUDA_TRY(cudaMemsetAsync(d_win, 0, (hi - lo) * 32, c->stream));
+        for (int write = 0; write < 2; ++write) {
+            int rc = for_records([&](const unsigned long long* dc, const int32_t* dn, unsigned long long len, unsigned long long first) -> int {
+                CUDA_TRY(rcx_launch_table_fill(e, nlines, k, dc, dn, len, first, d_win, lo, hi, write, d_stat, d_big_keys, d_big_counts, big_cap,
+                                               c->stream));
+                return RCX_OK;
+            });
+            if (rc) return rc;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_stat, d_stat, sizeof h_stat, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(d_new);
-    cudaFree(d_vals);
-    c->entries = h_new;
+    cudaFree(d_win);
+    cudaFree(d_stat);
+    if (own_codes) cudaFree(own_codes);
+    if (own_counts) cudaFree(own_counts);
+    if (h_stat[3] > big_cap) {
+        cudaFree(e); cudaFree(d_big_keys); cudaFree(d_big_counts);
+        return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^20 k-mers with a count >= 2^24-1");
+    }
+    // exact counts of the saturated 24-bit fields: sorted side list, binary-searched on the device
+    c->nbig = (int)h_stat[3];
+    if (c->nbig > 0) {
+        std::vector<unsigned long long> bk(c->nbig);
+        std::vector<unsigned int> bc(c->nbig);
+        CUDA_TRY(cudaMemcpy(bk.data(), d_big_keys, c->nbig * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(bc.data(), d_big_counts, c->nbig * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        std::vector<int> order(c->nbig);
+        for (int i = 0; i < c->nbig; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return bk[a] < bk[b]; });
+        std::vector<unsigned long long> sk(c->nbig);
+        std::vector<unsigned int> sc(c->nbig);
+        for (int i = 0; i < c->nbig; ++i) { sk[i] = bk[order[i]]; sc[i] = bc[order[i]]; }
+        CUDA_TRY(cudaMemcpy(d_big_keys, sk.data(), c->nbig * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_big_counts, sc.data(), c->nbig * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    }
+    c->big_keys = d_big_keys;
+    c->big_counts = d_big_counts;
+    c->entries_dev = e;
+    c->nlines = nlines;
+    c->entries = h_stat[2];
+    c->contexts = h_stat[0];
     return RCX_OK;
 }
 
 static RcxTable table_of(const rcx_ctx* c) {
     RcxTable t;
-    t.buckets = c->buckets;
-    t.nbuckets = c->nbuckets;
+    t.e = c->entries_dev;
+    t.nlines = c->nlines;
     t.k = c->k;
+    t.big_keys = c->big_keys;
+    t.big_counts = c->big_counts;
+    t.nbig = c->nbig;
     return t;
 }
 
 extern "C" int rcx_table_lookup(rcx_ctx* c, const uint64_t* fwd_codes, int32_t* counts_out, uint64_t n) {
     if (!c) return fail(RCX_ERR_ARG, "rcx_table_lookup: null context");
-    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_table_lookup: no table built");
+    if (!c->entries_dev) return fail(RCX_ERR_STATE, "rcx_table_lookup: no table built");
     if (n && (!fwd_codes || !counts_out)) return fail(RCX_ERR_ARG, "rcx_table_lookup: null arrays");
     CUDA_TRY(cudaSetDevice(c->device));
     const uint64_t chunk = 1ull << 24;
@@ -236,8 +342,8 @@ extern "C" int rcx_table_lookup(rcx_ctx* c, const uint64_t* fwd_codes, int32_t* 
 extern "C" int rcx_table_info(rcx_ctx* c, uint64_t* entries, uint64_t* slots, uint64_t* bytes) {
     if (!c) return fail(RCX_ERR_ARG, "rcx_table_info: null context");
     if (entries) *entries = c->entries;
-    if (slots) *slots = c->nbuckets * RCX_SLOTS;
-    if (bytes) *bytes = c->nbuckets * sizeof(RcxBucket);
+    if (slots) *slots = c->nlines * 4;  // one context entry per 32-byte sector
+    if (bytes) *bytes = c->nlines * 4 * sizeof(RcxEntry);
     return RCX_OK;
 }
 
@@ -254,7 +360,7 @@ extern "C" int rcx_set_params(rcx_ctx* c, const rcx_params* p) {
 // ------------------------------------------------------------------------------------------------ hot path
 static int check_ready(const rcx_ctx* c, const char* who) {
     if (!c) return fail(RCX_ERR_ARG, std::string(who) + ": null context");
-    if (!c->buckets) return fail(RCX_ERR_STATE, std::string(who) + ": no table built (rcx_table_build)");
+    if (!c->entries_dev) return fail(RCX_ERR_STATE, std::string(who) + ": no table built (rcx_table_build)");
     if (!c->have_params) return fail(RCX_ERR_STATE, std::string(who) + ": parameters not set (rcx_set_params)");
     if (c->params.k != c->k) return fail(RCX_ERR_STATE, std::string(who) + ": params.k differs from the table's k");
     return RCX_OK;
@@ -379,7 +485,7 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
 extern "C" int rcx_scan_batch(rcx_ctx* c, int64_t n, const char* seq, const uint32_t* off, int32_t* counts_out,
                               int32_t* strong_threshold_out) {
     if (!c) return fail(RCX_ERR_ARG, "rcx_scan_batch: null context");
-    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_scan_batch: no table built");
+    if (!c->entries_dev) return fail(RCX_ERR_STATE, "rcx_scan_batch: no table built");
     if (n <= 0) return n == 0 ? RCX_OK : fail(RCX_ERR_ARG, "rcx_scan_batch: n < 0");
     if (!seq || !off || !counts_out || !strong_threshold_out) return fail(RCX_ERR_ARG, "rcx_scan_batch: null pointer");
     int32_t max_len = 0;
@@ -448,7 +554,7 @@ extern "C" int rcx_get_stats(rcx_ctx* c, rcx_stats* out) {
 // independent random reads (SURVEY §8d roofline denominator).
 extern "C" int rcx_measure_random_read(rcx_ctx* c, int sector_bytes, double* gbps) {
     if (!c || !gbps) return fail(RCX_ERR_ARG, "rcx_measure_random_read: null argument");
-    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_measure_random_read: no table built");
+    if (!c->entries_dev) return fail(RCX_ERR_STATE, "rcx_measure_random_read: no table built");
     if (sector_bytes != 32 && sector_bytes != 64) return fail(RCX_ERR_ARG, "rcx_measure_random_read: sector_bytes must be 32 or 64");
     CUDA_TRY(cudaSetDevice(c->device));
     const int grid = c->sm_count * 8;
@@ -482,22 +588,24 @@ extern "C" int rcx_debug_counters(rcx_ctx* c, uint64_t* out, int n) {
 // ------------------------------------------------------------------------------------------------ ERROR_RATE (main.cpp:310-358)
 extern "C" int rcx_estimate_error_rate(rcx_ctx* c, const uint64_t* fwd_codes, uint64_t n, double wk, double* out) {
     if (!c || !out) return fail(RCX_ERR_ARG, "rcx_estimate_error_rate: null argument");
-    if (!c->buckets) return fail(RCX_ERR_STATE, "rcx_estimate_error_rate: no table built");
-    const int k = c->k;
+    if (!c->entries_dev) return fail(RCX_ERR_STATE, "rcx_estimate_error_rate: no table built");
     const uint64_t cap = 100000;
     std::vector<double> rates;
     rates.reserve(cap + 1);
+    CUDA_TRY(cudaSetDevice(c->device));
     const uint64_t chunk = 1ull << 20;
-    std::vector<uint64_t> var;
-    std::vector<int32_t> cnt;
+    std::vector<int32_t> cnt(4 * std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1)));
+    unsigned long long* d_codes = nullptr;
+    int32_t* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_codes, cnt.size() / 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d_out, cnt.size() * sizeof(int32_t)));
     for (uint64_t s = 0; s < n && rates.size() < cap; s += chunk) {
         const uint64_t len = std::min<uint64_t>(chunk, n - s);
-        var.resize(len * 4);
-        cnt.resize(len * 4);
-        for (uint64_t i = 0; i < len; ++i)
-            for (uint64_t b = 0; b < 4; ++b) var[4 * i + b] = (fwd_codes[s + i] & ~3ull) | b;  // ShiftRight(1) + Append(b)
-        int rc = rcx_table_lookup(c, var.data(), cnt.data(), len * 4);
-        if (rc) return rc;
+        // the 4 last-base variants of a record (ShiftRight(1) + Append(b), main.cpp:327-331) share one context: one lookup
+        CUDA_TRY(cudaMemcpyAsync(d_codes, fwd_codes + s, len * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(rcx_launch_table_lookup4(table_of(c), d_codes, d_out, len, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_out, len * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
         for (uint64_t i = 0; i < len && rates.size() < cap; ++i) {
             int best = 0, second = 0;
             for (int b = 0; b < 4; ++b) {
@@ -509,7 +617,8 @@ extern "C" int rcx_estimate_error_rate(rcx_ctx* c, const uint64_t* fwd_codes, ui
             rates.push_back((double)second / (double)best);
         }
     }
-    (void)k;
+    cudaFree(d_codes);
+    cudaFree(d_out);
     double er = 0;
     const size_t kq = rates.size();
     if (kq > 0) {

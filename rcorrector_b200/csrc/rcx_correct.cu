@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
                 if ((rcx_bits(M.fixm, j) & kmask32) == 0) continue;
                 int c = 0;
                 if ((rcx_bits(M.P.inv, j) & kmask32) == 0) {
-                    c = rcx_probe_ool(a.t, rcx_canonical(rcx_window(M.P.pk, j, k), k));
+                    c = rcx_probe_kmer_ool(a.t, rcx_window(M.P.pk, j, k));
                     ++n_rprobes;
                 }
                 M.counts[j] = c;

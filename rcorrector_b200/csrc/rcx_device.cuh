@@ -18,35 +18,47 @@
 #define RCX_MAX_TRIAL 1025                   // ErrorCorrection.cpp:7
 
 // ----------------------------------------------------------------------------- table
-// Open-addressed, bucketed.  One bucket = 32 bytes = ONE DRAM sector:
-//     u64 key[2] | u32 count[2] | u64 meta            (16 + 8 + 8 bytes)
-// key = canonical code, empty = ~0 (never canonical for k <= 32: revcomp of T..T is 0); slots fill in order.
-// meta bit 0 = "overflow": some key whose HOME bucket this is lives in a later bucket.  A probe therefore ends at
-// its home bucket unless that bit is set (0.45 keys per bucket on average: Poisson(0.45) >= 3 keys, 1.1 % of
-// buckets) -- hits AND misses cost exactly one dependent memory round trip of one sector.
-// Why this shape (round-1 measurements, profiles/): random reads on this part are limited to ~40 G sectors/s
-// whether a probe takes 32 or 64 bytes (rcx_measure_random_read: 1.28 TB/s in both cases), so sectors per probe is
-// what counts.  Tried and measured: (a) 16-byte slots, 2 per sector, linear probing at load 0.37: 30 % of miss
-// probes needed a second DEPENDENT load; (b) one 64-byte bucket of 5 slots + overflow bit: no dependency, but 2
-// sectors per probe; (c) three 10-byte slots with 16-bit saturated counts + a side table for big counts: RNA-seq
-// reads concentrate on highly expressed k-mers, so the side lookup was hot.  (d) = this layout: exact 32-bit
-// counts inline, one sector, 71 B of HBM per k-mer (1 G k-mers = 71 GB, fits one B200).
-struct __align__(32) RcxBucket {
-    unsigned long long key[2];
-    unsigned int count[2];
-    unsigned long long meta;
+// The table is keyed by (k-1)-mer CONTEXTS, not by k-mers.  One entry = 32 bytes = ONE L2 sector:
+//     u64 key | u32 cw[6]
+// key = canonical (k-1)-mer code (<= 62 bits) | overflow << 63; empty = ~0.
+// cw[0..2] = RIGHT group: counts of the four k-mers  key+b  (b = A,C,G,T appended),
+// cw[3..5] = LEFT  group: counts of the four k-mers  b+key  (b prepended);
+// a group packs four 24-bit counts: word i = count_i | (byte i of count_3) << 24.  A count >= 0xFFFFFF is stored as
+// 0xFFFFFF and resolved exactly through a (tiny, sorted) side list of canonical k-mers.
+// Every stored k-mer appears twice: as a right extension of its prefix context and as a left extension of its suffix
+// context (both normalised to the canonical strand of the context).
+//
+// Why this shape (measured on the B200, profiles/r01_f_membench*): (1) an L2 miss always fetches the whole 128-byte
+// line from HBM, whatever the request size or cudaLimitMaxL2FetchGranularity; (2) independent random requests over a
+// footprint > 1 GiB top out at ~45 G requests/s (TLB-miss / DRAM-line rate), whether a request is 16, 32 or 2 x 32
+// bytes.  So the currency is REQUESTS, and a request should answer as many of the path's questions as possible:
+//   * the scan needs count(window j) for consecutive j: windows j-1 and j share the context seq[j .. j+k-1), so ONE
+//     sector answers two windows (left extension by seq[j-1], right extension by seq[j+k-1]);
+//   * a search node needs the counts of the four one-base extensions of its k-mer (InferPosThreshold, the keep-base
+//     test and the three alternatives): they share one context, so ONE sector answers the node (the k-mer-keyed
+//     table of the first round needed four).
+// Probe sequence of a key with home sector h: the four sectors of h's 128-byte line first (h, h^1, h^2, h^3: a second
+// probe is an L2 hit, the line is already there), then the following lines.  Keys are placed home-first (every home
+// sector that has a candidate gets one), the overflow bit of a home sector says that a key homed there lives further
+// on, so a lookup -- hit or miss -- ends at its home sector unless that bit is set.
+struct __align__(32) RcxEntry {
+    unsigned long long key;
+    unsigned int cw[6];
 };
-#define RCX_SLOTS 2
+#define RCX_KEY_MASK 0x7fffffffffffffffull
+#define RCX_OVERFLOW_BIT 0x8000000000000000ull
+#define RCX_BIG 0xffffffu
 struct RcxTable {
-    const RcxBucket* buckets;
-    unsigned long long nbuckets;
+    const RcxEntry* e;
+    unsigned long long nlines;   // 128-byte lines; sectors = 4 * nlines
     int k;
+    const unsigned long long* big_keys;  // sorted canonical k-mers whose count >= RCX_BIG
+    const unsigned int* big_counts;
+    int nbig;
 };
-// a bucket held in registers (one 256-bit load)
-struct RcxBucketRegs {
-    unsigned long long a0, a1;  // key[0..1]
-    unsigned long long w;       // count[0] | count[1] << 32
-    unsigned long long meta;
+// an entry held in registers (one 256-bit load)
+struct RcxEntryRegs {
+    unsigned long long q0, q1, q2, q3;  // key, cw0|cw1<<32, cw2|cw3<<32, cw4|cw5<<32
 };
 
 __device__ __forceinline__ unsigned long long rcx_hash(unsigned long long x) {
@@ -57,48 +69,110 @@ __device__ __forceinline__ unsigned long long rcx_hash(unsigned long long x) {
     x ^= x >> 32;
     return x;
 }
-__device__ __forceinline__ unsigned long long rcx_home(const RcxTable& t, unsigned long long canon) {
-    return __umul64hi(rcx_hash(canon), t.nbuckets);  // uniform over [0, nbuckets) without a power-of-two table
-}
 
-// reverse complement of a k-mer code (A0 C1 G2 T3 => complement is 3-x = ~x on 2 bits)
-__device__ __forceinline__ unsigned long long rcx_revcomp(unsigned long long code, int k) {
+// reverse complement of an n-base code (A0 C1 G2 T3 => complement is 3-x = ~x on 2 bits), 1 <= n <= 32
+__device__ __forceinline__ unsigned long long rcx_revcomp(unsigned long long code, int n) {
     unsigned long long r = __brevll(code);                                                  // reverses bits, also inside pairs
     r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);            // restore pair order
-    return (~r) >> (64 - 2 * k);
+    return (~r) >> (64 - 2 * n);
 }
 __device__ __forceinline__ unsigned long long rcx_canonical(unsigned long long code, int k) {
     unsigned long long rc = rcx_revcomp(code, k);
     return rc < code ? rc : code;
 }
 
-// issue the 256-bit load of one bucket (LDG.E.256 on sm_100a; read-only path, no L1 allocation)
-__device__ __forceinline__ void rcx_issue(const RcxTable& t, unsigned long long b, RcxBucketRegs& d) {
-    const RcxBucket* p = t.buckets + b;
+// sector index of probe number i of a key whose home sector is h
+__device__ __forceinline__ unsigned long long rcx_probe_sector(const RcxTable& t, unsigned long long h, unsigned int i) {
+    unsigned long long line = (h >> 2) + (i >> 2);
+    if (line >= t.nlines) line -= t.nlines;
+    return (line << 2) | ((h ^ i) & 3);
+}
+// issue the 256-bit load of one entry (LDG.E.256 on sm_100a; read-only path, no L1 allocation)
+__device__ __forceinline__ void rcx_issue(const RcxTable& t, unsigned long long sector, RcxEntryRegs& d) {
+    const RcxEntry* p = t.e + sector;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(d.a0), "=l"(d.a1), "=l"(d.w), "=l"(d.meta)
+                 : "=l"(d.q0), "=l"(d.q1), "=l"(d.q2), "=l"(d.q3)
                  : "l"(p));
 }
-// consume a loaded HOME bucket: Store::GetCount for a canonical key (follows the overflow chain if needed)
-__device__ __forceinline__ int rcx_resolve(const RcxTable& t, unsigned long long canon, unsigned long long home, RcxBucketRegs& d) {
-    unsigned long long b = home;
-    bool at_home = true;
-    for (;;) {
-        if (d.a0 == canon) return (int)(unsigned int)d.w;
-        if (d.a1 == canon) return (int)(unsigned int)(d.w >> 32);
-        const bool more = at_home ? (d.meta & 1ull) != 0 : d.a1 != RCX_EMPTY_KEY;
-        if (!more) return 0;
-        at_home = false;
-        b = b + 1 == t.nbuckets ? 0 : b + 1;
-        rcx_issue(t, b, d);
+// one context lookup in flight
+struct RcxLookup {
+    unsigned long long key, home;
+    bool flip;  // the caller's orientation is the reverse complement of the stored key
+    RcxEntryRegs d;
+};
+// ctx = code of the (k-1)-mer in the caller's orientation
+__device__ __forceinline__ void rcx_lookup_begin(const RcxTable& t, unsigned long long ctx, RcxLookup& L) {
+    const unsigned long long rc = rcx_revcomp(ctx, t.k - 1);
+    L.flip = rc < ctx;
+    L.key = L.flip ? rc : ctx;
+    L.home = __umul64hi(rcx_hash(L.key), t.nlines << 2);  // uniform over the sectors without a power-of-two table
+    rcx_issue(t, L.home, L.d);
+}
+// finish: true if the context is stored (L.d then holds its entry)
+__device__ __forceinline__ bool rcx_lookup_end(const RcxTable& t, RcxLookup& L) {
+    if ((L.d.q0 & RCX_KEY_MASK) == L.key) return true;
+    if (L.d.q0 == ~0ull || !(L.d.q0 & RCX_OVERFLOW_BIT)) return false;
+    for (unsigned int i = 1;; ++i) {  // rare: a key homed here lives further along the probe sequence
+        rcx_issue(t, rcx_probe_sector(t, L.home, i), L.d);
+        if (L.d.q0 == ~0ull) return false;
+        if ((L.d.q0 & RCX_KEY_MASK) == L.key) return true;
+        if (i >= 4 * t.nlines) return false;
     }
 }
-// Store::GetCount for a canonical key.
-__device__ __forceinline__ int rcx_probe(const RcxTable& t, unsigned long long canon) {
-    const unsigned long long home = rcx_home(t, canon);
-    RcxBucketRegs d;
-    rcx_issue(t, home, d);
-    return rcx_resolve(t, canon, home, d);
+// the four 24-bit fields of the stored RIGHT (left = false) or LEFT group
+__device__ __forceinline__ void rcx_group(const RcxEntryRegs& d, bool left, unsigned int& f0, unsigned int& f1, unsigned int& f2, unsigned int& f3) {
+    const unsigned int x0 = left ? (unsigned int)(d.q2 >> 32) : (unsigned int)d.q1;
+    const unsigned int x1 = left ? (unsigned int)d.q3 : (unsigned int)(d.q1 >> 32);
+    const unsigned int x2 = left ? (unsigned int)(d.q3 >> 32) : (unsigned int)d.q2;
+    f0 = x0 & RCX_BIG; f1 = x1 & RCX_BIG; f2 = x2 & RCX_BIG;
+    f3 = (x0 >> 24) | ((x1 >> 24) << 8) | ((x2 >> 24) << 16);
+}
+// exact count of a canonical k-mer whose 24-bit field saturated (binary search in the side list)
+static __device__ __noinline__ int rcx_big_count(const RcxTable& t, unsigned long long canon) {
+    int lo = 0, hi = t.nbig - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned long long v = t.big_keys[mid];
+        if (v == canon) return (int)t.big_counts[mid];
+        if (v < canon) lo = mid + 1; else hi = mid - 1;
+    }
+    return (int)RCX_BIG;
+}
+// k-mer formed by extending ctx (caller's orientation) with base b on the right / left
+__device__ __forceinline__ unsigned long long rcx_ext_kmer(unsigned long long ctx, bool left, int b, int k) {
+    return left ? (ctx | ((unsigned long long)b << (2 * (k - 1)))) : ((ctx << 2) | (unsigned long long)b);
+}
+// counts of the four extensions ctx+b (left = false) or b+ctx (left = true), b in the caller's orientation
+__device__ __forceinline__ void rcx_counts4(const RcxTable& t, unsigned long long ctx, bool left, const RcxLookup& L, bool found,
+                                            int& c0, int& c1, int& c2, int& c3) {
+    c0 = c1 = c2 = c3 = 0;
+    if (!found) return;
+    unsigned int f0, f1, f2, f3;
+    rcx_group(L.d, left != L.flip, f0, f1, f2, f3);
+    c0 = (int)(L.flip ? f3 : f0); c1 = (int)(L.flip ? f2 : f1); c2 = (int)(L.flip ? f1 : f2); c3 = (int)(L.flip ? f0 : f3);
+    if (((f0 + 1) | (f1 + 1) | (f2 + 1) | (f3 + 1)) & 0x1000000u) {  // some field == RCX_BIG
+        if (c0 == (int)RCX_BIG) c0 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 0, t.k), t.k));
+        if (c1 == (int)RCX_BIG) c1 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 1, t.k), t.k));
+        if (c2 == (int)RCX_BIG) c2 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 2, t.k), t.k));
+        if (c3 == (int)RCX_BIG) c3 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 3, t.k), t.k));
+    }
+}
+// count of the single extension by base b
+__device__ __forceinline__ int rcx_count1(const RcxTable& t, unsigned long long ctx, bool left, int b, const RcxLookup& L, bool found) {
+    if (!found) return 0;
+    unsigned int f0, f1, f2, f3;
+    rcx_group(L.d, left != L.flip, f0, f1, f2, f3);
+    const int bb = L.flip ? 3 - b : b;
+    const unsigned int f = bb == 0 ? f0 : bb == 1 ? f1 : bb == 2 ? f2 : f3;
+    if (f == RCX_BIG) return rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, b, t.k), t.k));
+    return (int)f;
+}
+// Store::GetCount of a valid k-mer given by its forward code: right extension of its prefix context
+__device__ __forceinline__ int rcx_probe_kmer(const RcxTable& t, unsigned long long code) {
+    RcxLookup L;
+    rcx_lookup_begin(t, code >> 2, L);
+    const bool found = rcx_lookup_end(t, L);
+    return rcx_count1(t, code >> 2, false, (int)(code & 3), L, found);
 }
 
 // ----------------------------------------------------------------------------- KmerCode state machine
@@ -123,7 +197,7 @@ __device__ __forceinline__ void rcx_k_prepend(RcxKmer& x, int v, bool bad, int k
 }
 __device__ __forceinline__ int rcx_k_count(const RcxTable& t, const RcxKmer& x) {
     if (x.inv != -1) return 0;
-    return rcx_probe(t, rcx_canonical(x.code, t.k));
+    return rcx_probe_kmer(t, x.code);
 }
 
 // ----------------------------------------------------------------------------- GetBound
@@ -142,7 +216,7 @@ __device__ __forceinline__ int rcx_bound_i(int c, double er) {
 // out-of-line copies for the (large) correction kernel: its hot loops must stay inside the instruction cache
 static __device__ __noinline__ int rcx_bound_i_ool(int c, double er) { return rcx_bound_i(c, er); }
 static __device__ __noinline__ double rcx_bound_d_ool(int c, double er) { return rcx_bound_d(c, er); }
-static __device__ __noinline__ int rcx_probe_ool(const RcxTable& t, unsigned long long canon) { return rcx_probe(t, canon); }
+static __device__ __noinline__ int rcx_probe_kmer_ool(const RcxTable& t, unsigned long long code) { return rcx_probe_kmer(t, code); }
 
 // ----------------------------------------------------------------------------- per-read bit planes
 // A warp turns one read into bit planes in shared memory:

@@ -29,34 +29,19 @@ enum { T_FETCH = 0, T_SEG = 1, T_ENTER = 2, T_ALT0 = 3 /* ..T_ALT0+3 */, T_JUMP 
 
 __device__ __forceinline__ int dfs_sel4(int b, int c0, int c1, int c2, int c3) { return b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3; }
 
-// counts of the 4 one-base extensions of kc: DFS_ILP independent one-sector bucket probes per thread in flight
-#ifndef DFS_ILP
-#define DFS_ILP 2
-#endif
+// counts of the 4 one-base extensions of kc: they share one (k-1)-mer context, so ONE sector answers the node
+// (InferPosThreshold, the keep-base test and the three alternatives)
 __device__ __noinline__ void dfs_probe4(const RcxTable& t, const RcxKmer& kc, bool right, unsigned long long mask, int& c0, int& c1,
                                         int& c2, int& c3) {
-    int c[4];
-#pragma unroll
-    for (int h = 0; h < 4 / DFS_ILP; ++h) {
-        unsigned long long canon[DFS_ILP], home[DFS_ILP];
-        RcxBucketRegs d[DFS_ILP];
-        bool live[DFS_ILP];
-#pragma unroll
-        for (int u = 0; u < DFS_ILP; ++u) {
-            RcxKmer x = kc;
-            if (right) rcx_k_append(x, DFS_ILP * h + u, false, t.k, mask);
-            else rcx_k_prepend(x, DFS_ILP * h + u, false, t.k, mask);
-            live[u] = x.inv == -1;
-            if (live[u]) {
-                canon[u] = rcx_canonical(x.code, t.k);
-                home[u] = rcx_home(t, canon[u]);
-                rcx_issue(t, home[u], d[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < DFS_ILP; ++u) c[DFS_ILP * h + u] = live[u] ? rcx_resolve(t, canon[u], home[u], d[u]) : 0;
-    }
-    c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3];
+    // validity of the children after Append / Prepend of a valid base (KmerCode.cpp:7-42)
+    const bool valid = kc.inv == -1 || (right ? kc.inv + 1 >= t.k : kc.inv <= 0);
+    c0 = c1 = c2 = c3 = 0;
+    if (!valid) return;
+    const unsigned long long ctx = right ? (kc.code & (mask >> 2)) : (kc.code >> 2);
+    RcxLookup L;
+    rcx_lookup_begin(t, ctx, L);
+    const bool found = rcx_lookup_end(t, L);
+    rcx_counts4(t, ctx, !right, L, found, c0, c1, c2, c3);
 }
 
 // InferPosThreshold (:144-173) given the four extension counts; lut[c] = max(1, (int)GetBound(c)) for small c
@@ -211,7 +196,7 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
                 stage = T_POP;
             } else {
                 dfs_probe4(a.t, kc, right, mask, c0, c1, c2, c3);
-                n_probes += 4;
+                n_probes += 1;
                 thr = dfs_infer(c0, c1, c2, c3, t, er, lut);
                 ext = 0;
                 stage = T_ALT0;
@@ -308,7 +293,7 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
                     for (i = pos; i < to; ++i) {
                         int d0, d1, d2, d3;
                         dfs_probe4(a.t, x, true, mask, d0, d1, d2, d3);
-                        n_probes += 4;
+                        n_probes += 1;
                         th = dfs_infer(d0, d1, d2, d3, t, er, lut);
                         const int qi = pinfo[i];
                         const bool bad = (qi & 4) != 0;
@@ -325,7 +310,7 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
                     for (i = pos; i >= to; --i) {
                         int d0, d1, d2, d3;
                         dfs_probe4(a.t, x, false, mask, d0, d1, d2, d3);
-                        n_probes += 4;
+                        n_probes += 1;
                         th = dfs_infer(d0, d1, d2, d3, t, er, lut);
                         const int qi = pinfo[i];
                         const bool bad = (qi & 4) != 0;

@@ -76,13 +76,17 @@ struct RcxCorrectArgs {
 __host__ __device__ inline int rcx_state_stride(int max_len, int k) { return ST_HDR + ST_SEGW * (max_len / k + 4); }
 
 // table (rcx_table.cu)
-cudaError_t rcx_launch_table_init(RcxBucket* buckets, unsigned long long nbuckets, cudaStream_t s);
-cudaError_t rcx_launch_table_insert(RcxBucket* buckets, unsigned long long nbuckets, unsigned long long* vals, int k,
-                                    const unsigned long long* codes, const int32_t* counts, unsigned long long n,
-                                    unsigned long long first_index, unsigned long long* new_keys, cudaStream_t s);
-cudaError_t rcx_launch_table_finalize(RcxBucket* buckets, unsigned long long nbuckets, const unsigned long long* vals, cudaStream_t s);
+cudaError_t rcx_launch_table_init(RcxEntry* e, unsigned long long nlines, cudaStream_t s);
+cudaError_t rcx_launch_table_claim(RcxEntry* e, unsigned long long nlines, int k, const unsigned long long* codes, const int32_t* counts,
+                                   unsigned long long n, int home_only, unsigned long long* stat, unsigned long long fresh_limit,
+                                   cudaStream_t s);
+cudaError_t rcx_launch_table_fill(RcxEntry* e, unsigned long long nlines, int k, const unsigned long long* codes, const int32_t* counts,
+                                  unsigned long long n, unsigned long long first_index, unsigned int* win, unsigned long long part_lo,
+                                  unsigned long long part_hi, int write, unsigned long long* stat, unsigned long long* big_keys,
+                                  unsigned int* big_counts, unsigned long long big_cap, cudaStream_t s);
 cudaError_t rcx_launch_table_lookup(RcxTable t, const unsigned long long* codes, int32_t* out, unsigned long long n,
                                     cudaStream_t s);
+cudaError_t rcx_launch_table_lookup4(RcxTable t, const unsigned long long* codes, int32_t* out4, unsigned long long n, cudaStream_t s);
 cudaError_t rcx_launch_random_read(RcxTable t, int bytes, int grid, unsigned long long iters, unsigned long long* sink, cudaStream_t s);
 // scan (rcx_scan.cu)
 size_t rcx_scan_smem_per_warp(int max_len, int k);

@@ -90,32 +90,43 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 4) rcx_scan_kernel(RcxScanArg
         int nN, nA, nT;
         rcx_build_planes(P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
 
-        // ---- probes: SCAN_ILP windows per lane in flight
-        for (int j0 = 0; j0 < kcnt; j0 += 32 * SCAN_ILP) {
-            unsigned long long canon[SCAN_ILP], home[SCAN_ILP];
-            RcxBucketRegs d[SCAN_ILP];
+        // ---- lookups: windows c-1 and c share the context seq[c .. c+k-1) (c odd), so one sector answers both: the left
+        // extension by seq[c-1] and the right extension by seq[c+k-1].  SCAN_ILP contexts per lane in flight.
+        const int nctx = (kcnt + 1) >> 1;
+        for (int i0 = 0; i0 < nctx; i0 += 32 * SCAN_ILP) {
+            RcxLookup L[SCAN_ILP];
+            unsigned long long ctx[SCAN_ILP];
             bool live[SCAN_ILP];
 #pragma unroll
             for (int u = 0; u < SCAN_ILP; ++u) {
-                const int j = j0 + u * 32 + lane;
-                live[u] = j < kcnt && (rcx_bits(P.inv, j < kcnt ? j : 0) & kmask32) == 0;
+                const int i = i0 + u * 32 + lane;
+                const int c = 2 * i + 1;
+                live[u] = i < nctx && (rcx_bits(P.inv, i < nctx ? c : 0) & (kmask32 >> 1)) == 0;  // no non-ACGT base in the context
                 if (live[u]) {
-                    canon[u] = rcx_canonical(rcx_window(P.pk, j, k), k);
-                    home[u] = rcx_home(a.t, canon[u]);
-                    rcx_issue(a.t, home[u], d[u]);
+                    ctx[u] = rcx_window(P.pk, c, k - 1);
+                    rcx_lookup_begin(a.t, ctx[u], L[u]);
                 }
             }
 #pragma unroll
             for (int u = 0; u < SCAN_ILP; ++u) {
-                const int j = j0 + u * 32 + lane;
-                int c = 0;
+                const int i = i0 + u * 32 + lane;
+                const int c = 2 * i + 1;
+                int cl = 0, cr = 0;
                 if (live[u]) {
                     ++probes;
-                    c = rcx_resolve(a.t, canon[u], home[u], d[u]);
+                    const bool found = rcx_lookup_end(a.t, L[u]);
+                    // the context is clean, so a window is valid iff its one extra base is
+                    if (!((P.inv[(c - 1) >> 5] >> ((c - 1) & 31)) & 1u)) cl = rcx_count1(a.t, ctx[u], true, rcx_base(P.pk, c - 1), L[u], found);  // window c-1
+                    if (c < kcnt && !((P.inv[(c + k - 1) >> 5] >> ((c + k - 1) & 31)) & 1u))
+                        cr = rcx_count1(a.t, ctx[u], false, rcx_base(P.pk, c + k - 1), L[u], found);  // window c
                 }
-                if (j < kcnt) {
-                    a.counts[o + j] = c;
-                    sbuf[j] = rcx_polya(P, j, k, kmask32, loose) ? -1 : c;  // :1530-1539
+                if (i < nctx) {
+                    a.counts[o + c - 1] = cl;
+                    sbuf[c - 1] = rcx_polya(P, c - 1, k, kmask32, loose) ? -1 : cl;  // :1530-1539
+                    if (c < kcnt) {
+                        a.counts[o + c] = cr;
+                        sbuf[c] = rcx_polya(P, c, k, kmask32, loose) ? -1 : cr;
+                    }
                 }
             }
         }

@@ -124,3 +124,58 @@ def test_edge_cases(gpu, workdir):
     got = gpu.correct(T.SINGLE, eb.seq, eb.qual, eb.off)
     for e, g in zip(exp, got):
         assert np.array_equal(e, g)
+
+
+def _code(s):
+    v = 0
+    for ch in s:
+        v = (v << 2) | "ACGT".index(ch)
+    return v
+
+
+def _rc(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+@pytest.mark.parametrize("k", [2, 3, 15, 22, 23, 31, 32])
+def test_context_table_semantics(gpu, k):
+    """The table is keyed by (k-1)-mer contexts (two placements per k-mer): overlapping k-mers from both strands,
+    reverse-complement duplicates (last record wins), palindromic contexts, counts beyond the 24-bit fields."""
+    import random
+
+    rnd = random.Random(100 + k)
+    kmers = []
+    for _ in range(60):  # chains of overlapping k-mers, random strand per k-mer
+        s = "".join(rnd.choice("ACGT") for _ in range(k + 200))
+        for j in range(len(s) - k + 1):
+            x = s[j : j + k]
+            kmers.append(x if rnd.random() < 0.5 else _rc(x))
+    if k >= 3 and (k - 1) % 2 == 0:  # palindromic (k-1)-mer contexts extended on both sides
+        for _ in range(200):
+            half = "".join(rnd.choice("ACGT") for _ in range((k - 1) // 2))
+            p = half + _rc(half)
+            for b in "ACGT":
+                kmers.append(p + b)
+                kmers.append(b + p)
+    kmers += ["A" * k, "T" * k, "AC" * (k // 2) + "A" * (k % 2), ("ACGT" * 9)[:k]]
+    n0 = len(kmers)
+    kmers += [_rc(x) for x in kmers[:: 7]]  # the other strand again, later in the file
+    kmers += kmers[:: 11]                   # plain duplicates
+    counts = [rnd.choice([0, 1, 2, 3, 50, 70000, (1 << 24) - 2, (1 << 24) - 1, 1 << 24, (1 << 31) - 1]) for _ in kmers]
+    codes = np.array([_code(x) for x in kmers], dtype=np.uint64)
+    counts = np.array(counts, dtype=np.int32)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    gpu.build_table(k, codes, counts)
+    assert gpu.table_info()["entries"] == len(table)
+    # queries: everything stored (both strands), one-base neighbours, random k-mers
+    q = list(kmers[:n0]) + [_rc(x) for x in kmers[:n0]]
+    for x in kmers[:2000]:
+        i = rnd.randrange(k)
+        q.append(x[:i] + rnd.choice("ACGT") + x[i + 1 :])
+    q += ["".join(rnd.choice("ACGT") for _ in range(k)) for _ in range(2000)]
+    qc = np.array([_code(x) for x in q], dtype=np.uint64)
+    exp = np.array([T.oracle().orc_table_count(table.h, int(x)) for x in qc], dtype=np.int32)
+    got = gpu.lookup(qc)
+    bad = np.nonzero(exp != got)[0]
+    assert len(bad) == 0, "%d mismatches, first %s exp %d got %d" % (len(bad), q[bad[0]], exp[bad[0]], got[bad[0]])
