@@ -448,9 +448,9 @@ def main_ours(a):
     # per-kernel CUDA-event times of the last device step; dominant kernel and its roofline.
     # Algorithmic bytes: 32 B per table probe + the bytes of the reads / counts[] a kernel streams.
     bases = st["bases"]
+    # A "probe" is one 32-byte table sector request: it answers two scan windows, or the four extensions of a search node.
     kern = {
-        "rcx_scan_kernel": {"ms": st["ms_scan"], "probes": st["scan_probes"], "bytes": 32 * st["scan_probes"] + bases},
-        "rcx_triage_kernel": {"ms": st["ms_triage"], "probes": 0, "bytes": 5 * bases},
+        "rcx_scan_kernel": {"ms": st["ms_scan"], "probes": st["scan_probes"], "bytes": 32 * st["scan_probes"] + bases + 4 * bases},
         "rcx_prep_kernel": {"ms": st["ms_prep"], "probes": 0, "bytes": 7 * bases},
         "rcx_dfs_kernel": {"ms": st["ms_dfs"], "probes": st["search_probes"], "nodes": st["search_nodes"], "bytes": 32 * st["search_probes"] + 2 * bases},
         "rcx_finalize_kernel": {"ms": st["ms_finalize"], "probes": st["rescan_probes"], "bytes": 32 * st["rescan_probes"] + 8 * bases},
@@ -469,7 +469,7 @@ def main_ours(a):
         "mbase_per_s": value * a.len / 1e6,
         "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": int(2 * total + 4 * (n + 1)) * world, "d2h_bytes_per_step": int(total + 16 * n) * world},
-        "gpu_launches": int(st["kernel_launches"]) * a.steps * world,  # 7 kernels per step per GPU in the timed region of `value` (the e2e region launches the same 7)
+        "gpu_launches": int(st["kernel_launches"]) * a.steps * world,  # 6 kernels per step per GPU in the timed region of `value` (the e2e region launches the same 6)
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
                      "kernel_ms": dom_ms, "random_read_peak_gbs": {"32B": rr32, "64B": rr64},

@@ -384,8 +384,16 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
     sa.t = table_of(c);
     sa.seq = d_seq; sa.off = d_off; sa.n = n; sa.max_len = max_len;
     sa.counts = c->d_counts.p; sa.thr = c->d_thr.p; sa.flags = c->d_flags.p; sa.counters = c->d_counters;
+    sa.triage = correct ? 1 : 0; sa.mode = correct ? mode : RCX_SINGLE; sa.error_rate = c->params.error_rate;
+    sa.correction = d_corr; sa.l = d_l; sa.m = d_m; sa.h = d_h; sa.worklist = correct ? c->d_worklist.p : nullptr;
+    sa.total_bases = total_bases; sa.max_fix_per_k = c->params.max_fix_per_k;
+    sa.state = correct ? c->d_state.p : nullptr; sa.posbuf = correct ? c->d_posbuf.p : nullptr; sa.fixbuf = correct ? c->d_fixbuf.p : nullptr;
+    // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
+    // long reads (or RCX_SCAN_WARP=1): the warp-per-read kernels
+    const bool thread_scan = rcx_scan_thread_supported(max_len, c->k, d_seq) && !getenv("RCX_SCAN_WARP");
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    CUDA_TRY(rcx_launch_scan(sa, c->sm_count, c->stream));
+    if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, c->stream));
+    else CUDA_TRY(rcx_launch_scan(sa, c->sm_count, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     c->stats.kernel_launches = 1;
     c->kev_valid = false;
@@ -402,9 +410,9 @@ static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const c
         CUDA_TRY(c->d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
         CUDA_TRY(c->d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
         ca.posbuf = c->d_posbuf.p; ca.dfs_stack = c->d_dfs_stack.p; ca.dfs_path = c->d_dfs_path.p;
-        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, c->stream, c->kev));
+        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, c->stream, c->kev, thread_scan));
         c->kev_valid = true;
-        c->stats.kernel_launches = 7;  // scan, triage, 2 x (prep, search), finalize
+        c->stats.kernel_launches = thread_scan ? 5 : 6;  // scan (+ thresholds + triage [+ first preparation]), search, preparation + search of the second pass, finalize
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     c->stats.reads = (uint64_t)n;

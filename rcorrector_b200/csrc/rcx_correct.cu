@@ -234,51 +234,6 @@ __device__ __forceinline__ void initial_thresholds(const RcxCorrectArgs& a, long
     if (trust < 2) trust = 2;
 }
 
-__global__ void __launch_bounds__(COR_WARPS * 32) rcx_triage_kernel(RcxCorrectArgs a) {
-    extern __shared__ unsigned int smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = a.t.k;
-    const CorLayout L = cor_layout(a.max_len, k);
-    WarpMem M;
-    setup_warpmem(M, smem, warp, L);
-    const unsigned int kmask32 = k >= 32 ? 0xffffffffu : ((1u << k) - 1);
-    #pragma unroll 1
-    for (long long r = (long long)blockIdx.x * COR_WARPS + warp; r < a.n; r += (long long)gridDim.x * COR_WARPS) {
-        const uint32_t o = a.off[r];
-        const int len = (int)(a.off[r + 1] - o);
-        const int kcnt = len - k + 1;
-        if (kcnt <= 0) {  // :713 -> -1 ; GetKmerInformation gives 0,0,0
-            if (lane == 0) { a.correction[r] = -1; a.l[r] = 0; a.m[r] = 0; a.h[r] = 0; }
-            continue;
-        }
-        int nN, nA, nT;
-        build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
-        #pragma unroll 1
-        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
-        const uint8_t fl = a.flags[r];
-        __syncwarp();
-        int result = -2;
-        if (fl & RCX_F_REJECT) {
-            result = -1;
-        } else {
-            int strong, trust;
-            initial_thresholds(a, r, fl, a.error_rate, strong, trust);
-            bool bad = false;  // any untrusted k-mer (:875)?
-            #pragma unroll 1
-            for (int j = lane; j < kcnt; j += 32) bad |= !(M.counts[j] >= strong && !rcx_polya(M.P, j, k, kmask32, 2));
-            if (!__any_sync(RCX_FULL, bad)) result = 0;  // longestTrustedLength == kcnt (:1110)
-        }
-        if (result == -2) {
-            if (lane == 0) a.worklist[atomicAdd(&a.counters[RCX_C_NWORK], 1ull)] = (uint32_t)r;
-        } else {
-            int l, m, h;
-            kmer_info(M, kcnt, kmask32, lane, l, m, h);
-            if (lane == 0) { a.correction[r] = result; a.l[r] = l; a.m[r] = m; a.h[r] = h; }
-        }
-        __syncwarp();
-    }
-}
-
 // work-item fetch shared by the persistent warp-per-read kernels: pass 0 walks the triage work list, pass 1 the
 // (short) list of items whose first pass asked for a second one (forceNextRound, ErrorCorrection.cpp:1195-1211; at
 // most two passes can happen because forceNextRound needs iter == 0 and `unfixable` is never set)
@@ -679,22 +634,23 @@ static cudaError_t launch_one(void (*kern)(RcxCorrectArgs), const RcxCorrectArgs
 
 size_t rcx_state_words(int max_len, int k) { return (size_t)rcx_state_stride(max_len, k); }
 
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev) {
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev, bool prep0_done) {
     if (a0.n <= 0) return cudaSuccess;
     RcxCorrectArgs a = a0;
     const size_t smem = rcx_correct_smem_per_warp(a.max_len, a.t.k) * COR_WARPS;
     int ke = 0;
 #define MARK() do { if (kev) { cudaError_t _e = cudaEventRecord(kev[ke++], s); if (_e != cudaSuccess) return _e; } } while (0)
     a.pass = 0;
-    MARK();
-    cudaError_t e = launch_one(rcx_triage_kernel, a, sm_count, a.n, smem, s);
-    if (e != cudaSuccess) return e;
+    MARK();  // (the triage is fused into the scan kernel: kev[0..1] brackets nothing)
+    cudaError_t e = cudaSuccess;
     // the work-list lengths live on the device: the persistent kernels read them there (no host round trip)
     for (int pass = 0; pass < 2; ++pass) {
         a.pass = pass;
         MARK();
-        e = launch_one(rcx_prep_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
-        if (e != cudaSuccess) return e;
+        if (!(pass == 0 && prep0_done)) {  // the thread-per-read scan kernel already prepared the first pass
+            e = launch_one(rcx_prep_kernel, a, sm_count, pass == 0 ? a.n : a.n / 8 + 1, smem, s);
+            if (e != cudaSuccess) return e;
+        }
         MARK();
         e = rcx_launch_dfs(a, dfs_grid, s);
         if (e != cudaSuccess) return e;

@@ -28,7 +28,23 @@ struct RcxScanArgs {
     int32_t* thr;      // [n] GetStrongTrustedThreshold
     uint8_t* flags;    // [n]
     unsigned long long* counters;
+    // fused triage (triage != 0): clean / rejected reads get correction + l/m/h here, the others go to the work list
+    int triage;
+    int mode;          // rcx_mode: in interleaved mode a warp owns both mates (pair threshold)
+    double error_rate;
+    int32_t* correction;
+    int32_t* l;
+    int32_t* m;
+    int32_t* h;
+    uint32_t* worklist;
+    // fused first pass of the A.4 preparation (thread-per-read kernel only)
+    unsigned long long total_bases;
+    int max_fix_per_k;
+    int32_t* state;
+    unsigned char* posbuf;
+    signed char* fixbuf;
 };
+#define RCX_TS_MAX_KCNT 232  // reads with more k-windows use the warp-per-read kernels
 
 struct RcxCorrectArgs {
     RcxTable t;
@@ -91,11 +107,14 @@ cudaError_t rcx_launch_random_read(RcxTable t, int bytes, int grid, unsigned lon
 // scan (rcx_scan.cu)
 size_t rcx_scan_smem_per_warp(int max_len, int k);
 cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s);
+// thread-per-read scan + thresholds + triage + first-pass preparation (rcx_scan_thread.cu)
+bool rcx_scan_thread_supported(int max_len, int k, const void* seq);
+cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s);
 // correction (rcx_correct.cu)
 size_t rcx_correct_smem_per_warp(int max_len, int k);
 size_t rcx_state_words(int max_len, int k);
 // kev: 7 events recorded before triage, prep0, dfs0, prep1, dfs1, finalize and after finalize (may be null)
-cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev);
+cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev, bool prep0_done);
 // search (rcx_dfs.cu)
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad);
 size_t rcx_dfs_stack_words(int grid, int depth);

@@ -1,0 +1,553 @@
+// rcx_scan_thread.cu — K1 for reads of ordinary length: ONE THREAD owns one read, a block stages a tile of reads
+// through shared memory.  Fuses, in one pass over the read:
+//   * the scan (ErrorCorrection.cpp:716-723 / :1494-1501): counts[j] for every k-window, one table sector per TWO windows;
+//   * GetStrongTrustedThreshold (:1482-1565);
+//   * the triage of ErrorCorrection (:713-755 rejects, :772-842 thresholds, :1110 "every k-mer trusted") with the
+//     l/m/h tags (GetKmerInformation, :1567-1602) of the reads that leave here;
+//   * for the reads that need the search, steps 1-4 of the iteration loop (:863-1046): trusted runs, island adjustment,
+//     trusted positions, segments with their seed k-mers and maxFixCnt, per-base info for the search kernel.
+//
+// Why a thread per read (measured, profiles/r01_g): the warp-per-read version of this work executed ~2 000 warp
+// instructions per 100-bp read spread evenly over bit-plane construction, funnel shifts, ballots and reductions, ran at
+// 65 % issue utilisation and took the same 24 ms per 10 M reads whether the table needed 737 M or 369 M sector
+// requests: it was instruction-bound, not memory-bound.  The per-read work is scalar bookkeeping over ~80 windows; a
+// thread does it with a rolling k-mer in registers (~200 warp-instruction equivalents per read) and 32 reads share
+// every instruction.  The block keeps the memory side coalesced: the tile's bases are copied HBM -> shared with
+// 16-byte vector loads, each thread's counts live in its own conflict-free shared-memory row (odd stride), and
+// counts[] / per-base info / the cleared fix[] go back to HBM as contiguous block-wide copies.  Table lookups are
+// software-pipelined four deep per thread (512 threads x 4 independent sector requests in flight per SM).
+//
+// Reads with more than TS_MAX_KCNT windows keep the warp-per-read kernels (rcx_scan.cu, rcx_correct.cu).
+#include "rcx_internal.h"
+
+#define TS_THREADS 128
+#define TS_DEPTH 4
+#define TS_LOOSE 0x80000000u   // flag bits stored with a count in shared memory
+#define TS_STRICT 0x40000000u
+#define TS_INVALID 0x20000000u
+#define TS_CMASK 0x1fffffffu
+// per-base byte in shared memory: code (bits 0-1) | not-ACGT (bit 2) | allow-Right (3) | allow-Left (4) | literal N (5) |
+// strongly trusted position (6)
+#define TB_BAD 4
+#define TB_N 32
+#define TB_STRONG 64
+
+struct TsLayout {
+    int cw;         // words per count row (odd)
+    int bytes_cap;  // staged bases
+    size_t smem;
+};
+__host__ __device__ inline TsLayout ts_layout(int max_len, int k) {
+    TsLayout L;
+    int kc = max_len - k + 1;
+    if (kc < 1) kc = 1;
+    L.cw = kc | 1;
+    L.bytes_cap = ((TS_THREADS * max_len + 15) & ~15) + 32;
+    L.smem = sizeof(uint32_t) * (TS_THREADS + 4) + sizeof(int) * 16 + sizeof(int) * (size_t)TS_THREADS * L.cw + (size_t)L.bytes_cap;
+    return L;
+}
+bool rcx_scan_thread_supported(int max_len, int k, const void* seq) {
+    const int kc = max_len - k + 1;
+    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && ((uintptr_t)seq & 15) == 0 && ts_layout(max_len, k).smem <= 200 * 1024;
+}
+
+struct TsPend {
+    unsigned long long key;
+    RcxEntryRegs d;
+    int info;  // -1: empty;  else  j (right window index, 10 bits) | left base << 10 | right base << 12 | wantL << 14 | wantR << 15 | flip << 16
+};
+
+__device__ __forceinline__ bool ts_find_slow(const RcxTable& t, unsigned long long key, RcxEntryRegs& d) {
+    const unsigned long long home = __umul64hi(rcx_hash(key), t.nlines << 2);
+    for (unsigned int i = 1;; ++i) {
+        rcx_issue(t, rcx_probe_sector(t, home, i), d);
+        if (d.q0 == ~0ull) return false;
+        if ((d.q0 & RCX_KEY_MASK) == key) return true;
+        if (i >= 4 * t.nlines) return false;
+    }
+}
+__device__ __forceinline__ bool ts_find(const RcxTable& t, unsigned long long key, RcxEntryRegs& d) {
+    if ((d.q0 & RCX_KEY_MASK) == key) return true;
+    if (d.q0 == ~0ull || !(d.q0 & RCX_OVERFLOW_BIT)) return false;
+    return ts_find_slow(t, key, d);
+}
+// count of the extension by base b (caller's orientation) from a found entry
+__device__ __forceinline__ int ts_field(const RcxTable& t, const RcxEntryRegs& d, unsigned long long key, bool flip, bool left, int b) {
+    unsigned int f0, f1, f2, f3;
+    rcx_group(d, left != flip, f0, f1, f2, f3);
+    const int bb = flip ? 3 - b : b;
+    const unsigned int f = bb == 0 ? f0 : bb == 1 ? f1 : bb == 2 ? f2 : f3;
+    if (f == RCX_BIG) {
+        const unsigned long long ctx = flip ? rcx_revcomp(key, t.k - 1) : key;
+        return rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, b, t.k), t.k));
+    }
+    return (int)f;
+}
+
+__device__ __forceinline__ int ts_octave(int v) { return v <= 0 ? 0 : 32 - __clz(v); }
+__device__ __forceinline__ int ts_masked(unsigned int x) { return (x & TS_LOOSE) ? -1 : (int)(x & TS_CMASK); }
+
+// smallest x with #{value <= x} > rank over the row; kind 0: loose-masked counts, kind 1: valid windows with 0 -> 1
+template <int KIND>
+__device__ __forceinline__ int ts_select(const unsigned int* row, int kcnt, int rank, int lo, int hi) {
+    while (lo < hi) {
+        const int mid = lo + (int)(((unsigned int)hi - (unsigned int)lo) >> 1);
+        int c = 0;
+        for (int j = 0; j < kcnt; ++j) {
+            const unsigned int x = row[j];
+            if (KIND == 0) c += ts_masked(x) <= mid;
+            else if (!(x & TS_INVALID)) { int v = (int)(x & TS_CMASK); v = v == 0 ? 1 : v; c += v <= mid; }
+        }
+        if (c > rank) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// a bit mask over the positions / k-mers of one read in NW 64-bit registers (all loops unrolled: no dynamic indexing)
+template <int NW>
+struct TsMask {
+    unsigned long long m[NW];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) m[w] = 0;
+    }
+    __device__ __forceinline__ bool nonzero() const {
+        unsigned long long o = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) o |= m[w];
+        return o != 0;
+    }
+    // bits [lo, hi] (inclusive) of word w as a mask, 0 if the range misses the word
+    static __device__ __forceinline__ unsigned long long range_word(int w, int lo, int hi) {
+        int l = lo - 64 * w, h = hi - 64 * w;
+        if (l < 0) l = 0;
+        if (h > 63) h = 63;
+        if (l > h) return 0;
+        return ((~0ull) >> (63 - (h - l))) << l;
+    }
+    __device__ __forceinline__ void set(int lo, int hi) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) m[w] |= range_word(w, lo, hi);
+    }
+    __device__ __forceinline__ bool any(int lo, int hi) const {
+        unsigned long long o = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) o |= m[w] & range_word(w, lo, hi);
+        return o != 0;
+    }
+    // first index in [from, limit) whose bit equals `want`, or `limit`
+    __device__ __forceinline__ int next(int from, int limit, bool want) const {
+        int best = limit;
+        if (from < limit) {
+#pragma unroll
+            for (int w = NW - 1; w >= 0; --w) {
+                unsigned long long x = (want ? m[w] : ~m[w]) & range_word(w, from, limit - 1);
+                if (x) best = 64 * w + __ffsll((long long)x) - 1;
+            }
+        }
+        return best;
+    }
+    // shift towards higher indices by s (0 <= s < 64)
+    __device__ __forceinline__ void shl(int s) {
+        if (s == 0) return;
+#pragma unroll
+        for (int w = NW - 1; w >= 0; --w) m[w] = (m[w] << s) | (w > 0 ? m[w - 1] >> (64 - s) : 0ull);
+    }
+};
+
+template <int NW>
+__global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = a.t.k;
+    const TsLayout LY = ts_layout(a.max_len, k);
+    uint32_t* offs = reinterpret_cast<uint32_t*>(smem_raw);                       // [T + 1] (+3 pad)
+    int* blk = reinterpret_cast<int*>(offs + TS_THREADS + 4);                     // [16] block scratch
+    unsigned int* cnt_all = reinterpret_cast<unsigned int*>(blk + 16);            // [T][cw]
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(cnt_all + (size_t)TS_THREADS * LY.cw);  // 16-byte aligned (all sizes above are multiples of 16)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const int loose_thr = (k / 2 > 7) ? k / 2 : 7;
+    const double er = a.error_rate;
+    const int K = a.max_fix_per_k;
+    const int stride = rcx_state_stride(a.max_len, k);
+    const int nseg_cap = a.max_len / k + 4;
+    unsigned int probes = 0, toobig = 0;
+    const long long ntiles = (a.n + TS_THREADS - 1) / TS_THREADS;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long r0 = tile * TS_THREADS;
+        const int nr = (int)((a.n - r0) < TS_THREADS ? (a.n - r0) : TS_THREADS);
+        __syncthreads();  // previous tile fully written out
+        for (int t = tid; t <= nr; t += TS_THREADS) offs[t] = a.off[r0 + t];
+        __syncthreads();
+        const unsigned long long g0 = offs[0], g1 = offs[nr];
+        const unsigned long long a0 = g0 & ~15ull;
+        {   // stage the tile's bases: 16-byte vectors, byte tail (never reads past the batch)
+            unsigned long long e16 = (g1 + 15) & ~15ull;
+            if (e16 > (a.total_bases & ~15ull)) e16 = a.total_bases & ~15ull;
+            if (e16 < a0) e16 = a0;
+            const uint4* src = reinterpret_cast<const uint4*>(a.seq + a0);
+            uint4* dst = reinterpret_cast<uint4*>(bytes);
+            const int nv = (int)((e16 - a0) >> 4);
+            for (int v = tid; v < nv; v += TS_THREADS) dst[v] = src[v];
+            for (unsigned long long p = e16 + tid; p < g1; p += TS_THREADS) bytes[p - a0] = (unsigned char)a.seq[p];
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------------ per-thread scan
+        const long long r = r0 + tid;
+        const bool have = tid < nr;
+        const uint32_t o = have ? offs[tid] : 0;
+        const int len = have ? (int)(offs[tid + 1] - o) : 0;
+        const int kcnt = len - k + 1;
+        unsigned char* B = bytes + (o - a0);
+        unsigned int* row = cnt_all + (size_t)tid * LY.cw;
+        int thr = -1;
+        uint8_t flags = RCX_F_REJECT;
+        int nN = 0, nA = 0, nT = 0;
+        if (have && kcnt > 0) {
+            unsigned long long F = 0;
+            int run = 0, run_prev = 0, wA = 0, wT = 0, left = 0;
+            int i = 0;
+            auto append = [&]() {
+                const unsigned char ch = B[i];
+                const unsigned int idx = (unsigned int)ch - 'A';
+                const bool ok = idx < 26u && ((0x00080045u >> idx) & 1u);  // A, C, G, T
+                const int code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 3;   // A0 C1 G2 T3, anything else coded as 3 (KmerCode.cpp:12-13)
+                nN += ch == 'N';
+                nA += ch == 'A';
+                nT += ch == 'T';
+                B[i] = (unsigned char)(code | (ok ? 0 : TB_BAD) | (ch == 'N' ? TB_N : 0));
+                wA += ch == 'A';
+                wT += ch == 'T';
+                if (i >= k) {  // base leaving the window (already converted)
+                    const unsigned char q = B[i - k];
+                    wA -= (q & 7) == 0;
+                    wT -= (q & 7) == 3;
+                }
+                left = (int)((F >> (2 * (k - 1))) & 3);
+                F = ((F << 2) | (unsigned long long)code) & kmask;
+                run_prev = run;
+                run = ok ? run + 1 : 0;
+                ++i;
+            };
+            while (i < k - 1) append();
+            while (i < len) {
+                TsPend p[TS_DEPTH];
+#pragma unroll
+                for (int u = 0; u < TS_DEPTH; ++u) {
+                    p[u].info = -1;
+                    bool trig = false;
+                    int j = 0;
+                    while (i < len && !trig) {
+                        append();
+                        j = i - k;  // window that ends at the base just appended
+                        const bool lo_ = wA >= k - loose_thr || wT >= k - loose_thr;  // IsPolyA(seq + j, k, max(7, k/2))
+                        const bool st_ = wA >= k - 2 || wT >= k - 2;                  // IsPolyA(seq + j, k, 2)
+                        row[j] = (lo_ ? TS_LOOSE : 0u) | (st_ ? TS_STRICT : 0u) | (run >= k ? 0u : TS_INVALID);
+                        trig = (j & 1) || i == len;
+                    }
+                    if (trig) {
+                        // context = the k-1 bases before the newest one: window j-1 is its left extension (by the base that
+                        // just left F), window j its right extension (by the newest base)
+                        const bool wantL = (j & 1) && run_prev >= k;
+                        const bool wantR = run >= k;
+                        if (wantL || wantR) {
+                            const unsigned long long ctx = F >> 2;
+                            const unsigned long long rc = rcx_revcomp(ctx, k - 1);
+                            const bool flip = rc < ctx;
+                            p[u].key = flip ? rc : ctx;
+                            p[u].info = j | (left << 10) | ((int)(F & 3) << 12) | (wantL ? 1 << 14 : 0) | (wantR ? 1 << 15 : 0) | (flip ? 1 << 16 : 0);
+                            rcx_issue(a.t, __umul64hi(rcx_hash(p[u].key), a.t.nlines << 2), p[u].d);
+                            ++probes;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < TS_DEPTH; ++u) {
+                    const int info = p[u].info;
+                    if (info >= 0 && ts_find(a.t, p[u].key, p[u].d)) {
+                        const int j = info & 1023;
+                        const bool flip = (info >> 16) & 1;
+                        if (info & (1 << 14)) {
+                            const int c = ts_field(a.t, p[u].d, p[u].key, flip, true, (info >> 10) & 3);
+                            toobig |= (unsigned int)c > TS_CMASK;
+                            row[j - 1] |= (unsigned int)c & TS_CMASK;
+                        }
+                        if (info & (1 << 15)) {
+                            const int c = ts_field(a.t, p[u].d, p[u].key, flip, false, (info >> 12) & 3);
+                            toobig |= (unsigned int)c > TS_CMASK;
+                            row[j] |= (unsigned int)c & TS_CMASK;
+                        }
+                    }
+                }
+            }
+        } else if (have) {
+            for (int i = 0; i < len; ++i) {  // shorter than k: only the per-base conversion (the bytes go out as per-base info)
+                const unsigned char ch = B[i];
+                const unsigned int idx = (unsigned int)ch - 'A';
+                const bool ok = idx < 26u && ((0x00080045u >> idx) & 1u);
+                B[i] = (unsigned char)((ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 3) | (ok ? 0 : TB_BAD) | (ch == 'N' ? TB_N : 0));
+            }
+        }
+
+        // ------------------------------------------------------------------ GetStrongTrustedThreshold (:1507-1563)
+        int minc = 0x7fffffff, nvalid = 0, vmin = 0x7fffffff, vmax = 0;
+        bool any_strict = false;
+        if (have && kcnt > 0 && !(nN > 5 || nA > len - k || nT > len - k)) {
+            unsigned int present = 0;
+            int nonpos = 0, gmin = 0x7fffffff, gmax = -1;
+            for (int j = 0; j < kcnt; ++j) {
+                const unsigned int x = row[j];
+                const int c = (int)(x & TS_CMASK);
+                const int m = (x & TS_LOOSE) ? -1 : c;
+                present |= 1u << ts_octave(m);
+                nonpos += m <= 0;
+                gmin = m < gmin ? m : gmin;
+                gmax = m > gmax ? m : gmax;
+                minc = c < minc ? c : minc;
+                any_strict |= (x & TS_STRICT) != 0;
+            }
+            bool found = false;
+            int below = 0;
+            unsigned int leftm = present;
+            while (leftm) {
+                const int b = 31 - __clz(leftm);
+                const unsigned int lower = leftm & ~(1u << b);
+                if (b < 4 || lower == 0) break;  // values <= 10 cannot be a drop; the smallest element has no predecessor
+                const int lo_b = 1 << (b - 1);   // octave b = [2^(b-1), 2^b)
+                int mn = 0x7fffffff, mx = (int)0x80000000;
+                for (int j = 0; j < kcnt; ++j) {
+                    const int m = ts_masked(row[j]);
+                    if ((unsigned int)(m - lo_b) < (unsigned int)lo_b) mn = m < mn ? m : mn;  // smallest value of this octave
+                    else if (m < lo_b) mx = m > mx ? m : mx;                                  // largest value below it
+                }
+                if (mn <= 10) break;  // everything further down is smaller still
+                if (mn > 2 * mx) { found = true; thr = mn; below = mx; break; }
+                leftm = lower;
+            }
+            if (!found) thr = ts_select<0>(row, kcnt, (nonpos + kcnt - 1) / 2, gmin, gmax);  // median of the positive entries
+            flags = found ? (uint8_t)(RCX_F_DROP | (below == 2 ? RCX_F_PREV2 : 0)) : (uint8_t)0;
+        }
+        if (have) { a.thr[r] = thr; a.flags[r] = flags; }
+
+        // ------------------------------------------------------------------ triage
+        int result = -3;  // -3: no read / scan only; -2: work item; else final
+        int strong = 0, trust = 0;
+        const int mate_thr = __shfl_xor_sync(RCX_FULL, thr, 1);  // mates are records 2i, 2i+1 = neighbouring lanes
+        if (have && a.triage) {
+            if (kcnt <= 0) {  // :713 -> -1 ; GetKmerInformation gives 0,0,0
+                a.correction[r] = -1; a.l[r] = 0; a.m[r] = 0; a.h[r] = 0;
+                result = -1;
+            } else {
+                if (flags & RCX_F_REJECT) result = -1;
+                else {
+                    const int pair_t = a.mode == 1 ? (thr < mate_thr ? thr : mate_thr) : -1;
+                    // A.3 (:772-842)
+                    strong = thr;
+                    bool flag = false;
+                    trust = rcx_bound_i(strong, er);
+                    if ((flags & RCX_F_DROP) && strong >= 20 && (flags & RCX_F_PREV2) && trust < 3) { flag = true; trust = 3; }
+                    if (pair_t >= 1 && strong > pair_t) {
+                        if (!flag || pair_t < 20) trust = rcx_bound_i(pair_t, er);
+                        strong = pair_t;
+                    }
+                    if (trust < 2) trust = 2;
+                    result = (!any_strict && minc >= strong) ? 0 : -2;  // every k-mer trusted (:875, :1110)
+                }
+                if (result != -2) {  // GetKmerInformation (:1567-1602) on the unchanged read
+                    for (int j = 0; j < kcnt; ++j) {
+                        const unsigned int x = row[j];
+                        if (!(x & TS_INVALID)) {
+                            int v = (int)(x & TS_CMASK);
+                            v = v == 0 ? 1 : v;
+                            ++nvalid;
+                            vmin = v < vmin ? v : vmin;
+                            vmax = v > vmax ? v : vmax;
+                        }
+                    }
+                    int l = 0, m = 0, h = 0;
+                    if (nvalid > 0) { l = vmin; h = vmax; m = ts_select<1>(row, kcnt, nvalid / 2, vmin, vmax); }
+                    a.correction[r] = result; a.l[r] = l; a.m[r] = m; a.h[r] = h;
+                }
+            }
+        }
+        // work-list slots: one atomic per block
+        const bool is_work = result == -2;
+        const unsigned int wb = __ballot_sync(RCX_FULL, is_work);
+        if (lane == 0) blk[warp] = __popc(wb);
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < TS_THREADS / 32; ++w) { const int c = blk[w]; blk[w] = tot; tot += c; }
+            blk[8] = tot ? (int)atomicAdd(&a.counters[RCX_C_NWORK], (unsigned long long)tot) : 0;
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------------ A.4 steps 1-4 for the work items (:863-1046)
+        // Bit masks in registers (NW 64-bit words cover the read) keep the lanes of a warp in step: one uniform pass over
+        // the k-mers builds them, runs and islands are then found with ffs/clz instead of per-element loops.
+        if (is_work) {
+            const long long item = (long long)(unsigned int)blk[8] + blk[warp] + __popc(wb & ((1u << lane) - 1));
+            a.worklist[item] = (uint32_t)r;
+            int* st = a.state + item * stride;
+            TsMask<NW> T, S, LOWM, M;  // trusted k-mers (:875), strict poly-A k-mers, counts <= 2 && < trust, trusted positions
+            T.clear(); S.clear(); LOWM.clear(); M.clear();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                unsigned long long tw = 0, sw = 0, lw = 0;
+                const int jn = kcnt - 64 * w < 64 ? kcnt - 64 * w : 64;
+                for (int b = 0; b < jn; ++b) {
+                    const unsigned int x = row[64 * w + b];
+                    const int c = (int)(x & TS_CMASK);
+                    const bool strict = (x & TS_STRICT) != 0;
+                    tw |= (unsigned long long)(c >= strong && !strict) << b;
+                    sw |= (unsigned long long)strict << b;
+                    lw |= (unsigned long long)(c <= 2 && c < trust) << b;
+                }
+                T.m[w] = tw; S.m[w] = sw; LOWM.m[w] = lw;
+            }
+            int longest = 0, tstart = 0, tend = -1;
+            {
+                int pf = 0, pt = -1;
+                bool havei = false;
+                int p = 0;
+                while (p < kcnt) {
+                    const int s = T.next(p, kcnt, true);
+                    if (s >= kcnt) break;
+                    const int e = T.next(s, kcnt, false);
+                    const int rl = e - s;
+                    if (rl > longest) { longest = rl; tstart = s; tend = e - 1; }
+                    if (rl >= 2) {
+                        int cf = s, ct = e - 1;
+                        if (havei) {
+                            if (cf <= pt + k) {  // :936-964
+                                const int len1 = pt - pf, len2 = ct - cf, overlap = pt + k - cf;
+                                if (overlap <= 3 && LOWM.any(pt + 1, cf - 1)) {
+                                    if (len1 < len2) pt -= overlap + 1; else cf += overlap + 1;
+                                }
+                            }
+                            if (pf <= pt) M.set(pf, pt + k - 1);
+                        }
+                        pf = cf; pt = ct; havei = true;
+                    }
+                    p = e;
+                }
+                if (havei && pf <= pt) M.set(pf, pt + k - 1);
+            }
+            // islands of trusted positions (:977-1007); none: the longest trusted run stands in (without becoming "strong")
+            TsMask<NW> I = M;
+            if (!M.nonzero()) I.set(tstart, tend + k - 1);
+            // seed k-mer of a search = Restart + k Appends of seq[j0 .. j0+k) (j0 may be -1, see :1139-1142)
+            auto seed = [&](int j0, unsigned long long& code, int& inv) {
+                code = 0; inv = -1;
+                for (int q = 0; q < k; ++q) {
+                    const int p = j0 + q;
+                    const unsigned char bq = (p >= 0 && p < len) ? B[p] : 0;
+                    if (inv != -1) ++inv;
+                    code = (code << 2) | (unsigned long long)(bq & 3);
+                    if (p >= 0 && (bq & TB_BAD)) inv = 0;
+                }
+                code &= kmask;
+            };
+            int nseg = 0;
+            {
+                int ifrom = I.next(0, len, true);
+                int ito = ifrom < len ? I.next(ifrom, len, false) - 1 : len - 1;
+                int prev_to = -1, prev_len = 0;
+                bool first = true;
+                for (;;) {
+                    int sf, sto, la, ra;
+                    bool is_seg;
+                    if (ifrom < len) {
+                        sf = prev_to + 1; sto = ifrom - 1;
+                        la = first ? 0 : prev_len; ra = ito - ifrom + 1;
+                        is_seg = first ? ifrom > 0 : true;
+                    } else {
+                        sf = prev_to + 1; sto = len; la = prev_len; ra = 0;
+                        is_seg = prev_to < len - 1;
+                    }
+                    if (is_seg) {
+                        if (nseg < nseg_cap) {
+                            const bool right = la >= ra;  // :1136
+                            const int extend = right ? (sto == len ? 0 : k - 1) : (sf == 0 ? 0 : k - 1);
+                            unsigned long long code;
+                            int inv;
+                            seed(right ? sf - k : sto + 1, code, inv);
+                            int max_fix = (sto - sf + 1) * K / k * 2 + 1;  // :1128-1131
+                            if (max_fix < K) max_fix = K;
+                            int* sg = st + ST_HDR + ST_SEGW * nseg;
+                            sg[0] = (right ? sf : sto) | ((right ? sto + extend : sf - extend) << 16);
+                            sg[1] = (right ? 1 : 0) | (max_fix << 1);
+                            sg[2] = (int)(unsigned int)code;
+                            sg[3] = (int)(unsigned int)(code >> 32);
+                            sg[4] = inv;
+                            sg[5] = -1;  // top2FixBottleNeck[1], filled by the search
+                        }
+                        ++nseg;
+                    }
+                    if (ifrom >= len) break;
+                    prev_to = ito; prev_len = ito - ifrom + 1; first = false;
+                    ifrom = I.next(ito + 1, len, true);
+                    ito = ifrom < len ? I.next(ifrom, len, false) - 1 : len - 1;
+                }
+            }
+            // per-base info for the search (:343 / :577): substitutions are allowed on untrusted positions outside strict
+            // poly-A k-mers: Right tests k-mer i-k+1, Left k-mer i
+            TsMask<NW> SR = S;
+            SR.shl(k - 1);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const unsigned long long ar = ~M.m[w] & ~SR.m[w], al = ~M.m[w] & ~S.m[w];
+                const int in = len - 64 * w < 64 ? len - 64 * w : 64;
+                for (int b = 0; b < in; ++b) {
+                    const int i = 64 * w + b;
+                    B[i] = (unsigned char)((B[i] & 7) | (((ar >> b) & 1) << 3) | (((al >> b) & 1) << 4));
+                }
+            }
+            st[ST_STATUS] = RCX_ST_SEARCH; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
+            st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < nseg_cap ? nseg : nseg_cap;
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------------ coalesced write-out: counts[], per-base info, cleared fix[]
+        for (int t = warp; t < nr; t += TS_THREADS / 32) {
+            const uint32_t ot = offs[t];
+            const int kc = (int)(offs[t + 1] - ot) - k + 1;
+            const unsigned int* rw = cnt_all + (size_t)t * LY.cw;
+            for (int j = lane; j < kc; j += 32) a.counts[ot + j] = (int)(rw[j] & TS_CMASK);
+        }
+        if (a.triage) {
+            for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) {
+                a.posbuf[p] = bytes[p - a0] & 31;
+                a.fixbuf[p] = -1;
+            }
+        }
+    }
+    probes = __reduce_add_sync(RCX_FULL, probes);
+    toobig = __reduce_or_sync(RCX_FULL, toobig);
+    if (lane == 0 && probes) atomicAdd(&a.counters[RCX_C_SCAN_PROBES], (unsigned long long)probes);
+    if (lane == 0 && toobig) atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);  // a count >= 2^29: flagged, not hidden
+}
+
+template <int NW>
+static cudaError_t launch_scan_thread_nw(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
+    const TsLayout L = ts_layout(a.max_len, a.t.k);
+    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW>, TS_THREADS, L.smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (a.n + TS_THREADS - 1) / TS_THREADS;
+    long long grid = (long long)sm_count * per_sm;  // persistent grid: a multiple of the SM count
+    if (grid > want) grid = want;
+    rcx_scan_thread_kernel<NW><<<(unsigned int)grid, TS_THREADS, L.smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
+    if (a.max_len <= 128) return launch_scan_thread_nw<2>(a, sm_count, s);
+    return launch_scan_thread_nw<4>(a, sm_count, s);  // max_len <= 255
+}

@@ -54,7 +54,7 @@ def test_correct_batch_matches_oracle(gpu, workdir, name, k, paired, maxcor, kw)
     gpu.set_params(k, er, bq, maxcor)
     got = gpu.correct(mode, b.seq, b.qual, b.off)
     st = gpu.stats()
-    assert st["kernel_launches"] == 7
+    assert st["kernel_launches"] in (5, 6)
 
     names = ["seq", "correction", "l", "m", "h"]
     for nm, e, g in zip(names, exp, got):
