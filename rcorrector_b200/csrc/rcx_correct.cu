@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
         int nN, nA, nT;
         build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
         #pragma unroll 1
-        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
+        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j] & 0x7fffffff;  // bit 31: validity flag of the thread-per-read scan
         __syncwarp();
         int strong, trust;
         if (a.pass == 0) {
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
         int nN = 0, nA = 0, nT = 0;
         build_planes_ool(M.P, a.seq + o, len, a.max_len, lane, nN, nA, nT);
         #pragma unroll 1
-        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j];
+        for (int j = lane; j < kcnt; j += 32) M.counts[j] = a.counts[o + j] & 0x7fffffff;  // bit 31: validity flag of the thread-per-read scan
         if (result == -2) {
             #pragma unroll 1
             for (int i = lane; i < len; i += 32) M.fix[i] = a.fixbuf[o + i];
@@ -656,7 +656,8 @@ cudaError_t rcx_launch_correct(const RcxCorrectArgs& a0, int sm_count, int dfs_g
         if (e != cudaSuccess) return e;
     }
     MARK();
-    e = launch_one(rcx_finalize_kernel, a, sm_count, a.n, smem, s);
+    if (prep0_done && rcx_finalize_thread_supported(a.max_len, a.t.k)) e = rcx_launch_finalize_thread(a, sm_count, s);
+    else e = launch_one(rcx_finalize_kernel, a, sm_count, a.n, smem, s);
     if (e != cudaSuccess) return e;
     MARK();
 #undef MARK

@@ -16,6 +16,7 @@
 #define RCX_EMPTY_KEY 0xffffffffffffffffull  // never canonical for k <= 32 (revcomp of T..T is 0)
 #define RCX_INF 1000000000                   // utils.h:10
 #define RCX_MAX_TRIAL 1025                   // ErrorCorrection.cpp:7
+#define RCX_COUNT_INVALID 0x80000000u        // counts[] between the thread-per-read kernels: the window holds a non-ACGT base
 
 // ----------------------------------------------------------------------------- table
 // The table is keyed by (k-1)-mer CONTEXTS, not by k-mers.  One entry = 32 bytes = ONE L2 sector:
@@ -350,6 +351,58 @@ __device__ __forceinline__ int rcx_regsort_get(const int (&v)[R], int idx) {
         if ((idx >> 5) == r) x = v[r];
     return __shfl_sync(RCX_FULL, x, idx & 31);
 }
+
+// a bit mask over the positions / k-mers of one read in NW 64-bit registers (all loops unrolled: no dynamic indexing)
+template <int NW>
+struct RcxMask {
+    unsigned long long m[NW];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) m[w] = 0;
+    }
+    __device__ __forceinline__ bool nonzero() const {
+        unsigned long long o = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) o |= m[w];
+        return o != 0;
+    }
+    // bits [lo, hi] (inclusive) of word w as a mask, 0 if the range misses the word
+    static __device__ __forceinline__ unsigned long long range_word(int w, int lo, int hi) {
+        int l = lo - 64 * w, h = hi - 64 * w;
+        if (l < 0) l = 0;
+        if (h > 63) h = 63;
+        if (l > h) return 0;
+        return ((~0ull) >> (63 - (h - l))) << l;
+    }
+    __device__ __forceinline__ void set(int lo, int hi) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) m[w] |= range_word(w, lo, hi);
+    }
+    __device__ __forceinline__ bool any(int lo, int hi) const {
+        unsigned long long o = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) o |= m[w] & range_word(w, lo, hi);
+        return o != 0;
+    }
+    // first index in [from, limit) whose bit equals `want`, or `limit`
+    __device__ __forceinline__ int next(int from, int limit, bool want) const {
+        int best = limit;
+        if (from < limit) {
+#pragma unroll
+            for (int w = NW - 1; w >= 0; --w) {
+                unsigned long long x = (want ? m[w] : ~m[w]) & range_word(w, from, limit - 1);
+                if (x) best = 64 * w + __ffsll((long long)x) - 1;
+            }
+        }
+        return best;
+    }
+    // shift towards higher indices by s (0 <= s < 64)
+    __device__ __forceinline__ void shl(int s) {
+        if (s == 0) return;
+#pragma unroll
+        for (int w = NW - 1; w >= 0; --w) m[w] = (m[w] << s) | (w > 0 ? m[w - 1] >> (64 - s) : 0ull);
+    }
+};
 
 __host__ __device__ __forceinline__ int rcx_pow2_at_least(int n) {
     int p = 64;

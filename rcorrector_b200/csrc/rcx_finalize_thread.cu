@@ -1,0 +1,343 @@
+// rcx_finalize_thread.cu — the end of ErrorCorrection for reads of ordinary length, ONE THREAD per work item:
+// post-filters on fix[] (ErrorCorrection.cpp:1296-1466), apply (:1468-1479) and GetKmerInformation on the final
+// sequence (:1567-1602).  Same organisation as rcx_scan_thread.cu: a block stages a tile of work items through
+// shared memory (counts[], bases and fix[] of each item copied by a warp with coalesced loads), every thread then
+// runs the scalar filter logic on its own conflict-free rows, re-probes only the k-windows that cover a changed base
+// (software-pipelined one-sector lookups) and the few medians are served warp-cooperatively.
+//
+// The warp-per-item version of this kernel (rcx_correct.cu, still used for long reads) spent ~2 000 warp
+// instructions per item on bit-plane rebuilds, ballots and reductions (profiles/r01_g).
+#include "rcx_internal.h"
+
+#define TF_THREADS 128
+#define TF_DEPTH 4
+#define TF_INVALID 0x80000000u
+#define TF_CMASK 0x7fffffffu
+
+struct TfLayout {
+    int cw, bw;  // words per count row (odd), bytes per base / fix row
+    size_t smem;
+};
+__host__ __device__ inline TfLayout tf_layout(int max_len, int k) {
+    TfLayout L;
+    int kc = max_len - k + 1;
+    if (kc < 1) kc = 1;
+    L.cw = kc | 1;
+    L.bw = ((max_len + 3 + 3) & ~3) | 4;  // room for a word-aligned copy; multiple of 4 with an odd number of words (conflict-free across lanes)
+    L.smem = (size_t)TF_THREADS * (sizeof(int) * L.cw + 2 * (size_t)L.bw + 16) + 64;
+    return L;
+}
+
+__device__ __forceinline__ bool tf_find(const RcxTable& t, unsigned long long key, RcxEntryRegs& d) {
+    if ((d.q0 & RCX_KEY_MASK) == key) return true;
+    if (d.q0 == ~0ull || !(d.q0 & RCX_OVERFLOW_BIT)) return false;
+    const unsigned long long home = __umul64hi(rcx_hash(key), t.nlines << 2);
+    for (unsigned int i = 1;; ++i) {
+        rcx_issue(t, rcx_probe_sector(t, home, i), d);
+        if (d.q0 == ~0ull) return false;
+        if ((d.q0 & RCX_KEY_MASK) == key) return true;
+        if (i >= 4 * t.nlines) return false;
+    }
+}
+
+struct TfMeta {
+    uint32_t r, o;
+    int len, status;
+};
+// 4-byte global -> shared copy without a register round trip (LDGSTS)
+__device__ __forceinline__ void tf_cp4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+struct TfPend {
+    unsigned long long key;
+    RcxEntryRegs d;
+    int info;  // -1: empty; else window j | base << 10 | flip << 12
+};
+
+template <int NW>
+__global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxCorrectArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = a.t.k, K = a.max_fix_per_k, Q = a.bad_qual;
+    const TfLayout LY = tf_layout(a.max_len, k);
+    unsigned int* cnt_all = reinterpret_cast<unsigned int*>(smem_raw);
+    unsigned char* seq_all = reinterpret_cast<unsigned char*>(cnt_all + (size_t)TF_THREADS * LY.cw);
+    signed char* fix_all = reinterpret_cast<signed char*>(seq_all + (size_t)TF_THREADS * LY.bw);
+    TfMeta* meta = reinterpret_cast<TfMeta*>(fix_all + (size_t)TF_THREADS * LY.bw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const long long nwork = (long long)a.counters[RCX_C_NWORK];
+    const long long ntiles = (nwork + TF_THREADS - 1) / TF_THREADS;
+    const int stride = rcx_state_stride(a.max_len, k);
+    unsigned int n_rprobes = 0;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long w0 = tile * TF_THREADS;
+        const int nw = (int)((nwork - w0) < TF_THREADS ? (nwork - w0) : TF_THREADS);
+        __syncthreads();
+        // ---- stage: every thread fetches the metadata of its own item, then a warp copies one item at a time with
+        // cp.async (global -> shared without a register round trip, so the copies of all items overlap)
+        if (tid < nw) {
+            const long long rr = a.worklist[w0 + tid];
+            const uint32_t oo = a.off[rr];
+            meta[tid].r = (uint32_t)rr;
+            meta[tid].o = oo;
+            meta[tid].len = (int)(a.off[rr + 1] - oo);
+            meta[tid].status = a.state[(w0 + tid) * stride + ST_STATUS];
+        }
+        __syncthreads();
+        for (int t = warp; t < nw; t += TF_THREADS / 32) {
+            const uint32_t o = meta[t].o;
+            const int len = meta[t].len, kc = len - k + 1;
+            const bool post = meta[t].status == RCX_ST_POSTFILTER;
+            unsigned int* row = cnt_all + (size_t)t * LY.cw;
+            unsigned char* Sw = seq_all + (size_t)t * LY.bw;   // word-aligned copies: the row starts at base (o & ~3)
+            signed char* Xw = fix_all + (size_t)t * LY.bw;
+            for (int j = lane; j < kc; j += 32) tf_cp4(row + j, a.counts + o + j);
+            const uint32_t ob = o & ~3u;
+            const int nwords = (int)(((o + len + 3) & ~3u) - ob) >> 2;
+            for (int i = lane; i < nwords; i += 32) {
+                tf_cp4(Sw + 4 * i, a.seq + ob + 4 * i);
+                if (post) tf_cp4(Xw + 4 * i, a.fixbuf + ob + 4 * i);
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+
+        const bool have = tid < nw;
+        long long r = 0;
+        uint32_t o = 0;
+        int len = 0, kcnt = 0, result = 0;
+        unsigned int* row = cnt_all + (size_t)tid * LY.cw;
+        unsigned char* S = seq_all + (size_t)tid * LY.bw;
+        signed char* X = fix_all + (size_t)tid * LY.bw;
+        int nvalid = 0, vmin = 0x7fffffff, vmax = 0, med = 0;
+        if (have) {
+            r = meta[tid].r;
+            o = meta[tid].o;
+            len = meta[tid].len;
+            kcnt = len - k + 1;
+            S += o & 3;
+            X += o & 3;
+            const int* st = a.state + (w0 + tid) * stride;
+            result = meta[tid].status;
+            const bool post_staged = result == RCX_ST_POSTFILTER;
+            const int total_fix = st[ST_TOTALFIX], bad_segments = st[ST_BADSEG];
+            (void)post_staged;
+            bool changed = false;
+            RcxMask<NW> need;  // k-windows whose count must be looked up again
+            need.clear();
+            if (result == RCX_ST_POSTFILTER) {
+                // ---------------- A.7 post-filters (:1296-1466)
+                const char* q = a.qual + o;
+                const int q0 = q[0];
+                unsigned char P[256];  // ascending positions with a fix on a non-N base (max_len <= 255)
+                int np = 0;
+                for (int i = 0; i < len; ++i)
+                    if (X[i] != -1 && S[i] != 'N') P[np++] = (unsigned char)i;
+                for (int i = 1; i < np; ++i) {  // pair filter (:1314-1398)
+                    const int pa = P[i - 1], pb = P[i];
+                    if (q0 != 0 && q[pb] <= Q && q[pa] <= Q) continue;
+                    if (pb - pa + 1 > k) continue;
+                    const int lim = (i < np - 1) ? P[i + 1] - k + 1 : 0x7fffffff;  // j + k - 1 >= P[i+1]  <=>  j >= lim
+                    int j0 = pa - k + 1;
+                    if (j0 < 0) j0 = 0;
+                    const int skip = (i >= 2) ? P[i - 2] : -1;  // j <= P[i-2] is skipped BEFORE the break tests
+                    int e1 = pb - k + 1;
+                    if (e1 > lim) e1 = lim;
+                    if (e1 < skip + 1) e1 = skip + 1;
+                    if (e1 < j0) e1 = j0;
+                    if (e1 > kcnt) e1 = kcnt;
+                    int e2 = pa + 1;
+                    if (e2 > lim) e2 = lim;
+                    if (e2 > kcnt) e2 = kcnt;
+                    if (e2 < e1) e2 = e1;
+                    int e3 = pb + 1;
+                    if (e3 > lim) e3 = lim;
+                    if (e3 > kcnt) e3 = kcnt;
+                    if (e3 < e2) e3 = e2;
+                    int ms = RCX_INF, md = RCX_INF;
+                    for (int j = j0; j < e3; ++j) {
+                        const int c = (int)(row[j] & TF_CMASK);  // (bit 31 = validity flag; an invalid window counts 0)
+                        if (j < e1) { if (j > skip && c < ms) ms = c; }
+                        else if (j < e2) { if (c < md) md = c; }
+                        else { if (c < ms) ms = c; }
+                    }
+                    if (ms != RCX_INF && md != RCX_INF && ms > 1 && md > 1 && ms > md / 2 && ms < 2 * md) {
+                        X[pb] = -1; X[pa] = -1;
+                        int j = i - 2;
+                        while (j >= 0 && P[j + 1] - P[j] + 1 <= k) { X[P[j]] = -1; --j; }
+                        while (i + 1 < np && P[i + 1] - P[i] + 1 <= k) { X[P[i + 1]] = -1; ++i; }
+                    }
+                }
+                if (total_fix > 3 && len > 10) {  // edge filter (:1407-1430)
+                    int c = 0;
+                    for (int i = 0; i < 10; ++i) c += S[i] != 'N' && X[i] != -1 && q[i] > Q;
+                    if (c >= 2)
+                        for (int i = 0; i < 10; ++i) if (S[i] != 'N') X[i] = -1;
+                    c = 0;
+                    for (int i = len - 10; i < len; ++i) c += S[i] != 'N' && X[i] != -1 && q[i] > Q;
+                    if (c >= 3)
+                        for (int i = len - 10; i < len; ++i) if (S[i] != 'N') X[i] = -1;
+                }
+                if (total_fix >= K) {  // density filter (:1432-1455), weights doubled to stay in integers
+                    int sum = 0;
+                    bool dense = false;
+                    for (int i = 0; i < len; ++i) {
+                        if (X[i] != -1 && S[i] != 'N') sum += q[i] > Q ? 2 : 1;
+                        if (i >= k && X[i - k] != -1 && S[i - k] != 'N') sum -= q[i - k] > Q ? 2 : 1;
+                        if (i >= k - 1 && sum > 2 * K) dense = true;
+                    }
+                    if (dense) result = -1;
+                }
+                if (result == RCX_ST_POSTFILTER) {  // apply (:1468-1479)
+                    int ret = 0;
+                    for (int i = 0; i < len; ++i)
+                        if (X[i] != -1) {
+                            a.seq[o + i] = "ACGT"[X[i]];
+                            ++ret;
+                            need.set(i - k + 1 > 0 ? i - k + 1 : 0, i < kcnt - 1 ? i : kcnt - 1);  // windows that cover the changed base
+                        }
+                    if (ret == 0 && bad_segments > 0) result = -1;
+                    else { result = ret; changed = ret > 0; }
+                }
+            }
+            // ---------------- GetKmerInformation on the final sequence (:1567-1602).  Unchanged windows keep the count and the
+            // validity flag of the scan; the runs of windows that cover a changed base are rolled and looked up again
+            // (TF_DEPTH one-sector lookups in flight).
+            if (changed) {
+                int jpos = 0;
+                for (;;) {
+                    const int s0 = need.next(jpos, kcnt, true);
+                    if (s0 >= kcnt) break;
+                    const int e0 = need.next(s0, kcnt, false);
+                    jpos = e0;
+                    unsigned long long F = 0;
+                    int run = 0, i = s0;
+                    auto append = [&]() {
+                        const unsigned char ch = S[i];
+                        const int fx = X[i];
+                        const unsigned int idx = (unsigned int)ch - 'A';
+                        const bool ok = fx != -1 || (idx < 26u && ((0x00080045u >> idx) & 1u));
+                        const int code = fx != -1 ? fx : (ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 3);
+                        F = ((F << 2) | (unsigned long long)code) & kmask;
+                        run = ok ? run + 1 : 0;
+                        ++i;
+                    };
+                    for (int q = 0; q < k - 1; ++q) append();
+                    int j = s0;
+                    while (j < e0) {
+                        TfPend p[TF_DEPTH];
+#pragma unroll
+                        for (int u = 0; u < TF_DEPTH; ++u) {
+                            p[u].info = -1;
+                            if (j < e0) {
+                                append();  // window j = the k bases that end here
+                                if (run >= k) {  // right extension of its prefix context
+                                    const unsigned long long ctx = F >> 2;
+                                    const unsigned long long rc = rcx_revcomp(ctx, k - 1);
+                                    const bool flip = rc < ctx;
+                                    p[u].key = flip ? rc : ctx;
+                                    p[u].info = j | ((int)(F & 3) << 10) | (flip ? 1 << 12 : 0);
+                                    rcx_issue(a.t, __umul64hi(rcx_hash(p[u].key), a.t.nlines << 2), p[u].d);
+                                    ++n_rprobes;
+                                } else {
+                                    row[j] = TF_INVALID;
+                                }
+                                ++j;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < TF_DEPTH; ++u) {
+                            const int info = p[u].info;
+                            if (info >= 0) {
+                                int c = 0;
+                                if (tf_find(a.t, p[u].key, p[u].d)) {
+                                    const bool flip = (info >> 12) & 1;
+                                    const int b = (info >> 10) & 3;
+                                    unsigned int f0, f1, f2, f3;
+                                    rcx_group(p[u].d, flip, f0, f1, f2, f3);  // right extension: RIGHT group, LEFT when flipped
+                                    const int bb = flip ? 3 - b : b;
+                                    const unsigned int f = bb == 0 ? f0 : bb == 1 ? f1 : bb == 2 ? f2 : f3;
+                                    c = (int)f;
+                                    if (f == RCX_BIG) {
+                                        const unsigned long long ctx = flip ? rcx_revcomp(p[u].key, k - 1) : p[u].key;
+                                        c = rcx_big_count(a.t, rcx_canonical(rcx_ext_kmer(ctx, false, b, k), k));
+                                    }
+                                }
+                                row[info & 1023] = (unsigned int)c;
+                            }
+                        }
+                    }
+                }
+            }
+            for (int j = 0; j < kcnt; ++j) {
+                const unsigned int x = row[j];
+                if (!(x & TF_INVALID)) {
+                    int v = (int)x;
+                    v = v == 0 ? 1 : v;
+                    ++nvalid;
+                    vmin = v < vmin ? v : vmin;
+                    vmax = v > vmax ? v : vmax;
+                }
+            }
+            // element [nvalid / 2] of the ascending valid counts: bisection on the value, the bounds snap to values that
+            // occur (every lane of the warp needs one, so each walks its own row)
+            if (nvalid > 0) {
+                const int rank = nvalid / 2;
+                int lo = vmin, hi = vmax;
+                while (lo < hi) {
+                    const int mid = lo + (int)(((unsigned int)hi - (unsigned int)lo) >> 1);
+                    int c = 0, maxle = lo, mingt = hi;
+                    for (int j = 0; j < kcnt; ++j) {
+                        const unsigned int x = row[j];
+                        if (!(x & TF_INVALID)) {
+                            int v = (int)x;
+                            v = v == 0 ? 1 : v;
+                            const bool le = v <= mid;
+                            c += le;
+                            maxle = (le && v > maxle) ? v : maxle;
+                            mingt = (!le && v < mingt) ? v : mingt;
+                        }
+                    }
+                    if (c > rank) hi = maxle; else lo = mingt;
+                }
+                med = lo;
+            }
+        }
+        if (have) {
+            int l = 0, m = 0, h = 0;
+            if (nvalid > 0) { l = vmin; h = vmax; m = med; }
+            a.correction[r] = result; a.l[r] = l; a.m[r] = m; a.h[r] = h;
+        }
+    }
+    n_rprobes = __reduce_add_sync(RCX_FULL, n_rprobes);
+    if (lane == 0 && n_rprobes) atomicAdd(&a.counters[RCX_C_RESCAN_PROBES], (unsigned long long)n_rprobes);
+}
+
+bool rcx_finalize_thread_supported(int max_len, int k) {
+    const int kc = max_len - k + 1;
+    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && tf_layout(max_len, k).smem <= 200 * 1024;
+}
+
+template <int NW>
+static cudaError_t launch_finalize_thread_nw(const RcxCorrectArgs& a, int sm_count, cudaStream_t s) {
+    const TfLayout L = tf_layout(a.max_len, a.t.k);
+    cudaError_t e = cudaFuncSetAttribute(rcx_finalize_thread_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_finalize_thread_kernel<NW>, TF_THREADS, L.smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (a.n + TF_THREADS - 1) / TF_THREADS;
+    long long grid = (long long)sm_count * per_sm;  // persistent grid (the work-list length lives on the device)
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    rcx_finalize_thread_kernel<NW><<<(unsigned int)grid, TF_THREADS, L.smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cudaStream_t s) {
+    if (a.max_len <= 128) return launch_finalize_thread_nw<2>(a, sm_count, s);
+    return launch_finalize_thread_nw<4>(a, sm_count, s);
+}

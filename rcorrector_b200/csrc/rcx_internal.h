@@ -115,6 +115,9 @@ size_t rcx_correct_smem_per_warp(int max_len, int k);
 size_t rcx_state_words(int max_len, int k);
 // kev: 7 events recorded before triage, prep0, dfs0, prep1, dfs1, finalize and after finalize (may be null)
 cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_grid, cudaStream_t s, cudaEvent_t* kev, bool prep0_done);
+// thread-per-item post-filters + apply + l/m/h (rcx_finalize_thread.cu)
+bool rcx_finalize_thread_supported(int max_len, int k);
+cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);
 // search (rcx_dfs.cu)
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad);
 size_t rcx_dfs_stack_words(int grid, int depth);

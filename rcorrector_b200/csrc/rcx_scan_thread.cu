@@ -103,57 +103,35 @@ __device__ __forceinline__ int ts_select(const unsigned int* row, int kcnt, int 
     return lo;
 }
 
-// a bit mask over the positions / k-mers of one read in NW 64-bit registers (all loops unrolled: no dynamic indexing)
-template <int NW>
-struct TsMask {
-    unsigned long long m[NW];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) m[w] = 0;
-    }
-    __device__ __forceinline__ bool nonzero() const {
-        unsigned long long o = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) o |= m[w];
-        return o != 0;
-    }
-    // bits [lo, hi] (inclusive) of word w as a mask, 0 if the range misses the word
-    static __device__ __forceinline__ unsigned long long range_word(int w, int lo, int hi) {
-        int l = lo - 64 * w, h = hi - 64 * w;
-        if (l < 0) l = 0;
-        if (h > 63) h = 63;
-        if (l > h) return 0;
-        return ((~0ull) >> (63 - (h - l))) << l;
-    }
-    __device__ __forceinline__ void set(int lo, int hi) {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) m[w] |= range_word(w, lo, hi);
-    }
-    __device__ __forceinline__ bool any(int lo, int hi) const {
-        unsigned long long o = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) o |= m[w] & range_word(w, lo, hi);
-        return o != 0;
-    }
-    // first index in [from, limit) whose bit equals `want`, or `limit`
-    __device__ __forceinline__ int next(int from, int limit, bool want) const {
-        int best = limit;
-        if (from < limit) {
-#pragma unroll
-            for (int w = NW - 1; w >= 0; --w) {
-                unsigned long long x = (want ? m[w] : ~m[w]) & range_word(w, from, limit - 1);
-                if (x) best = 64 * w + __ffsll((long long)x) - 1;
+// The same selection for the FEW lanes of a warp that need it (reads without a drop, reads that leave at the triage):
+// instead of every lane walking its own row while the others idle, the warp serves the requests one after the other,
+// all 32 lanes counting a slice of the requester's row (conflict-free: consecutive words).  Must be called convergently.
+template <int KIND>
+__device__ __forceinline__ int ts_select_coop(const unsigned int* warp_rows, int cw, int lane, bool need, int kcnt, int rank, int lo, int hi) {
+    int result = lo;
+    __syncwarp();  // the rows were written by their owner lanes
+    unsigned int pending = __ballot_sync(RCX_FULL, need);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const unsigned int* row = warp_rows + (size_t)src * cw;
+        const int n = __shfl_sync(RCX_FULL, kcnt, src), rk = __shfl_sync(RCX_FULL, rank, src);
+        int l = __shfl_sync(RCX_FULL, lo, src), h = __shfl_sync(RCX_FULL, hi, src);
+        while (l < h) {
+            const int mid = l + (int)(((unsigned int)h - (unsigned int)l) >> 1);
+            int c = 0;
+            for (int j = lane; j < n; j += 32) {
+                const unsigned int x = row[j];
+                if (KIND == 0) c += ts_masked(x) <= mid;
+                else if (!(x & TS_INVALID)) { int v = (int)(x & TS_CMASK); v = v == 0 ? 1 : v; c += v <= mid; }
             }
+            c = __reduce_add_sync(RCX_FULL, c);
+            if (c > rk) h = mid; else l = mid + 1;
         }
-        return best;
+        if (lane == src) result = l;
     }
-    // shift towards higher indices by s (0 <= s < 64)
-    __device__ __forceinline__ void shl(int s) {
-        if (s == 0) return;
-#pragma unroll
-        for (int w = NW - 1; w >= 0; --w) m[w] = (m[w] << s) | (w > 0 ? m[w - 1] >> (64 - s) : 0ull);
-    }
-};
+    return result;
+}
 
 template <int NW>
 __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanArgs a) {
@@ -293,7 +271,8 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
 
         // ------------------------------------------------------------------ GetStrongTrustedThreshold (:1507-1563)
         int minc = 0x7fffffff, nvalid = 0, vmin = 0x7fffffff, vmax = 0;
-        bool any_strict = false;
+        bool any_strict = false, need_sel = false;
+        int sel_rank = 0, sel_lo = 0, sel_hi = 0;
         if (have && kcnt > 0 && !(nN > 5 || nA > len - k || nT > len - k)) {
             unsigned int present = 0;
             int nonpos = 0, gmin = 0x7fffffff, gmax = -1;
@@ -326,13 +305,18 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
                 if (mn > 2 * mx) { found = true; thr = mn; below = mx; break; }
                 leftm = lower;
             }
-            if (!found) thr = ts_select<0>(row, kcnt, (nonpos + kcnt - 1) / 2, gmin, gmax);  // median of the positive entries
+            if (!found) { need_sel = true; sel_rank = (nonpos + kcnt - 1) / 2; sel_lo = gmin; sel_hi = gmax; }  // median of the positive entries
             flags = found ? (uint8_t)(RCX_F_DROP | (below == 2 ? RCX_F_PREV2 : 0)) : (uint8_t)0;
+        }
+        {
+            const int med = ts_select_coop<0>(cnt_all + (size_t)(warp * 32) * LY.cw, LY.cw, lane, need_sel, kcnt, sel_rank, sel_lo, sel_hi);
+            if (need_sel) thr = med;
         }
         if (have) { a.thr[r] = thr; a.flags[r] = flags; }
 
         // ------------------------------------------------------------------ triage
         int result = -3;  // -3: no read / scan only; -2: work item; else final
+        bool need_info = false;
         int strong = 0, trust = 0;
         const int mate_thr = __shfl_xor_sync(RCX_FULL, thr, 1);  // mates are records 2i, 2i+1 = neighbouring lanes
         if (have && a.triage) {
@@ -366,10 +350,16 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
                             vmax = v > vmax ? v : vmax;
                         }
                     }
-                    int l = 0, m = 0, h = 0;
-                    if (nvalid > 0) { l = vmin; h = vmax; m = ts_select<1>(row, kcnt, nvalid / 2, vmin, vmax); }
-                    a.correction[r] = result; a.l[r] = l; a.m[r] = m; a.h[r] = h;
+                    need_info = true;
                 }
+            }
+        }
+        {   // the median of the tags, served warp-cooperatively for the lanes that leave here
+            const int med = ts_select_coop<1>(cnt_all + (size_t)(warp * 32) * LY.cw, LY.cw, lane, need_info && nvalid > 0, kcnt, nvalid / 2, vmin, vmax);
+            if (need_info) {
+                int l = 0, m = 0, h = 0;
+                if (nvalid > 0) { l = vmin; h = vmax; m = med; }
+                a.correction[r] = result; a.l[r] = l; a.m[r] = m; a.h[r] = h;
             }
         }
         // work-list slots: one atomic per block
@@ -391,7 +381,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             const long long item = (long long)(unsigned int)blk[8] + blk[warp] + __popc(wb & ((1u << lane) - 1));
             a.worklist[item] = (uint32_t)r;
             int* st = a.state + item * stride;
-            TsMask<NW> T, S, LOWM, M;  // trusted k-mers (:875), strict poly-A k-mers, counts <= 2 && < trust, trusted positions
+            RcxMask<NW> T, S, LOWM, M;  // trusted k-mers (:875), strict poly-A k-mers, counts <= 2 && < trust, trusted positions
             T.clear(); S.clear(); LOWM.clear(); M.clear();
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
@@ -436,7 +426,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
                 if (havei && pf <= pt) M.set(pf, pt + k - 1);
             }
             // islands of trusted positions (:977-1007); none: the longest trusted run stands in (without becoming "strong")
-            TsMask<NW> I = M;
+            RcxMask<NW> I = M;
             if (!M.nonzero()) I.set(tstart, tend + k - 1);
             // seed k-mer of a search = Restart + k Appends of seq[j0 .. j0+k) (j0 may be -1, see :1139-1142)
             auto seed = [&](int j0, unsigned long long& code, int& inv) {
@@ -494,7 +484,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             }
             // per-base info for the search (:343 / :577): substitutions are allowed on untrusted positions outside strict
             // poly-A k-mers: Right tests k-mer i-k+1, Left k-mer i
-            TsMask<NW> SR = S;
+            RcxMask<NW> SR = S;
             SR.shl(k - 1);
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
@@ -515,7 +505,8 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             const uint32_t ot = offs[t];
             const int kc = (int)(offs[t + 1] - ot) - k + 1;
             const unsigned int* rw = cnt_all + (size_t)t * LY.cw;
-            for (int j = lane; j < kc; j += 32) a.counts[ot + j] = (int)(rw[j] & TS_CMASK);
+            // (with the correction kernels downstream, bit 31 tells them that the window holds a non-ACGT base)
+            for (int j = lane; j < kc; j += 32) a.counts[ot + j] = (int)((rw[j] & TS_CMASK) | ((a.triage && (rw[j] & TS_INVALID)) ? RCX_COUNT_INVALID : 0u));
         }
         if (a.triage) {
             for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) {
