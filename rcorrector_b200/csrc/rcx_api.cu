@@ -49,10 +49,39 @@ struct DevBuf {
     }
 };
 
+// One pipeline slot = everything one batch (or one chunk of a host batch) needs on the device: a stream, the staging
+// buffers, the intermediates of the hot path and the events that time it.  Host batches are cut into chunks that cycle
+// through RCX_NSLOTS slots so that the PCIe copies of one chunk overlap the kernels of another.
+#define RCX_NSLOTS 3
+struct RcxSlot {
+    cudaStream_t stream = nullptr;
+    DevBuf<char> d_seq, d_qual;
+    DevBuf<uint32_t> d_off;
+    DevBuf<int32_t> d_counts, d_thr, d_corr, d_l, d_m, d_h;
+    DevBuf<uint8_t> d_flags;
+    DevBuf<uint32_t> d_worklist, d_worklist2;
+    DevBuf<int32_t> d_state;
+    DevBuf<signed char> d_fixbuf, d_dfs_path;
+    DevBuf<unsigned char> d_posbuf;
+    DevBuf<unsigned int> d_dfs_stack;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* h_counters = nullptr;  // pinned landing area of the counters
+    cudaEvent_t ev[6]{};
+    cudaEvent_t kev[7]{};  // per-kernel marks inside the correction pipeline
+    bool kev_valid = false;
+    bool pending = false;  // work enqueued whose counters / timings have not been harvested yet
+    int launches = 0;
+    void release() {
+        d_seq.release(); d_qual.release(); d_off.release(); d_counts.release(); d_thr.release(); d_corr.release(); d_l.release();
+        d_m.release(); d_h.release(); d_flags.release(); d_worklist.release(); d_worklist2.release(); d_state.release();
+        d_fixbuf.release(); d_dfs_path.release(); d_posbuf.release(); d_dfs_stack.release();
+    }
+};
+
 struct rcx_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // = slot[0].stream: table build, device-resident batches
     // table
     RcxEntry* entries_dev = nullptr;     // the table: nlines * 4 sectors of 32 bytes
     unsigned long long nlines = 0;
@@ -65,20 +94,7 @@ struct rcx_ctx {
     // params
     rcx_params params{};
     bool have_params = false;
-    // intermediates + staging
-    DevBuf<char> d_seq, d_qual;
-    DevBuf<uint32_t> d_off;
-    DevBuf<int32_t> d_counts, d_thr, d_corr, d_l, d_m, d_h;
-    DevBuf<uint8_t> d_flags;
-    DevBuf<uint32_t> d_worklist, d_worklist2;
-    DevBuf<int32_t> d_state;
-    DevBuf<signed char> d_fixbuf, d_dfs_path;
-    DevBuf<unsigned char> d_posbuf;
-    DevBuf<unsigned int> d_dfs_stack;
-    unsigned long long* d_counters = nullptr;
-    cudaEvent_t ev[6]{};
-    cudaEvent_t kev[7]{};  // per-kernel marks inside the correction pipeline
-    bool kev_valid = false;
+    RcxSlot slot[RCX_NSLOTS];
     rcx_stats stats{};
 };
 
@@ -100,19 +116,16 @@ extern "C" int rcx_create(int device, rcx_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    // The table probes are independent random 32-byte sectors: ask the L2 not to fetch neighbouring sectors from HBM
-    // (default granularity fetched ~85 B per 32-B probe, profiles/r01_e).  RCX_L2_FETCH=64|128 overrides (a hint).
-    {
-        size_t gran = 32;
-        if (const char* e = getenv("RCX_L2_FETCH")) gran = (size_t)atoi(e);
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-        cudaGetLastError();
+    for (auto& sl : c->slot) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&sl.d_counters, sizeof(unsigned long long) * RCX_C_COUNT));
+        CUDA_TRY(cudaMemset(sl.d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT));
+        CUDA_TRY(cudaHostAlloc(&sl.h_counters, sizeof(unsigned long long) * RCX_C_COUNT, cudaHostAllocDefault));
+        memset(sl.h_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT);
+        for (auto& ev : sl.ev) CUDA_TRY(cudaEventCreate(&ev));
+        for (auto& ev : sl.kev) CUDA_TRY(cudaEventCreate(&ev));
     }
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * RCX_C_COUNT));
-    CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT));
-    for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
-    for (auto& ev : c->kev) CUDA_TRY(cudaEventCreate(&ev));
+    c->stream = c->slot[0].stream;
     *out = c;
     return RCX_OK;
 }
@@ -122,14 +135,16 @@ static void free_table(rcx_ctx* c);
 extern "C" void rcx_destroy(rcx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& sl : c->slot) if (sl.stream) cudaStreamSynchronize(sl.stream);
     free_table(c);
-    c->d_seq.release(); c->d_qual.release(); c->d_off.release(); c->d_counts.release(); c->d_thr.release();
-    c->d_corr.release(); c->d_l.release(); c->d_m.release(); c->d_h.release(); c->d_flags.release(); c->d_worklist.release(); c->d_worklist2.release(); c->d_state.release(); c->d_fixbuf.release(); c->d_dfs_path.release(); c->d_posbuf.release(); c->d_dfs_stack.release();
-    if (c->d_counters) cudaFree(c->d_counters);
-    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto& sl : c->slot) {
+        sl.release();
+        if (sl.d_counters) cudaFree(sl.d_counters);
+        if (sl.h_counters) cudaFreeHost(sl.h_counters);
+        for (auto& ev : sl.ev) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : sl.kev) if (ev) cudaEventDestroy(ev);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     delete c;
 }
 
@@ -147,14 +162,15 @@ extern "C" void rcx_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+static int harvest(rcx_ctx* c, RcxSlot& sl);
+
 extern "C" int rcx_sync(rcx_ctx* c) {
     if (!c) return fail(RCX_ERR_ARG, "rcx_sync: null context");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (auto& sl : c->slot) CUDA_TRY(cudaStreamSynchronize(sl.stream));
     return RCX_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ table
 static void free_table(rcx_ctx* c) {
     if (c->entries_dev) { cudaFree(c->entries_dev); c->entries_dev = nullptr; }
     if (c->big_keys) { cudaFree(c->big_keys); c->big_keys = nullptr; }
@@ -366,60 +382,6 @@ static int check_ready(const rcx_ctx* c, const char* who) {
     return RCX_OK;
 }
 
-static int launch_pipeline(rcx_ctx* c, int mode, int64_t n, char* d_seq, const char* d_qual, const uint32_t* d_off,
-                           uint64_t total_bases, int32_t max_len, int32_t* d_corr, int32_t* d_l, int32_t* d_m, int32_t* d_h,
-                           bool correct) {
-    CUDA_TRY(c->d_counts.ensure(total_bases + 1));
-    CUDA_TRY(c->d_thr.ensure((size_t)n + 2));
-    CUDA_TRY(c->d_flags.ensure((size_t)n + 2));
-    if (correct) {
-        CUDA_TRY(c->d_worklist.ensure((size_t)n + 2));
-        CUDA_TRY(c->d_worklist2.ensure((size_t)n + 2));
-        CUDA_TRY(c->d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
-        CUDA_TRY(c->d_fixbuf.ensure(total_bases + 64));
-        CUDA_TRY(c->d_posbuf.ensure(total_bases + 64));
-    }
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, c->stream));
-    RcxScanArgs sa;
-    sa.t = table_of(c);
-    sa.seq = d_seq; sa.off = d_off; sa.n = n; sa.max_len = max_len;
-    sa.counts = c->d_counts.p; sa.thr = c->d_thr.p; sa.flags = c->d_flags.p; sa.counters = c->d_counters;
-    sa.triage = correct ? 1 : 0; sa.mode = correct ? mode : RCX_SINGLE; sa.error_rate = c->params.error_rate;
-    sa.correction = d_corr; sa.l = d_l; sa.m = d_m; sa.h = d_h; sa.worklist = correct ? c->d_worklist.p : nullptr;
-    sa.total_bases = total_bases; sa.max_fix_per_k = c->params.max_fix_per_k;
-    sa.state = correct ? c->d_state.p : nullptr; sa.posbuf = correct ? c->d_posbuf.p : nullptr; sa.fixbuf = correct ? c->d_fixbuf.p : nullptr;
-    // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
-    // long reads (or RCX_SCAN_WARP=1): the warp-per-read kernels
-    const bool thread_scan = rcx_scan_thread_supported(max_len, c->k, d_seq) && !getenv("RCX_SCAN_WARP");
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, c->stream));
-    else CUDA_TRY(rcx_launch_scan(sa, c->sm_count, c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    c->stats.kernel_launches = 1;
-    c->kev_valid = false;
-    if (correct) {
-        RcxCorrectArgs ca;
-        ca.t = sa.t;
-        ca.seq = d_seq; ca.qual = d_qual; ca.off = d_off; ca.n = n; ca.max_len = max_len; ca.mode = mode;
-        ca.max_fix_per_k = c->params.max_fix_per_k; ca.error_rate = c->params.error_rate; ca.bad_qual = c->params.bad_qual;
-        ca.counts = c->d_counts.p; ca.thr = c->d_thr.p; ca.flags = c->d_flags.p;
-        ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = c->d_counters;
-        ca.worklist = c->d_worklist.p; ca.worklist2 = c->d_worklist2.p; ca.state = c->d_state.p; ca.fixbuf = c->d_fixbuf.p; ca.pass = 0;
-        int dfs_grid = 0;
-        rcx_dfs_geometry(c->sm_count, max_len, c->k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
-        CUDA_TRY(c->d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
-        CUDA_TRY(c->d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
-        ca.posbuf = c->d_posbuf.p; ca.dfs_stack = c->d_dfs_stack.p; ca.dfs_path = c->d_dfs_path.p;
-        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, c->stream, c->kev, thread_scan));
-        c->kev_valid = true;
-        c->stats.kernel_launches = thread_scan ? 5 : 6;  // scan (+ thresholds + triage [+ first preparation]), search, preparation + search of the second pass, finalize
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    c->stats.reads = (uint64_t)n;
-    c->stats.bases = total_bases;
-    return RCX_OK;
-}
-
 static int scan_lengths(const uint32_t* off, int64_t n, int32_t* max_len) {
     uint32_t mx = 0;
     for (int64_t r = 0; r < n; ++r) {
@@ -428,6 +390,115 @@ static int scan_lengths(const uint32_t* off, int64_t n, int32_t* max_len) {
     }
     if (mx > RCX_MAX_READ_LENGTH) return fail(RCX_ERR_ARG, "a read is longer than RCX_MAX_READ_LENGTH (1023)");
     *max_len = (int32_t)mx;
+    return RCX_OK;
+}
+
+
+// Enqueue the kernels of the hot path for one batch on `sl`.  The pointers may be "virtual" bases (a slot buffer minus the
+// chunk's first offset): the kernels index them with the ABSOLUTE offsets of `d_off`.
+static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d_seq, const char* d_qual, const uint32_t* d_off,
+                           uint64_t first_base, uint64_t end_base, int32_t max_len, int32_t* d_corr, int32_t* d_l, int32_t* d_m,
+                           int32_t* d_h, bool correct) {
+    const uint64_t span = end_base - first_base;
+    const uint64_t lead = first_base & 15;  // keeps every virtual base 16-byte aligned
+    CUDA_TRY(sl.d_counts.ensure(span + 32));
+    CUDA_TRY(sl.d_thr.ensure((size_t)n + 2));
+    CUDA_TRY(sl.d_flags.ensure((size_t)n + 2));
+    if (correct) {
+        CUDA_TRY(sl.d_worklist.ensure((size_t)n + 2));
+        CUDA_TRY(sl.d_worklist2.ensure((size_t)n + 2));
+        CUDA_TRY(sl.d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
+        CUDA_TRY(sl.d_fixbuf.ensure(span + 96));
+        CUDA_TRY(sl.d_posbuf.ensure(span + 96));
+    }
+    CUDA_TRY(cudaMemsetAsync(sl.d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, sl.stream));
+    RcxScanArgs sa;
+    sa.t = table_of(c);
+    sa.seq = d_seq; sa.off = d_off; sa.n = n; sa.max_len = max_len;
+    sa.counts = sl.d_counts.p + lead - first_base; sa.thr = sl.d_thr.p; sa.flags = sl.d_flags.p; sa.counters = sl.d_counters;
+    sa.triage = correct ? 1 : 0; sa.mode = correct ? mode : RCX_SINGLE; sa.error_rate = c->params.error_rate;
+    sa.correction = d_corr; sa.l = d_l; sa.m = d_m; sa.h = d_h; sa.worklist = correct ? sl.d_worklist.p : nullptr;
+    sa.total_bases = end_base; sa.max_fix_per_k = c->params.max_fix_per_k;
+    sa.state = correct ? sl.d_state.p : nullptr;
+    sa.posbuf = correct ? sl.d_posbuf.p + lead - first_base : nullptr;
+    sa.fixbuf = correct ? sl.d_fixbuf.p + lead - first_base : nullptr;
+    // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
+    // long reads (or RCX_SCAN_WARP=1): the warp-per-read kernels
+    const bool thread_scan = rcx_scan_thread_supported(max_len, c->k, d_seq) && !getenv("RCX_SCAN_WARP");
+    CUDA_TRY(cudaEventRecord(sl.ev[1], sl.stream));
+    if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, sl.stream));
+    else CUDA_TRY(rcx_launch_scan(sa, c->sm_count, sl.stream));
+    CUDA_TRY(cudaEventRecord(sl.ev[2], sl.stream));
+    sl.launches = 1;
+    sl.kev_valid = false;
+    if (correct) {
+        RcxCorrectArgs ca;
+        ca.t = sa.t;
+        ca.seq = d_seq; ca.qual = d_qual; ca.off = d_off; ca.n = n; ca.max_len = max_len; ca.mode = mode;
+        ca.max_fix_per_k = c->params.max_fix_per_k; ca.error_rate = c->params.error_rate; ca.bad_qual = c->params.bad_qual;
+        ca.counts = sa.counts; ca.thr = sl.d_thr.p; ca.flags = sl.d_flags.p;
+        ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = sl.d_counters;
+        ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
+        int dfs_grid = 0;
+        rcx_dfs_geometry(c->sm_count, max_len, c->k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
+        CUDA_TRY(sl.d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
+        CUDA_TRY(sl.d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
+        ca.posbuf = sa.posbuf; ca.dfs_stack = sl.d_dfs_stack.p; ca.dfs_path = sl.d_dfs_path.p;
+        CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, sl.stream, sl.kev, thread_scan));
+        sl.kev_valid = true;
+        sl.launches = thread_scan ? 5 : 6;  // scan (+ thresholds + triage [+ first preparation]), search, preparation + search of the second pass, finalize
+    }
+    CUDA_TRY(cudaEventRecord(sl.ev[3], sl.stream));
+    return RCX_OK;
+}
+
+// add the counters and CUDA-event times of a finished slot to the statistics of the current call
+static int harvest(rcx_ctx* c, RcxSlot& sl) {
+    if (!sl.pending) return RCX_OK;
+    CUDA_TRY(cudaStreamSynchronize(sl.stream));
+    const unsigned long long* h = sl.h_counters;
+    c->stats.scan_probes += h[RCX_C_SCAN_PROBES];
+    c->stats.search_probes += h[RCX_C_SEARCH_PROBES];
+    c->stats.rescan_probes += h[RCX_C_RESCAN_PROBES];
+    c->stats.search_nodes += h[RCX_C_SEARCH_NODES];
+    c->stats.work_items += h[RCX_C_NWORK];
+    c->stats.second_pass += h[RCX_C_NWORK2];
+    c->stats.unsupported += h[RCX_C_UNSUPPORTED];
+    c->stats.kernel_launches += (uint64_t)sl.launches;
+    auto ms = [&](cudaEvent_t a, cudaEvent_t b) {
+        float v = 0;
+        if (cudaEventElapsedTime(&v, a, b) != cudaSuccess) { cudaGetLastError(); v = 0; }
+        return v;
+    };
+    c->stats.ms_h2d += ms(sl.ev[0], sl.ev[1]);
+    c->stats.ms_scan += ms(sl.ev[1], sl.ev[2]);
+    c->stats.ms_correct += ms(sl.ev[2], sl.ev[3]);
+    c->stats.ms_d2h += ms(sl.ev[4], sl.ev[5]);
+    c->stats.ms_total += ms(sl.ev[0], sl.ev[5]);
+    if (sl.kev_valid) {
+        c->stats.ms_triage += ms(sl.kev[0], sl.kev[1]);
+        c->stats.ms_prep += ms(sl.kev[1], sl.kev[2]) + ms(sl.kev[3], sl.kev[4]);
+        c->stats.ms_dfs += ms(sl.kev[2], sl.kev[3]) + ms(sl.kev[4], sl.kev[5]);
+        c->stats.ms_finalize += ms(sl.kev[5], sl.kev[6]);
+    }
+    sl.pending = false;
+    return RCX_OK;
+}
+static int begin_call(rcx_ctx* c, uint64_t reads, uint64_t bases) {
+    for (auto& sl : c->slot) {
+        int rc = harvest(c, sl);
+        if (rc) return rc;
+    }
+    c->stats = rcx_stats{};
+    c->stats.reads = reads;
+    c->stats.bases = bases;
+    return RCX_OK;
+}
+// the tail every enqueue shares: counters to the pinned landing area, final event
+static int finish_enqueue(RcxSlot& sl) {
+    CUDA_TRY(cudaMemcpyAsync(sl.h_counters, sl.d_counters, sizeof(unsigned long long) * RCX_C_COUNT, cudaMemcpyDeviceToHost, sl.stream));
+    CUDA_TRY(cudaEventRecord(sl.ev[5], sl.stream));
+    sl.pending = true;
     return RCX_OK;
 }
 
@@ -442,14 +513,19 @@ extern "C" int rcx_correct_batch_device(rcx_ctx* c, int mode, int64_t n, char* s
     if (!seq || !qual || !off || !correction || !l || !m || !h) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: null pointer");
     if (max_len < 1 || max_len > RCX_MAX_READ_LENGTH) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: bad max_len");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    rc = launch_pipeline(c, mode, n, seq, qual, off, total, max_len, correction, l, m, h, true);
+    rc = begin_call(c, (uint64_t)n, total);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-    return RCX_OK;
+    RcxSlot& sl = c->slot[0];
+    CUDA_TRY(cudaEventRecord(sl.ev[0], sl.stream));
+    rc = launch_pipeline(c, sl, mode, n, seq, qual, off, 0, total, max_len, correction, l, m, h, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(sl.ev[4], sl.stream));
+    return finish_enqueue(sl);
 }
 
+// Host batch: cut into chunks of whole records (pairs stay together) that cycle through the slots, so that the
+// host -> device copy of chunk i+1 and the device -> host copy of chunk i-1 overlap the kernels of chunk i
+// (needs pinned host buffers to be truly asynchronous: rcx_host_alloc).  Results do not depend on the chunking.
 extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* seq_in, const char* qual, const uint32_t* off,
                                  char* seq_out, int32_t* correction, int32_t* l, int32_t* m, int32_t* h) {
     int rc = check_ready(c, "rcx_correct_batch");
@@ -459,34 +535,51 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
     if (n == 0) return RCX_OK;
     if (!seq_in || !qual || !off || !seq_out || !correction || !l || !m || !h) return fail(RCX_ERR_ARG, "rcx_correct_batch: null pointer");
     if (off[0] != 0) return fail(RCX_ERR_ARG, "rcx_correct_batch: off[0] must be 0");
-    int32_t max_len = 0;
-    rc = scan_lengths(off, n, &max_len);
-    if (rc) return rc;
-    const uint64_t total = off[n];
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(c->d_seq.ensure(total + 64));
-    CUDA_TRY(c->d_qual.ensure(total + 64));
-    CUDA_TRY(c->d_off.ensure((size_t)n + 1));
-    CUDA_TRY(c->d_corr.ensure((size_t)n));
-    CUDA_TRY(c->d_l.ensure((size_t)n));
-    CUDA_TRY(c->d_m.ensure((size_t)n));
-    CUDA_TRY(c->d_h.ensure((size_t)n));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_seq.p, seq_in, total, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_qual.p, qual, total, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_off.p, off, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    if (max_len < 1) max_len = 1;
-    rc = launch_pipeline(c, mode, n, c->d_seq.p, c->d_qual.p, c->d_off.p, total, max_len, c->d_corr.p, c->d_l.p, c->d_m.p,
-                         c->d_h.p, true);
+    rc = begin_call(c, (uint64_t)n, off[n]);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(seq_out, c->d_seq.p, total, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(correction, c->d_corr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(l, c->d_l.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(m, c->d_m.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(h, c->d_h.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int64_t chunk_reads = 1 << 20;
+    if (const char* e = getenv("RCX_CHUNK_READS")) chunk_reads = atoll(e);
+    if (chunk_reads < 2) chunk_reads = 2;
+    chunk_reads &= ~(int64_t)1;
+    int si = 0;
+    for (int64_t lo = 0; lo < n; lo += chunk_reads, si = (si + 1) % RCX_NSLOTS) {
+        const int64_t hi = std::min<int64_t>(n, lo + chunk_reads), cn = hi - lo;
+        int32_t max_len = 0;
+        rc = scan_lengths(off + lo, cn, &max_len);
+        if (rc) return rc;
+        if (max_len < 1) max_len = 1;
+        RcxSlot& sl = c->slot[si];
+        rc = harvest(c, sl);  // the slot's previous chunk (also makes its buffers reusable)
+        if (rc) return rc;
+        const uint64_t b0 = off[lo], b1 = off[hi], span = b1 - b0, lead = b0 & 15;
+        CUDA_TRY(sl.d_seq.ensure(span + 96));
+        CUDA_TRY(sl.d_qual.ensure(span + 96));
+        CUDA_TRY(sl.d_off.ensure((size_t)cn + 1));
+        CUDA_TRY(sl.d_corr.ensure((size_t)cn));
+        CUDA_TRY(sl.d_l.ensure((size_t)cn));
+        CUDA_TRY(sl.d_m.ensure((size_t)cn));
+        CUDA_TRY(sl.d_h.ensure((size_t)cn));
+        CUDA_TRY(cudaEventRecord(sl.ev[0], sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.d_seq.p + lead, seq_in + b0, span, cudaMemcpyHostToDevice, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.d_qual.p + lead, qual + b0, span, cudaMemcpyHostToDevice, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.d_off.p, off + lo, ((size_t)cn + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.stream));
+        rc = launch_pipeline(c, sl, mode, cn, sl.d_seq.p + lead - b0, sl.d_qual.p + lead - b0, sl.d_off.p, b0, b1, max_len, sl.d_corr.p,
+                             sl.d_l.p, sl.d_m.p, sl.d_h.p, true);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sl.ev[4], sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(seq_out + b0, sl.d_seq.p + lead, span, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(correction + lo, sl.d_corr.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(l + lo, sl.d_l.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(m + lo, sl.d_m.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(h + lo, sl.d_h.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
+        rc = finish_enqueue(sl);
+        if (rc) return rc;
+    }
+    for (auto& sl : c->slot) {
+        rc = harvest(c, sl);
+        if (rc) return rc;
+    }
     return RCX_OK;
 }
 
@@ -502,58 +595,33 @@ extern "C" int rcx_scan_batch(rcx_ctx* c, int64_t n, const char* seq, const uint
     if (max_len < 1) max_len = 1;
     const uint64_t total = off[n];
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(c->d_seq.ensure(total + 64));
-    CUDA_TRY(c->d_off.ensure((size_t)n + 1));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_seq.p, seq, total, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_off.p, off, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c->d_counts.ensure(total + 1));
-    CUDA_TRY(cudaMemsetAsync(c->d_counts.p, 0, (total + 1) * sizeof(int32_t), c->stream));
-    rc = launch_pipeline(c, RCX_SINGLE, n, c->d_seq.p, nullptr, c->d_off.p, total, max_len, nullptr, nullptr, nullptr, nullptr, false);
+    rc = begin_call(c, (uint64_t)n, total);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(counts_out, c->d_counts.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(strong_threshold_out, c->d_thr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return RCX_OK;
+    RcxSlot& sl = c->slot[0];
+    CUDA_TRY(sl.d_seq.ensure(total + 96));
+    CUDA_TRY(sl.d_off.ensure((size_t)n + 1));
+    CUDA_TRY(cudaEventRecord(sl.ev[0], sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(sl.d_seq.p, seq, total, cudaMemcpyHostToDevice, sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(sl.d_off.p, off, ((size_t)n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.stream));
+    CUDA_TRY(sl.d_counts.ensure(total + 32));
+    CUDA_TRY(cudaMemsetAsync(sl.d_counts.p, 0, (total + 1) * sizeof(int32_t), sl.stream));
+    rc = launch_pipeline(c, sl, RCX_SINGLE, n, sl.d_seq.p, nullptr, sl.d_off.p, 0, total, max_len, nullptr, nullptr, nullptr, nullptr, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(sl.ev[4], sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(counts_out, sl.d_counts.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(strong_threshold_out, sl.d_thr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, sl.stream));
+    rc = finish_enqueue(sl);
+    if (rc) return rc;
+    return harvest(c, sl);
 }
 
 extern "C" int rcx_get_stats(rcx_ctx* c, rcx_stats* out) {
     if (!c || !out) return fail(RCX_ERR_ARG, "rcx_get_stats: null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    unsigned long long h[RCX_C_COUNT];
-    CUDA_TRY(cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    c->stats.scan_probes = h[RCX_C_SCAN_PROBES];
-    c->stats.search_probes = h[RCX_C_SEARCH_PROBES];
-    c->stats.rescan_probes = h[RCX_C_RESCAN_PROBES];
-    c->stats.search_nodes = h[RCX_C_SEARCH_NODES];
-    auto ms = [&](int a, int b) {
-        float v = 0;
-        if (cudaEventElapsedTime(&v, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); v = 0; }
-        return v;
-    };
-    c->stats.ms_h2d = ms(0, 1);
-    c->stats.ms_scan = ms(1, 2);
-    c->stats.ms_correct = ms(2, 3);
-    c->stats.ms_d2h = ms(4, 5);
-    c->stats.ms_total = ms(0, 5);
-    c->stats.ms_triage = c->stats.ms_prep = c->stats.ms_dfs = c->stats.ms_finalize = 0;
-    if (c->kev_valid) {
-        auto kms = [&](int a, int b) {
-            float v = 0;
-            if (cudaEventElapsedTime(&v, c->kev[a], c->kev[b]) != cudaSuccess) { cudaGetLastError(); v = 0; }
-            return v;
-        };
-        c->stats.ms_triage = kms(0, 1);
-        c->stats.ms_prep = kms(1, 2) + kms(3, 4);
-        c->stats.ms_dfs = kms(2, 3) + kms(4, 5);
-        c->stats.ms_finalize = kms(5, 6);
+    for (auto& sl : c->slot) {
+        int rc = harvest(c, sl);
+        if (rc) return rc;
     }
-    c->stats.work_items = h[RCX_C_NWORK];
-    c->stats.second_pass = h[RCX_C_NWORK2];
-    c->stats.unsupported = h[RCX_C_UNSUPPORTED];
     *out = c->stats;
     return RCX_OK;
 }
@@ -565,33 +633,38 @@ extern "C" int rcx_measure_random_read(rcx_ctx* c, int sector_bytes, double* gbp
     if (!c->entries_dev) return fail(RCX_ERR_STATE, "rcx_measure_random_read: no table built");
     if (sector_bytes != 32 && sector_bytes != 64) return fail(RCX_ERR_ARG, "rcx_measure_random_read: sector_bytes must be 32 or 64");
     CUDA_TRY(cudaSetDevice(c->device));
+    RcxSlot& sl = c->slot[0];
+    int rc = harvest(c, sl);
+    if (rc) return rc;
     const int grid = c->sm_count * 8;
     const unsigned long long iters = 256;
-    unsigned long long* sink = c->d_counters + RCX_C_COUNT - 1;
+    unsigned long long* sink = sl.d_counters + RCX_C_COUNT - 1;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
-        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-        CUDA_TRY(rcx_launch_random_read(table_of(c), sector_bytes, grid, iters, sink, c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaEventRecord(sl.ev[0], sl.stream));
+        CUDA_TRY(rcx_launch_random_read(table_of(c), sector_bytes, grid, iters, sink, sl.stream));
+        CUDA_TRY(cudaEventRecord(sl.ev[1], sl.stream));
+        CUDA_TRY(cudaStreamSynchronize(sl.stream));
         float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[1]));
         if (rep > 0 && ms < best) best = ms;
     }
     *gbps = (double)grid * 256.0 * (double)iters * 8.0 * sector_bytes / (best * 1e-3) / 1e9;
     return RCX_OK;
 }
 
-// raw device counters of the last call (debug / profiling builds: search breakdown and per-phase cycles)
+// raw device counters of the last call on the first slot (debug / profiling builds: search breakdown and per-phase cycles)
 extern "C" int rcx_debug_counters(rcx_ctx* c, uint64_t* out, int n) {
     if (!c || !out) return fail(RCX_ERR_ARG, "rcx_debug_counters: null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    RcxSlot& sl = c->slot[0];
+    CUDA_TRY(cudaStreamSynchronize(sl.stream));
     unsigned long long h[RCX_C_COUNT];
-    CUDA_TRY(cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h, sl.d_counters, sizeof h, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) out[i] = i < RCX_C_COUNT ? h[i] : 0;
     return RCX_OK;
 }
+
 
 // ------------------------------------------------------------------------------------------------ ERROR_RATE (main.cpp:310-358)
 extern "C" int rcx_estimate_error_rate(rcx_ctx* c, const uint64_t* fwd_codes, uint64_t n, double wk, double* out) {

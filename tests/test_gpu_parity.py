@@ -179,3 +179,26 @@ def test_context_table_semantics(gpu, k):
     got = gpu.lookup(qc)
     bad = np.nonzero(exp != got)[0]
     assert len(bad) == 0, "%d mismatches, first %s exp %d got %d" % (len(bad), q[bad[0]], exp[bad[0]], got[bad[0]])
+
+
+@pytest.mark.parametrize("chunk", [2, 998, 4096])
+def test_chunked_host_batch_matches_oracle(gpu, workdir, chunk, monkeypatch):
+    """rcx_correct_batch cuts a host batch into chunks that cycle through pipeline slots (copies overlap kernels);
+    the result must not depend on the chunking (chunks start at arbitrary byte offsets, pairs stay together)."""
+    name, k, paired, maxcor, kw = CASES[0]
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    if chunk == 2:
+        b = b.slice(0, 600)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    exp = T.oracle_correct(table, b, k, T.INTERLEAVED, er, bq, maxcor)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, maxcor)
+    monkeypatch.setenv("RCX_CHUNK_READS", str(chunk))
+    got = gpu.correct(T.INTERLEAVED, b.seq, b.qual, b.off)
+    st = gpu.stats()
+    assert st["kernel_launches"] >= 5 * ((b.n + chunk - 1) // chunk)
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        assert np.array_equal(np.asarray(e), np.asarray(g)), nm
