@@ -56,8 +56,17 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
     return (upper > r || upper <= 0) ? r : upper;
 }
 
-__global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs a) {
+#ifndef DFS_MINBLOCKS
+#define DFS_MINBLOCKS 6
+#endif
+// row stride (bytes) of the per-thread path[] / fix[] rows in shared memory: a multiple of 4 with an odd word count
+__host__ __device__ inline int dfs_row_bytes(int max_len) { return ((max_len + 2 + 3) & ~3) | 4; }
+// SMEM: path[] and fix[] of every thread live in shared memory (reads up to 255 bases); otherwise path[] is the lane-
+// interleaved global scratch and fix[] is written straight to HBM.
+template <bool SMEM>
+__global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(RcxCorrectArgs a) {
     __shared__ int lut[DFS_LUT];
+    extern __shared__ __align__(16) signed char dfs_rows[];
     const int lane = threadIdx.x & 31;
     const int k = a.t.k;
     const double er = a.error_rate;
@@ -73,9 +82,10 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
     // per-thread scratch, interleaved by lane
     const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
     unsigned int* stack = a.dfs_stack + gwarp * (long long)a.dfs_depth * DFS_FRAME * 32 + lane;
-    signed char* path = a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;
+    signed char* path = SMEM ? dfs_rows + (size_t)threadIdx.x * dfs_row_bytes(a.max_len) : a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;
+    signed char* fixrow = dfs_rows + (size_t)(DFS_THREADS + threadIdx.x) * dfs_row_bytes(a.max_len);  // SMEM only
 #define STK(f, w) stack[((f) * DFS_FRAME + (w)) * 32]
-#define PATH(p) path[(p) * 32]
+#define PATH(p) path[SMEM ? (p) : (p) * 32]
 
     unsigned long long n_nodes = 0, n_probes = 0;
     // ---- per-item state
@@ -109,6 +119,10 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
             pinfo = a.posbuf + o;
             fix = a.fixbuf + o;
             nseg = st[ST_NSEG]; trust = st[ST_TRUST]; strong = st[ST_STRONG];
+            if (SMEM) {  // fix[] = -1 (:1113-1114), kept in shared memory until the read is decided
+                int* fw = reinterpret_cast<int*>(fixrow);
+                for (int i = 0; i < (len + 3) >> 2; ++i) fw[i] = -1;
+            }
             g = 0; total_fix = 0; bad_segments = 0; best_bn_all = RCX_INF; abort_read = false;
             stage = T_SEG;
         }
@@ -150,6 +164,14 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
                 } else {
                     st[ST_STATUS] = result;
                 }
+                // the post-filters read fix[] from HBM; a read that asked for a second pass may still keep this pass' edits
+                // (no lower plateau found, :1288-1289).  fixbuf is -1 everywhere, so only the edits are written.
+                if (SMEM && (rethreshold || result == RCX_ST_POSTFILTER)) {
+                    for (int i = 0; i < len; ++i) {
+                        const signed char f = fixrow[i];
+                        if (f != -1) fix[i] = f;
+                    }
+                }
                 stage = T_FETCH;
                 continue;
             }
@@ -185,7 +207,8 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
                 if (fc < max_fix || (fc == max_fix && bn > best_bn)) {
                     if (fc < max_fix) trial = -(max_fix - fc + 1) * RCX_MAX_TRIAL;
                     const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
-                    for (int i = lo; i <= hi; ++i) fix[i] = PATH(i);
+                    if (SMEM) { for (int i = lo; i <= hi; ++i) fixrow[i] = PATH(i); }
+                    else { for (int i = lo; i <= hi; ++i) fix[i] = PATH(i); }
                     max_fix = fc; best_bn = bn; best_cnt = 1;
                 } else if (fc == max_fix && bn == best_bn) {
                     best_cnt += 1;
@@ -368,9 +391,19 @@ __global__ void __launch_bounds__(DFS_THREADS, 4) rcx_dfs_kernel(RcxCorrectArgs 
 }
 
 // scratch requirements of one launch
+static bool dfs_smem_rows(int max_len) { return max_len <= 255; }
+static size_t dfs_smem_bytes(int max_len) { return dfs_smem_rows(max_len) ? (size_t)2 * DFS_THREADS * dfs_row_bytes(max_len) : 0; }
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel, DFS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const size_t smem = dfs_smem_bytes(max_len);
+    cudaError_t e;
+    if (dfs_smem_rows(max_len)) {
+        cudaFuncSetAttribute(rcx_dfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<true>, DFS_THREADS, smem);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<false>, DFS_THREADS, 0);
+    }
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     *grid = sm_count * per_sm;
     int kc = max_len - k + 1;
     if (kc < 1) kc = 1;
@@ -381,6 +414,7 @@ size_t rcx_dfs_stack_words(int grid, int depth) { return (size_t)grid * (DFS_THR
 size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREADS / 32) * lpad * 32; }
 
 cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s) {
-    rcx_dfs_kernel<<<grid, DFS_THREADS, 0, s>>>(a);
+    if (dfs_smem_rows(a.max_len)) rcx_dfs_kernel<true><<<grid, DFS_THREADS, dfs_smem_bytes(a.max_len), s>>>(a);
+    else rcx_dfs_kernel<false><<<grid, DFS_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
