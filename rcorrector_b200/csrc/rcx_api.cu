@@ -440,7 +440,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = sl.d_counters;
         ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
         int dfs_grid = 0;
-        rcx_dfs_geometry(c->sm_count, max_len, c->k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
+        rcx_dfs_geometry(c->sm_count, max_len, c->k, c->params.max_fix_per_k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
         CUDA_TRY(sl.d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
         CUDA_TRY(sl.d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
         ca.posbuf = sa.posbuf; ca.dfs_stack = sl.d_dfs_stack.p; ca.dfs_path = sl.d_dfs_path.p;

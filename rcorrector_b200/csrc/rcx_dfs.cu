@@ -59,14 +59,24 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #ifndef DFS_MINBLOCKS
 #define DFS_MINBLOCKS 6
 #endif
-// row stride (bytes) of the per-thread path[] / fix[] rows in shared memory: a multiple of 4 with an odd word count
-__host__ __device__ inline int dfs_row_bytes(int max_len) { return ((max_len + 2 + 3) & ~3) | 4; }
-// SMEM: path[] and fix[] of every thread live in shared memory (reads up to 255 bases); otherwise path[] is the lane-
-// interleaved global scratch and fix[] is written straight to HBM.
+// SMEM (reads up to 255 bases): path[] / fix[] are kept as EDIT LISTS in shared memory.  Every accepted path of a segment
+// copies the same range path[start .. to) into fix[], and everything in that range was assigned by the nodes of the
+// current root-to-leaf path, so "path[] restricted to the current path" is just the list of substitutions made on it
+// (all other entries are -1), and fix[] is, per segment, the edit list of the LAST accepted path (a segment that ends
+// "bad" after a trial-overflow reset keeps it, like the reference's never-rolled-back fix[]).  This removes the dense
+// per-position writes, the O(segment) copy at every acceptance and the O(read) write-back.  One entry = pos | base << 8.
+// Row capacities (entries) for a launch: edits on one path / accepted edits of a whole read.
+__host__ __device__ inline int dfs_cap_path(int max_len, int k, int K) {
+    int c = (max_len * K / k) * 2 + 1;
+    if (c < K) c = K;
+    c += 8;  // the child that exceeds maxFixCnt is entered before it returns; up to 5 N positions; slack
+    return c < max_len ? c : max_len;
+}
+__host__ __device__ inline int dfs_row_entries(int max_len, int k, int K) { return (3 * dfs_cap_path(max_len, k, K)) | 1; }  // path + accepted (2x), odd
 template <bool SMEM>
 __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(RcxCorrectArgs a) {
     __shared__ int lut[DFS_LUT];
-    extern __shared__ __align__(16) signed char dfs_rows[];
+    extern __shared__ __align__(16) unsigned short dfs_rows[];
     const int lane = threadIdx.x & 31;
     const int k = a.t.k;
     const double er = a.error_rate;
@@ -82,10 +92,14 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     // per-thread scratch, interleaved by lane
     const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
     unsigned int* stack = a.dfs_stack + gwarp * (long long)a.dfs_depth * DFS_FRAME * 32 + lane;
-    signed char* path = SMEM ? dfs_rows + (size_t)threadIdx.x * dfs_row_bytes(a.max_len) : a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;
-    signed char* fixrow = dfs_rows + (size_t)(DFS_THREADS + threadIdx.x) * dfs_row_bytes(a.max_len);  // SMEM only
+    signed char* path = a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;  // dense path[] (long reads only)
+    const int cap_path = dfs_cap_path(a.max_len, k, a.max_fix_per_k);
+    unsigned short* E = dfs_rows + (size_t)threadIdx.x * dfs_row_entries(a.max_len, k, a.max_fix_per_k);  // edits on the current path
+    unsigned short* A = E + cap_path;                                                                        // accepted edits of the read
+    int ne = 0, na = 0, na_base = 0;
+    bool edit_overflow = false;
 #define STK(f, w) stack[((f) * DFS_FRAME + (w)) * 32]
-#define PATH(p) path[SMEM ? (p) : (p) * 32]
+#define PATH(p) path[(p) * 32]
 
     unsigned long long n_nodes = 0, n_probes = 0;
     // ---- per-item state
@@ -119,10 +133,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             pinfo = a.posbuf + o;
             fix = a.fixbuf + o;
             nseg = st[ST_NSEG]; trust = st[ST_TRUST]; strong = st[ST_STRONG];
-            if (SMEM) {  // fix[] = -1 (:1113-1114), kept in shared memory until the read is decided
-                int* fw = reinterpret_cast<int*>(fixrow);
-                for (int i = 0; i < (len + 3) >> 2; ++i) fw[i] = -1;
-            }
+            na_base = 0;  // fix[] = -1 (:1113-1114): no accepted edits yet
             g = 0; total_fix = 0; bad_segments = 0; best_bn_all = RCX_INF; abort_read = false;
             stage = T_SEG;
         }
@@ -167,10 +178,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 // the post-filters read fix[] from HBM; a read that asked for a second pass may still keep this pass' edits
                 // (no lower plateau found, :1288-1289).  fixbuf is -1 everywhere, so only the edits are written.
                 if (SMEM && (rethreshold || result == RCX_ST_POSTFILTER)) {
-                    for (int i = 0; i < len; ++i) {
-                        const signed char f = fixrow[i];
-                        if (f != -1) fix[i] = f;
-                    }
+                    for (int e = 0; e < na_base; ++e) { const unsigned int x = A[e]; fix[x & 255u] = (signed char)(x >> 8); }
                 }
                 stage = T_FETCH;
                 continue;
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             kc.inv = sg[4];
             best_cnt = -1; best_bn = -1; trial = 0; top2a = -1; top2b = -1;
             pos = start; t = trust; fix_cnt = 0; bn = RCX_INF; sp = 0;
+            ne = 0; na = 0;
             stage = T_ENTER;
         }
         if (stage == T_ENTER) {
@@ -207,8 +216,12 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 if (fc < max_fix || (fc == max_fix && bn > best_bn)) {
                     if (fc < max_fix) trial = -(max_fix - fc + 1) * RCX_MAX_TRIAL;
                     const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
-                    if (SMEM) { for (int i = lo; i <= hi; ++i) fixrow[i] = PATH(i); }
-                    else { for (int i = lo; i <= hi; ++i) fix[i] = PATH(i); }
+                    if (SMEM) {  // the edits of this path replace the segment's previously accepted ones
+                        if (na_base + ne <= 2 * cap_path) { for (int e = 0; e < ne; ++e) A[na_base + e] = E[e]; na = ne; }
+                        else edit_overflow = true;
+                    } else {
+                        for (int i = lo; i <= hi; ++i) fix[i] = PATH(i);
+                    }
                     max_fix = fc; best_bn = bn; best_cnt = 1;
                 } else if (fc == max_fix && bn == best_bn) {
                     best_cnt += 1;
@@ -233,7 +246,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     bool go = false;
                     int npos = 0, nfix = fix_cnt, nbn = bn;
                     if (c >= thr) {
-                        PATH(pos) = -1;
+                        if (!SMEM) PATH(pos) = -1;
                         go = true; npos = right ? pos + 1 : pos - 1; nbn = c < bn ? c : bn;
                     } else if (thr == 1 && t <= 2) {
                         // "accidentally below the threshold" rescue (:313-338 / :550-573)
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                         }
                         if (steps < k && (right ? i < to : i >= to)) {
                             const int lo = right ? pos : i, hi = right ? i : pos;
-                            for (int j = lo; j <= hi; ++j) PATH(j) = -1;
+                            if (!SMEM) { for (int j = lo; j <= hi; ++j) PATH(j) = -1; }
                             go = true; npos = right ? i + 1 : i - 1; nfix = fix_cnt + 1;
                         }
                     }
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                         if (alt_any) {
                             STK(sp, 0) = (unsigned int)kc.code; STK(sp, 1) = (unsigned int)(kc.code >> 32);
                             STK(sp, 2) = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)T_ALT0 << 20) | (1u << 24);
-                            STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt; STK(sp, 5) = (unsigned int)bn;
+                            STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt | ((unsigned int)ne << 16); STK(sp, 5) = (unsigned int)bn;
                             STK(sp, 6) = (unsigned int)thr;
                             STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
                             ++sp;
@@ -284,15 +297,17 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     if (here_ok && b == hb) continue;
                     const int c = dfs_sel4(b, c0, c1, c2, c3);
                     if (c >= thr) {
-                        PATH(pos) = (signed char)b;
+                        if (SMEM) { if (ne < cap_path) E[ne] = (unsigned short)(pos | (b << 8)); else edit_overflow = true; }
+                        else PATH(pos) = (signed char)b;
                         ++trial;
                         ext = 1;
                         STK(sp, 0) = (unsigned int)kc.code; STK(sp, 1) = (unsigned int)(kc.code >> 32);
                         STK(sp, 2) = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)(T_ALT0 + b + 1) << 20) | (1u << 24);
-                        STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt; STK(sp, 5) = (unsigned int)bn;
+                        STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt | ((unsigned int)ne << 16); STK(sp, 5) = (unsigned int)bn;
                         STK(sp, 6) = (unsigned int)thr;
                         STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
                         ++sp;
+                        if (SMEM && ne < cap_path) ++ne;  // the substitution joins the current path (the frame keeps the count before it)
                         if (right) rcx_k_append(kc, b, false, k, mask); else rcx_k_prepend(kc, b, false, k, mask);
                         if (!right) t = thr;
                         pos = right ? pos + 1 : pos - 1;
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                         const bool bad = (qi & 4) != 0;
                         rcx_k_append(x, qi & 3, bad, k, mask);
                         const int c = bad ? 0 : dfs_sel4(qi & 3, d0, d1, d2, d3);
-                        PATH(i) = -1;
+                        if (!SMEM) PATH(i) = -1;
                         if (c >= th) break;
                     }
                     int kk = (i < len) ? i - pos - k + 1 : (i - pos) / 2;
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                         const bool bad = (qi & 4) != 0;
                         rcx_k_prepend(x, qi & 3, bad, k, mask);
                         const int c = bad ? 0 : dfs_sel4(qi & 3, d0, d1, d2, d3);
-                        PATH(i) = -1;
+                        if (!SMEM) PATH(i) = -1;
                         if (c >= th) break;
                     }
                     int kk = (i >= 0) ? pos - i - k + 1 : pos - 1;
@@ -355,6 +370,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             if (sp == 0) {
                 // ---------------- segment finished (:1162-1174)
                 st[ST_HDR + ST_SEGW * g + 5] = top2b;
+                na_base += na;  // fix[] keeps the segment's last accepted edits whether or not the segment ends "bad"
                 if (best_bn == -1) {
                     ++bad_segments;
                 } else {
@@ -373,7 +389,8 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             kc.inv = (int)((w >> 12) & 0xff) - 1;
             stage = (int)((w >> 20) & 0xf);
             ext = (int)((w >> 24) & 1);
-            t = (int)STK(sp, 3); fix_cnt = (int)STK(sp, 4); bn = (int)STK(sp, 5); thr = (int)STK(sp, 6);
+            t = (int)STK(sp, 3); bn = (int)STK(sp, 5); thr = (int)STK(sp, 6);
+            { const unsigned int w4 = STK(sp, 4); fix_cnt = (int)(w4 & 0xffffu); ne = (int)(w4 >> 16); }
             c0 = (int)STK(sp, 7); c1 = (int)STK(sp, 8); c2 = (int)STK(sp, 9); c3 = (int)STK(sp, 10);
         }
     }
@@ -384,6 +401,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
         n_nodes += __shfl_xor_sync(RCX_FULL, n_nodes, o);
         n_probes += __shfl_xor_sync(RCX_FULL, n_probes, o);
     }
+    if (edit_overflow) atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);  // more substitutions on one path than the row holds: flagged, not hidden
     if (lane == 0) {
         if (n_nodes) atomicAdd(&a.counters[RCX_C_SEARCH_NODES], n_nodes);
         if (n_probes) atomicAdd(&a.counters[RCX_C_SEARCH_PROBES], n_probes);
@@ -392,10 +410,12 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
 
 // scratch requirements of one launch
 static bool dfs_smem_rows(int max_len) { return max_len <= 255; }
-static size_t dfs_smem_bytes(int max_len) { return dfs_smem_rows(max_len) ? (size_t)2 * DFS_THREADS * dfs_row_bytes(max_len) : 0; }
-void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad) {
+static size_t dfs_smem_bytes(int max_len, int k, int K) {
+    return dfs_smem_rows(max_len) ? sizeof(unsigned short) * (size_t)DFS_THREADS * dfs_row_entries(max_len, k, K) : 0;
+}
+void rcx_dfs_geometry(int sm_count, int max_len, int k, int K, int* grid, int* depth, int* lpad) {
     int per_sm = 0;
-    const size_t smem = dfs_smem_bytes(max_len);
+    const size_t smem = dfs_smem_bytes(max_len, k, K);
     cudaError_t e;
     if (dfs_smem_rows(max_len)) {
         cudaFuncSetAttribute(rcx_dfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -414,7 +434,7 @@ size_t rcx_dfs_stack_words(int grid, int depth) { return (size_t)grid * (DFS_THR
 size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREADS / 32) * lpad * 32; }
 
 cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s) {
-    if (dfs_smem_rows(a.max_len)) rcx_dfs_kernel<true><<<grid, DFS_THREADS, dfs_smem_bytes(a.max_len), s>>>(a);
+    if (dfs_smem_rows(a.max_len)) rcx_dfs_kernel<true><<<grid, DFS_THREADS, dfs_smem_bytes(a.max_len, a.t.k, a.max_fix_per_k), s>>>(a);
     else rcx_dfs_kernel<false><<<grid, DFS_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }

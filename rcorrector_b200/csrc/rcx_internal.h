@@ -119,7 +119,7 @@ cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_gr
 bool rcx_finalize_thread_supported(int max_len, int k);
 cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);
 // search (rcx_dfs.cu)
-void rcx_dfs_geometry(int sm_count, int max_len, int k, int* grid, int* depth, int* lpad);
+void rcx_dfs_geometry(int sm_count, int max_len, int k, int max_fix_per_k, int* grid, int* depth, int* lpad);
 size_t rcx_dfs_stack_words(int grid, int depth);
 size_t rcx_dfs_path_bytes(int grid, int lpad);
 cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s);
