@@ -420,6 +420,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
         if (lane == 0) {
             st[ST_STATUS] = status; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
             st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < L.nseg ? nseg : L.nseg;
+            st[ST_OFF] = (int)o; st[ST_LEN] = len;
         }
         __syncwarp();
     }

@@ -119,20 +119,26 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     RcxKmer kc;
     kc.code = 0; kc.inv = -1;
     int stage = T_FETCH;
+    int4 seg0a = make_int4(0, 0, 0, 0), seg0b = make_int4(0, 0, 0, 0);
+    long long nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
 
     for (;;) {
         if (stage == T_FETCH) {
-            const long long w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
+            const long long w = nx_w;  // reserved while the previous item was searched
             if (w >= nitems) break;
+            nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
             item = a.pass == 0 ? w : (long long)a.worklist2[w];
             st = a.state + item * stride;
-            if (st[ST_STATUS] != RCX_ST_SEARCH) continue;  // decided by the prep kernel
-            const long long r = a.worklist[item];
-            const uint32_t o = a.off[r];
-            len = (int)(a.off[r + 1] - o);
+            // header (8 words) + first segment in one round trip: four independent 16-byte loads
+            const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
+            seg0a = *reinterpret_cast<const int4*>(st + 8);
+            seg0b = *reinterpret_cast<const int4*>(st + 12);
+            if (h0.x != RCX_ST_SEARCH) continue;  // decided by the prep kernel
+            const uint32_t o = (uint32_t)h1.z;    // ST_OFF / ST_LEN: written with the header, no worklist -> off[] chase
+            len = h1.w;
             pinfo = a.posbuf + o;
             fix = a.fixbuf + o;
-            nseg = st[ST_NSEG]; trust = st[ST_TRUST]; strong = st[ST_STRONG];
+            nseg = h1.y; trust = h1.x; strong = h0.w;
             na_base = 0;  // fix[] = -1 (:1113-1114): no accepted edits yet
             g = 0; total_fix = 0; bad_segments = 0; best_bn_all = RCX_INF; abort_read = false;
             stage = T_SEG;
@@ -183,13 +189,14 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 stage = T_FETCH;
                 continue;
             }
-            const int* sg = st + ST_HDR + ST_SEGW * g;
-            const int w0 = sg[0], w1 = sg[1];
+            int w0, w1, w2, w3, w4;
+            if (g == 0) { w0 = seg0a.x; w1 = seg0a.y; w2 = seg0a.z; w3 = seg0a.w; w4 = seg0b.x; }  // came with the header
+            else { const int* sg = st + ST_HDR + ST_SEGW * g; w0 = sg[0]; w1 = sg[1]; w2 = sg[2]; w3 = sg[3]; w4 = sg[4]; }
             start = w0 & 0xffff; to = (w0 >> 16) & 0xffff;
             right = (w1 & 1) != 0;
             max_fix = w1 >> 1;
-            kc.code = (unsigned long long)(unsigned int)sg[2] | ((unsigned long long)(unsigned int)sg[3] << 32);
-            kc.inv = sg[4];
+            kc.code = (unsigned long long)(unsigned int)w2 | ((unsigned long long)(unsigned int)w3 << 32);
+            kc.inv = w4;
             best_cnt = -1; best_bn = -1; trial = 0; top2a = -1; top2b = -1;
             pos = start; t = trust; fix_cnt = 0; bn = RCX_INF; sp = 0;
             ne = 0; na = 0;

@@ -89,7 +89,10 @@ struct RcxCorrectArgs {
 #define RCX_ST_SEARCH (-4)       // waiting for the search kernel
 #define RCX_ST_RETHRESHOLD (-3)  // first pass asked for a second one (forceNextRound)
 #define RCX_ST_POSTFILTER (-2)   // searches done: post-filters decide
-__host__ __device__ inline int rcx_state_stride(int max_len, int k) { return ST_HDR + ST_SEGW * (max_len / k + 4); }
+#define ST_OFF 6    // off[r] and length of the read: the search kernel gets them with the header instead of chasing worklist -> off[]
+#define ST_LEN 7
+// multiple of 8 words: every item header is 32-byte aligned
+__host__ __device__ inline int rcx_state_stride(int max_len, int k) { return (ST_HDR + ST_SEGW * (max_len / k + 4) + 7) & ~7; }
 
 // table (rcx_table.cu)
 cudaError_t rcx_launch_table_init(RcxEntry* e, unsigned long long nlines, cudaStream_t s);

@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             }
             st[ST_STATUS] = RCX_ST_SEARCH; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
             st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < nseg_cap ? nseg : nseg_cap;
+            st[ST_OFF] = (int)o; st[ST_LEN] = len;
         }
         __syncthreads();
 
