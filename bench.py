@@ -3,14 +3,18 @@
 
 Workload (BASELINE.json configs[1]): 10 M synthetic single-end 100 bp reads,
 k = 23, ~50 M distinct k-mers in the count table, one B200.  A "step" is one
-pass of the hot path (scan kernel + correction kernel) over the whole batch.
+pass of the hot path over the whole batch: scan (+ thresholds, triage, first
+preparation) -> search -> [second-pass preparation -> search] -> finalize.
 
-  value : reads/s, whole job, inputs already resident in HBM (device arm)
+  value : reads/s, whole job, inputs already resident in HBM (device arm,
+          rcx_correct_batch_device)
   e2e   : reads/s through the C ABI with HOST buffers (rcx_correct_batch:
           pinned host -> device copies, kernels, device -> host copies, all
-          inside the timed region)
-  roofline : dominant kernel, algorithmic bytes (32 B per table probe + read
-          bytes) / CUDA-event time, against MEASURED_PEAKS.json's HBM copy GB/s
+          inside the timed region; the library streams the batch through 3
+          pipeline slots in 1 M-read chunks so copies overlap kernels)
+  roofline : dominant kernel (and the lookup kernel), algorithmic bytes (32 B
+          per GetCount + bases) / CUDA-event time, against MEASURED_PEAKS.json's
+          HBM copy GB/s and the random 32-B read rate measured in the same run
   cpu_baseline : the UNMODIFIED reference binary (oracle/_ref/rcorrector) with
           -t <all host cores> on a bounded sample of the same reads and the
           full-size table, timed from its "Bad quality threshold" stderr line
@@ -432,7 +436,7 @@ def main_ours(a):
         sampler.start()
     ms_dev = timed(step_device, a.steps, a.warmup)
     st = cor.stats()  # counters + per-kernel CUDA-event times of the last device step
-    ms_e2e = timed(step_e2e, a.steps, max(1, a.warmup - 1))
+    ms_e2e = timed(step_e2e, a.steps, a.warmup)
     clocks = sampler.stop() if sampler else None
 
     # parity spot check inside the bench (size-independent property): both arms give identical results
@@ -440,26 +444,46 @@ def main_ours(a):
     if chk[0] != chk[1]:
         raise SystemExit("bench: device-resident and host arms disagree (%d vs %d corrected-base checksum)" % tuple(chk))
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     reads_total = n * world
     value = reads_total * a.steps / (ms_dev / 1e3)
     e2e_value = reads_total * a.steps / (ms_e2e / 1e3)
     # per-kernel CUDA-event times of the last device step; dominant kernel and its roofline.
-    # Algorithmic bytes: 32 B per table probe + the bytes of the reads / counts[] a kernel streams.
+    # Algorithmic bytes follow SURVEY §8d / DESIGN.md §4: one GetCount = one 32-byte sector.  The scan needs one GetCount per
+    # k-window (sum of max(0, L-k+1) over the reads) plus the bases; a search node needs the 4 one-base extensions of its
+    # k-mer; the l/m/h re-scan one per window that covers a changed base.  "requests" is what the context-keyed table
+    # actually issues (one sector answers two windows / a whole node).
     bases = st["bases"]
-    # A "probe" is one 32-byte table sector request: it answers two scan windows, or the four extensions of a search node.
+    lens = np.diff(off_h.astype(np.int64))
+    windows = int(np.maximum(lens - a.k + 1, 0).sum())
     kern = {
-        "rcx_scan_kernel": {"ms": st["ms_scan"], "probes": st["scan_probes"], "bytes": 32 * st["scan_probes"] + bases + 4 * bases},
-        "rcx_prep_kernel": {"ms": st["ms_prep"], "probes": 0, "bytes": 7 * bases},
-        "rcx_dfs_kernel": {"ms": st["ms_dfs"], "probes": st["search_probes"], "nodes": st["search_nodes"], "bytes": 32 * st["search_probes"] + 2 * bases},
-        "rcx_finalize_kernel": {"ms": st["ms_finalize"], "probes": st["rescan_probes"], "bytes": 32 * st["rescan_probes"] + 8 * bases},
+        "rcx_scan_kernel": {"ms": st["ms_scan"], "requests": st["scan_probes"], "bytes": 32 * windows + bases,
+                            "does": "scan + GetStrongTrustedThreshold + triage + first-pass preparation"},
+        "rcx_prep_kernel": {"ms": st["ms_prep"], "requests": 0, "bytes": 7 * 0, "does": "second-pass re-threshold + preparation (few reads)"},
+        "rcx_dfs_kernel": {"ms": st["ms_dfs"], "requests": st["search_probes"], "nodes": st["search_nodes"],
+                           "bytes": 32 * 4 * st["search_probes"] + 2 * bases, "does": "ordered correction search"},
+        "rcx_finalize_kernel": {"ms": st["ms_finalize"], "requests": st["rescan_probes"], "bytes": 32 * st["rescan_probes"] + 6 * bases,
+                                "does": "post-filters + apply + l/m/h"},
     }
     for v in kern.values():
         v["gbs"] = v["bytes"] / max(v["ms"], 1e-9) / 1e6
+        v["grequests_per_s"] = v["requests"] / max(v["ms"], 1e-9) / 1e6
     dom = max(kern, key=lambda k: kern[k]["ms"])
     dom_ms, dom_bytes = kern[dom]["ms"], kern[dom]["bytes"]
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+    scan = kern["rcx_scan_kernel"]
+    # DRAM traffic of the kernels from the committed ncu --set full capture of this same workload (profiles/traffic.json)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj["workload"] == {"reads": a.reads, "len": a.len, "k": a.k}:
+            traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}
+    except Exception:
+        pass
     if st["unsupported"]:
         raise SystemExit("bench: %d reads needed a third A.4 pass (unsupported)" % st["unsupported"])
     line = {
@@ -471,9 +495,15 @@ def main_ours(a):
                 "h2d_bytes_per_step": int(2 * total + 4 * (n + 1)) * world, "d2h_bytes_per_step": int(total + 16 * n) * world},
         "gpu_launches": int(st["kernel_launches"]) * a.steps * world,  # 6 kernels per step per GPU in the timed region of `value` (the e2e region launches the same 6)
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
+                     "traffic": traffic.get(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
                      "kernel_ms": dom_ms, "random_read_peak_gbs": {"32B": rr32, "64B": rr64},
-                     "frac_of_random_read_peak": achieved / rr32, "note": "32 B per table probe (one DRAM sector) + streamed read/count bytes; random-access bound; the lookup kernel (rcx_scan_kernel) is reported under kernels"},
+                     "frac_of_random_read_peak": achieved / rr32,
+                     "lookup_kernel": {"kernel": "rcx_scan_kernel", "achieved": scan["gbs"], "frac": scan["gbs"] / hbm_peak,
+                                       "frac_of_random_read_peak": scan["gbs"] / rr32, "kernel_ms": scan["ms"],
+                                       "algorithmic_bytes_per_launch": int(scan["bytes"]), "requests": int(scan["requests"]),
+                                       "traffic": traffic.get("rcx_scan_kernel")},
+                     "note": "random-access bound: 32 B per GetCount (one DRAM sector) + streamed bases; peak = streaming copy, "
+                             "random_read_peak = independent random 32-B reads over this table measured in this run (the DRAM side moves 128 B per miss, profiles/r01_f)"},
         "kernels": kern, "work_items": st["work_items"], "second_pass": st["second_pass"],
         "clocks": clocks,
     }

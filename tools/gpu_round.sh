@@ -20,7 +20,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 # one full capture of the lookup (scan) kernel and the dfs kernel (first device step)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rcx_scan_kernel|rcx_dfs_kernel' -c 2 \
-  -o $OUT/full_scan_dfs -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rcx_scan_thread_kernel|rcx_dfs_kernel|rcx_finalize_thread_kernel' -c 3 \
+  -o $OUT/full_pipeline -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT
