@@ -51,16 +51,16 @@ typedef struct {
 typedef struct {
     uint64_t reads;
     uint64_t bases;
-    uint64_t scan_probes;    /* table probes issued by the scan kernel (one per k-mer window) */
-    uint64_t search_probes;  /* probes issued by the correction search (4 per interior node / jump step) */
-    uint64_t rescan_probes;  /* probes of the l/m/h re-scan of changed reads */
+    uint64_t scan_probes;    /* 32-byte table sector requests of the scan kernel (one answers two adjacent k-windows) */
+    uint64_t search_probes;  /* requests of the correction search (one answers the four extensions of a node / jump step) */
+    uint64_t rescan_probes;  /* requests of the l/m/h re-scan (one per window that covers a changed base) */
     uint64_t search_nodes;   /* SearchPaths_* node visits */
-    uint64_t kernel_launches;/* CUDA kernels launched by the call */
+    uint64_t kernel_launches;/* CUDA kernels launched by the call (5 per chunk of a host batch) */
     float ms_scan, ms_correct, ms_total, ms_h2d, ms_d2h; /* CUDA-event times on the context's stream; ms_correct = triage..finalize */
     float ms_triage, ms_prep, ms_dfs, ms_finalize;       /* per-kernel split of ms_correct (both passes summed) */
     uint64_t work_items;     /* reads that needed the search (not all-trusted, not rejected) */
     uint64_t second_pass;    /* of those, reads that took the second pass of the A.4 loop */
-    uint64_t unsupported;    /* reads that would have needed a third pass (must be 0) */
+    uint64_t unsupported;    /* must be 0: a read that would need a third A.4 pass, a count >= 2^29, an edit-row overflow */
 } rcx_stats;
 
 typedef struct rcx_ctx rcx_ctx;
@@ -84,7 +84,7 @@ int rcx_table_build(rcx_ctx* ctx, int k, const uint64_t* fwd_codes, const int32_
                     int src_on_device);
 /* Store::GetCount (Store.h:59-66) for n valid forward codes; host pointers. */
 int rcx_table_lookup(rcx_ctx* ctx, const uint64_t* fwd_codes, int32_t* counts_out, uint64_t n);
-/* number of distinct keys stored, slots allocated */
+/* number of distinct canonical k-mers stored, 32-byte sectors allocated (one (k-1)-mer context each), bytes of HBM */
 int rcx_table_info(rcx_ctx* ctx, uint64_t* entries, uint64_t* slots, uint64_t* bytes);
 
 int rcx_set_params(rcx_ctx* ctx, const rcx_params* p);
