@@ -6,16 +6,85 @@
 // "w1") so that the bytes written equal the reference's; the implementation is
 // a chunked block reader + batch formatter instead of per-line fgets/Printf.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace rcxio {
+
+// run fn(t) for t in [0, nthreads) on that many host threads
+template <class F>
+inline void parallel_for(int nthreads, F fn) {
+    if (nthreads <= 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) th.emplace_back([&fn, t]() { fn(t); });
+    for (auto& x : th) x.join();
+}
+
+// A plain (not gzip) input file mapped read-only: the parallel readers index and slice it in place.
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    bool open(const std::string& path) {
+        close();
+        int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); return false; }
+        size = (size_t)st.st_size;
+        if (size > 0) {
+            void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) { ::close(fd); size = 0; return false; }
+            madvise(p, size, MADV_SEQUENTIAL);
+            data = (const char*)p;
+        }
+        ::close(fd);
+        return true;
+    }
+    void close() {
+        if (data) munmap((void*)data, size);
+        data = nullptr;
+        size = 0;
+    }
+    ~MappedFile() { close(); }
+};
+
+// positions of every '\n' in [lo, hi) of a mapped file, found by `nthreads` threads (ascending, relative to `lo`)
+inline void index_newlines(const char* base, size_t lo, size_t hi, int nthreads, std::vector<uint32_t>& out) {
+    const size_t n = hi - lo;
+    std::vector<std::vector<uint32_t>> part(nthreads);
+    parallel_for(nthreads, [&](int t) {
+        const size_t a = lo + n * t / nthreads, b = lo + n * (t + 1) / nthreads;
+        std::vector<uint32_t>& v = part[t];
+        v.reserve((b - a) / 48 + 16);
+        const char* p = base + a;
+        const char* e = base + b;
+        while (p < e) {
+            const char* q = (const char*)memchr(p, '\n', e - p);
+            if (!q) break;
+            v.push_back((uint32_t)(q - (base + lo)));
+            p = q + 1;
+        }
+    });
+    size_t tot = 0;
+    for (auto& v : part) tot += v.size();
+    out.resize(tot);
+    std::vector<size_t> start(nthreads + 1, 0);
+    for (int t = 0; t < nthreads; ++t) start[t + 1] = start[t] + part[t].size();
+    parallel_for(nthreads, [&](int t) { if (!part[t].empty()) memcpy(out.data() + start[t], part[t].data(), part[t].size() * sizeof(uint32_t)); });
+}
 
 inline bool ends_with_gz(const std::string& p) {  // File.h:51-55
     return p.size() >= 2 && p[p.size() - 2] == 'g' && p[p.size() - 1] == 'z';
@@ -44,6 +113,15 @@ inline std::string output_stem(const std::string& in) {
 // Block reader over a plain or gzip file that hands out lines (without the '\n').
 class LineReader {
    public:
+    // serial reading of an already mapped file from byte `pos` (the parallel reader hands irregular input over here)
+    void open_mem(const char* data, size_t size, size_t pos) {
+        close();
+        mem_ = data;
+        beg_ = pos;
+        end_ = size;
+        eof_ = true;
+    }
+    size_t tell() const { return beg_; }  // memory mode: offset of the next unread byte
     bool open(const std::string& path) {
         close();
         gz_ = ends_with_gz(path);
@@ -60,6 +138,7 @@ class LineReader {
         if (g_) gzclose(g_);
         f_ = nullptr;
         g_ = nullptr;
+        mem_ = nullptr;
         beg_ = end_ = 0;
         eof_ = false;
     }
@@ -68,7 +147,7 @@ class LineReader {
     bool getline(const char*& p, size_t& n, bool& had_nl) {
         for (;;) {
             if (beg_ < end_) {
-                const char* s = buf_.data() + beg_;
+                const char* s = (mem_ ? mem_ : buf_.data()) + beg_;
                 const void* nl = memchr(s, '\n', end_ - beg_);
                 if (nl) {
                     p = s;
@@ -107,6 +186,7 @@ class LineReader {
     }
     FILE* f_ = nullptr;
     gzFile g_ = nullptr;
+    const char* mem_ = nullptr;
     bool gz_ = false, eof_ = false;
     std::vector<char> buf_ = std::vector<char>(8u << 20);
     size_t beg_ = 0, end_ = 0;
@@ -147,7 +227,14 @@ struct Chunk {
     std::vector<uint32_t> qual_text_off;
     bool ragged_qual = false;
     size_t n = 0;
-    void clear() { ids.clear(); id_off.assign(1, 0); qual_text.clear(); qual_text_off.assign(1, 0); ragged_qual = false; n = 0; }
+    // parallel reader: id lines stay in the mapped input file(s)
+    std::vector<const char*> id_ptr;
+    std::vector<uint32_t> id_len;
+    bool ext_ids = false;
+    void clear() {
+        ids.clear(); id_off.assign(1, 0); qual_text.clear(); qual_text_off.assign(1, 0); ragged_qual = false; n = 0;
+        id_ptr.clear(); id_len.clear(); ext_ids = false;
+    }
 };
 
 inline size_t format_int(char* p, int v) {  // "%d"

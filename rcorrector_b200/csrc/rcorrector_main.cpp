@@ -12,14 +12,16 @@
 // order.  There is no CPU correction path: without a GPU it exits 1.
 //
 // Extra options (not in the reference): -gpus N (default 1; env RCX_GPUS),
-// -batch N (records per device batch, default 4M).
+// -batch N (records per pipeline batch, default 1M).
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -97,7 +99,7 @@ struct Dump {
 
 static inline int nuc(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 
-static void load_dump(const char* path, int k, Dump& d) {  // main.cpp:294-308 with a block reader instead of fscanf("%s")
+static void load_dump_serial(const char* path, int k, Dump& d) {  // main.cpp:294-308 with a block reader instead of fscanf("%s")
     FILE* fp = fopen(path, "r");
     if (!fp) {
         fprintf(stderr, "Could not open file %s\n", path);
@@ -165,6 +167,105 @@ static void load_dump(const char* path, int k, Dump& d) {  // main.cpp:294-308 w
     }
     fclose(fp);
     if (last_inv_state != -1) d.rate_records = 0;  // main.cpp:323 tests the state the load loop left behind
+}
+
+
+// The same loader for a regular dump (">count\nKMER\n" records, which is what `jellyfish dump` writes): the file is mapped,
+// cut at record starts and parsed by `threads` host threads.  Anything irregular (a count token that does not start with
+// '>', a k-mer token that does, blanks inside a line, a missing final newline) falls back to the serial token parser.
+static bool load_dump_parallel(const char* path, int k, Dump& d, int threads) {
+    rcxio::MappedFile mf;
+    if (!mf.open(path) || mf.size < 4 || mf.data[0] != '>' || mf.data[mf.size - 1] != '\n') return false;
+    const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    const int T = std::max(1, threads);
+    struct Part {
+        std::vector<uint64_t> codes;
+        std::vector<int32_t> counts;
+        int64_t stored = 0;
+        int64_t first_bad = -1;  // first local record whose k-mer leaves KmerCode invalid with invalidPos > 0
+        int last_inv = -2;       // invalidPos after the last STORED record (-2: none stored here)
+        bool ok = true;
+    };
+    std::vector<Part> part(T);
+    std::vector<size_t> cut(T + 1, 0);
+    cut[T] = mf.size;
+    for (int t = 1; t < T; ++t) {  // a record starts at a '>' that follows a newline
+        size_t p = mf.size * t / T;
+        while (p < mf.size && !(mf.data[p] == '>' && mf.data[p - 1] == '\n')) ++p;
+        cut[t] = p;
+    }
+    rcxio::parallel_for(T, [&](int t) {
+        Part& P = part[t];
+        const char* p = mf.data + cut[t];
+        const char* e = mf.data + cut[t + 1];
+        P.codes.reserve((size_t)(e - p) / (k + 4) + 16);
+        P.counts.reserve((size_t)(e - p) / (k + 4) + 16);
+        while (p < e) {
+            if (*p != '>') { P.ok = false; return; }
+            const char* q = (const char*)memchr(p, '\n', e - p);
+            if (!q) { P.ok = false; return; }
+            long v = 0;  // atoi(&buffer[1])
+            const char* c = p + 1;
+            bool neg = false;
+            if (c < q && (*c == '-' || *c == '+')) { neg = *c == '-'; ++c; }
+            const char* c0 = c;
+            while (c < q && *c >= '0' && *c <= '9') { v = v * 10 + (*c - '0'); if (v > 2147483647L) v = 2147483647L; ++c; }
+            if (c != q || c == c0) { P.ok = false; return; }  // blanks / other characters in the count line: let the token parser decide
+            const int cur_count = (int)(neg ? -v : v);
+            const char* s0 = q + 1;
+            const char* q2 = (const char*)memchr(s0, '\n', e - s0);
+            if (!q2 || q2 == s0) { P.ok = false; return; }
+            uint64_t code = 0;
+            int inv = -1;
+            for (const char* x = s0; x < q2; ++x) {  // KmerCode::Append, KmerCode.cpp:7-21
+                const unsigned char ch = (unsigned char)*x;
+                if (ch <= ' ' || ch == '>') { P.ok = false; return; }
+                const int b = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+                if (inv != -1) ++inv;
+                code = ((code << 2) & mask) | (uint64_t)(b & 3);
+                if (b < 0) inv = 0;
+                if (inv >= k) inv = -1;
+            }
+            P.codes.push_back(code);
+            if (cur_count > 1) {
+                ++P.stored;
+                P.last_inv = inv;
+                P.counts.push_back(inv == -1 ? cur_count : 0);
+            } else {
+                P.counts.push_back(0);
+            }
+            if (P.first_bad < 0 && inv > 0) P.first_bad = (int64_t)P.codes.size() - 1;
+            p = q2 + 1;
+        }
+    });
+    size_t total = 0;
+    for (auto& P : part) { if (!P.ok) return false; total += P.codes.size(); }
+    d.codes.resize(total);
+    d.counts.resize(total);
+    std::vector<size_t> start(T + 1, 0);
+    for (int t = 0; t < T; ++t) start[t + 1] = start[t] + part[t].codes.size();
+    rcxio::parallel_for(T, [&](int t) {
+        if (part[t].codes.empty()) return;
+        memcpy(d.codes.data() + start[t], part[t].codes.data(), part[t].codes.size() * sizeof(uint64_t));
+        memcpy(d.counts.data() + start[t], part[t].counts.data(), part[t].counts.size() * sizeof(int32_t));
+    });
+    d.stored = 0;
+    d.rate_records = total;
+    int last_inv_state = -1;
+    bool rate_open = true;
+    for (int t = 0; t < T; ++t) {
+        d.stored += part[t].stored;
+        if (part[t].last_inv != -2) last_inv_state = part[t].last_inv;
+        if (rate_open && part[t].first_bad >= 0) { d.rate_records = start[t] + (size_t)part[t].first_bad; rate_open = false; }
+    }
+    if (last_inv_state != -1) d.rate_records = 0;  // main.cpp:323 tests the state the load loop left behind
+    return true;
+}
+
+static void load_dump(const char* path, int k, Dump& d, int threads) {
+    if (!getenv("RCX_SERIAL_IO") && load_dump_parallel(path, k, d, threads)) return;
+    d = Dump();
+    load_dump_serial(path, k, d);
 }
 
 // ---------------------------------------------------------------------------------------------- per-file processing
@@ -253,7 +354,8 @@ static void format_records(const HostBatch& b, const Chunk& c, int type, size_t 
     out.clear();
     char num[16];
     for (size_t r = lo; r < hi; r += stride) {
-        out.append(c.ids.data() + c.id_off[r], c.id_off[r + 1] - c.id_off[r]);
+        if (c.ext_ids) out.append(c.id_ptr[r], c.id_len[r]);
+        else out.append(c.ids.data() + c.id_off[r], c.id_off[r + 1] - c.id_off[r]);
         out.append(" l:");
         out.append(num, rcxio::format_int(num, b.l[r]));
         out.append(" m:");
@@ -274,6 +376,137 @@ static void format_records(const HostBatch& b, const Chunk& c, int type, size_t 
             out.push_back('\n');
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------- parallel FASTQ reader
+// One input file.  Plain FASTQ files are mapped and read by `threads` host threads (newline index, then every thread
+// copies its share of records into the pinned batch); gzip / FASTA input, and any file in which a record turns out to be
+// irregular (quality line of another length than the sequence line, missing final newline), is read record by record
+// with the reference's line semantics (read_record).
+struct Source {
+    std::string path;
+    int type = 1;
+    bool fast = false;
+    rcxio::MappedFile mf;
+    size_t pos = 0;             // fast mode: next unread byte
+    LineReader lr;              // serial mode
+    std::vector<uint32_t> nl;   // newline index of the current region, relative to reg_lo
+    size_t reg_lo = 0;
+    double rec_bytes = 300;     // running estimate of bytes per record
+    bool open(const std::string& p, int t, bool allow_fast) {
+        path = p; type = t; pos = 0;
+        fast = allow_fast && t == 1 && !rcxio::ends_with_gz(p) && mf.open(p) && mf.size > 0;
+        if (fast) return true;
+        return lr.open(p);
+    }
+    void go_serial() {  // hand the rest of a mapped file to the serial reader
+        lr.open_mem(mf.data, mf.size, pos);
+        fast = false;
+    }
+    // index enough of the file for up to `want` records; returns how many whole records are available
+    size_t peek(size_t want, int threads) {
+        size_t hi = pos + (size_t)(rec_bytes * 1.05 * (double)want) + 4096;
+        for (;;) {
+            if (hi > mf.size) hi = mf.size;
+            if (hi - pos > 0xfff00000ull) hi = pos + 0xfff00000ull;  // 32-bit relative offsets
+            reg_lo = pos;
+            rcxio::index_newlines(mf.data, pos, hi, threads, nl);
+            const size_t have = nl.size() / 4;
+            if (have >= want || hi >= mf.size || hi - pos >= 0xfff00000ull) return have < want ? have : want;
+            hi = pos + (hi - pos) * 2;
+        }
+    }
+    bool at_eof() const { return pos >= mf.size; }
+    // true if what is left cannot be taken by the parallel reader (bytes after the last newline)
+    const char* line(size_t i, uint32_t& len) const {  // line i of the indexed region
+        const size_t b = i == 0 ? 0 : (size_t)nl[i - 1] + 1;
+        len = (uint32_t)(nl[i] - b);
+        return mf.data + reg_lo + b;
+    }
+    void consume(size_t nrec) {
+        if (nrec == 0) return;
+        const size_t end = reg_lo + (size_t)nl[4 * nrec - 1] + 1;
+        rec_bytes = 0.5 * rec_bytes + 0.5 * (double)(end - pos) / (double)nrec;
+        pos = end;
+    }
+};
+
+// Fill `b` / `c` from the mapped sources: records r = stride * i + which come from source `which`.  Returns false (nothing
+// consumed) when a record is irregular; `n_out` = records appended.
+static bool fill_batch_fast(Source& A, Source* B2, bool interleaved, HostBatch& b, Chunk& c, int threads, size_t& n_out) {
+    n_out = 0;
+    const size_t per = B2 ? b.cap_reads / 2 : (interleaved ? (b.cap_reads & ~(size_t)1) : b.cap_reads);
+    size_t na = A.peek(per, threads);
+    size_t nb = B2 ? B2->peek(per, threads) : 0;
+    if (B2) {
+        if (na != nb) {
+            // one file ends before the other (main.cpp:463-466), unless the shorter one only has a ragged tail left
+            const size_t m = na < nb ? na : nb;
+            if (m == 0) return false;  // let the serial reader sort out what is left (and report unpaired files)
+            na = nb = m;
+        }
+    }
+    if (na == 0) return !(A.pos < A.mf.size) ? true : false;  // leftover bytes without 4 complete lines: serial reader
+    const size_t stride = B2 ? 2 : 1;
+    const size_t n = na * stride;
+    // lengths + regularity
+    std::vector<uint32_t> len(n);
+    std::vector<char> bad(threads > 0 ? threads : 1, 0), toolong(threads > 0 ? threads : 1, 0);
+    rcxio::parallel_for(threads, [&](int t) {
+        const size_t lo = na * t / threads, hi = na * (t + 1) / threads;
+        for (size_t i = lo; i < hi; ++i)
+            for (size_t w = 0; w < stride; ++w) {
+                const Source& S = w == 0 ? A : *B2;
+                uint32_t L, qn, pl;
+                S.line(4 * i + 1, L);
+                S.line(4 * i + 3, qn);
+                S.line(4 * i + 2, pl);
+                if (qn != L) bad[t] = 1;
+                if (L > RCX_MAX_READ_LENGTH) toolong[t] = 1;
+                len[i * stride + w] = L;
+            }
+    });
+    for (int t = 0; t < threads; ++t)
+        if (bad[t] || toolong[t]) return false;  // serial reader: reference line semantics / its error message
+    // offsets (and the base budget of the pinned buffers)
+    size_t keep = n, acc = 0;
+    b.off[0] = 0;
+    for (size_t r = 0; r < n; ++r) {
+        acc += len[r];
+        if (acc > b.cap_bases - 2 * (RCX_MAX_READ_LENGTH + 1)) { keep = r & ~(size_t)1; break; }
+        b.off[r + 1] = (uint32_t)acc;
+    }
+    if (keep == 0) return false;
+    const size_t nrec = keep / stride;
+    c.clear();
+    c.ext_ids = true;
+    c.id_ptr.resize(keep);
+    c.id_len.resize(keep);
+    rcxio::parallel_for(threads, [&](int t) {
+        const size_t lo = nrec * t / threads, hi = nrec * (t + 1) / threads;
+        for (size_t i = lo; i < hi; ++i)
+            for (size_t w = 0; w < stride; ++w) {
+                const Source& S = w == 0 ? A : *B2;
+                const size_t r = i * stride + w;
+                uint32_t l0, L;
+                const char* idp = S.line(4 * i, l0);
+                const char* sp = S.line(4 * i + 1, L);
+                uint32_t qn;
+                const char* qp = S.line(4 * i + 3, qn);
+                c.id_ptr[r] = idp;
+                c.id_len[r] = l0;
+                memcpy(b.seq + b.off[r], sp, L);
+                memcpy(b.qual + b.off[r], qp, L);
+            }
+    });
+    b.n = keep;
+    b.bases = b.off[keep];
+    c.n = keep;
+    A.consume(nrec);
+    if (B2) B2->consume(nrec);
+    n_out = keep;
+    return true;
 }
 
 static void correct_on_gpus(std::vector<Gpu>& gpus, int mode, HostBatch& b) {
@@ -314,7 +547,7 @@ int main(int argc, char* argv[]) {
     bool to_stdout = false;
     const char* dump_path = nullptr;
     std::string od = "./";
-    size_t batch_reads = 4u << 20;
+    size_t batch_reads = 1u << 20;  // records per pipeline batch (3 pinned buffers cycle through read -> correct -> write)
     if (const char* e = getenv("RCX_GPUS")) ngpu = atoi(e);
     if (argc == 1) {
         print_help();
@@ -395,11 +628,28 @@ int main(int argc, char* argv[]) {
     }
 
     // ---- GPUs and table
+    // CUDA context creation and the pinned batch buffers overlap the parsing of the dump
     std::vector<Gpu> gpus(ngpu);
-    for (int g = 0; g < ngpu; ++g)
-        if (rcx_create(g, &gpus[g].ctx)) die_rcx("rcx_create");
+    std::future<void> gpus_ready = std::async(std::launch::async, [&]() {
+        for (int g = 0; g < ngpu; ++g)
+            if (rcx_create(g, &gpus[g].ctx)) die_rcx("rcx_create");
+    });
+    // the three pinned batch buffers are allocated while the dump is parsed (pinning memory is slow)
+    const int NSETS = 3;
+    struct BatchSet {
+        HostBatch b;
+        Chunk c;
+        bool more = true;  // the file may have further records after this batch
+    };
+    std::vector<BatchSet> sets(NSETS);
+    std::future<void> sets_ready = std::async(std::launch::async, [&]() {
+        gpus_ready.wait();
+        const size_t cap_bases = batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u;
+        for (auto& st : sets) st.b.alloc(batch_reads, cap_bases);
+    });
     Dump dump;
-    load_dump(dump_path, k, dump);
+    load_dump(dump_path, k, dump, threads);
+    gpus_ready.wait();
     {
         std::vector<std::thread> th;
         std::vector<int> rc(ngpu, 0);
@@ -464,27 +714,50 @@ int main(int argc, char* argv[]) {
     for (auto& g : gpus)
         if (rcx_set_params(g.ctx, &params)) die_rcx("rcx_set_params");
 
-    // ---- correction loop (replaces main.cpp:368-523)
+    // ---- correction loop (replaces main.cpp:368-523): a three-stage pipeline over three pinned batch buffers --
+    // stage 1 reads + parses batch i+1 (parallel reader), stage 2 corrects batch i on the GPUs (this thread), stage 3
+    // formats (in parallel) and writes batch i-1; output order = input order.
     uint64_t total_reads = 0, total_corrections = 0;
-    HostBatch b;
-    b.alloc(batch_reads, batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u);
-    Chunk c;
+    sets_ready.get();
     const int nfmt = std::min(threads, 32);
-    std::vector<std::string> pieces;
+    const bool fast_io = !getenv("RCX_SERIAL_IO");
+    std::shared_future<void> last_write;  // chain of writes: keeps the output in input order
+    std::vector<std::shared_future<void>> set_write(NSETS);
     for (size_t fi = 0; fi < files.size(); ++fi) {
         const ReadFile& f = files[fi];
-        LineReader r1, r2;
-        if (!r1.open(f.path) || (f.paired && !r2.open(f.mate_path))) {
+        Source s1, s2;
+        if (!s1.open(f.path, f.type, fast_io) || (f.paired && !s2.open(f.mate_path, sniff_type(f.mate_path), fast_io))) {
             fprintf(stderr, "ERROR: Could not open file %s\n", f.path.c_str());
             exit(1);
         }
+        if (f.paired && s1.fast != s2.fast) {  // both mates through the same reader
+            if (s1.fast) s1.go_serial();
+            if (s2.fast) s2.go_serial();
+        }
         const int mode = (f.paired || f.interleaved) ? RCX_INTERLEAVED : RCX_SINGLE;
-        bool more = true;
-        while (more) {
+        // stage 1: fill a batch set; returns false when the file is exhausted and the set is empty
+        auto produce = [&](BatchSet& st) -> bool {
+            HostBatch& b = st.b;
+            Chunk& c = st.c;
             b.n = 0;
             b.bases = 0;
             b.off[0] = 0;
             c.clear();
+            st.more = true;
+            if (s1.fast) {
+                size_t got = 0;
+                if (fill_batch_fast(s1, f.paired ? &s2 : nullptr, f.interleaved, b, c, std::max(1, threads), got)) {
+                    if (got == 0) { st.more = false; return false; }
+                    return true;
+                }
+                s1.go_serial();  // irregular record ahead: the serial reader takes over from here
+                if (f.paired) s2.go_serial();
+                b.n = 0; b.bases = 0; b.off[0] = 0;
+                c.clear();
+            }
+            LineReader& r1 = s1.lr;
+            LineReader& r2 = s2.lr;
+            bool more = true;
             while (b.n + 2 <= b.cap_reads && b.bases + 2 * (RCX_MAX_READ_LENGTH + 1) <= b.cap_bases) {
                 if (!read_record(r1, f.type, b, c, f.path)) { more = false; break; }
                 if (f.paired) {
@@ -494,8 +767,8 @@ int main(int argc, char* argv[]) {
                     }
                 } else if (f.interleaved) {
                     if (!read_record(r1, f.type, b, c, f.path)) {
-                        // odd record count in an interleaved file: the reference pairs it with a stale buffer; treat the
-                        // last record as its own mate-less pair by duplicating nothing and correcting it single-end
+                        // odd record count in an interleaved file: the reference pairs it with a stale buffer; the dangling
+                        // record is corrected single-end below
                         more = false;
                         break;
                     }
@@ -505,51 +778,76 @@ int main(int argc, char* argv[]) {
                 const char* p; size_t n; bool nl;
                 if (r2.getline(p, n, nl)) { fprintf(stderr, "ERROR: The files are not paired!\n"); exit(1); }
             }
-            if (b.n == 0) break;
-            int m = mode;
+            st.more = more;
+            return b.n > 0;
+        };
+        // stage 3: format + write
+        auto consume = [&, fi](BatchSet& st, std::shared_future<void> prev) {
+            HostBatch& b = st.b;
+            Chunk& c = st.c;
+            auto emit = [&](Writer& w, size_t start, size_t stride, bool first) {
+                const size_t recs = (b.n - start + stride - 1) / stride;
+                const int parts = (int)std::min<size_t>((size_t)nfmt, std::max<size_t>(1, recs / 4096));
+                std::vector<std::string> pieces(parts);
+                rcxio::parallel_for(parts, [&](int t) {
+                    const size_t lo = start + stride * (recs * t / parts), hi = start + stride * (recs * (t + 1) / parts);
+                    format_records(b, c, f.type, lo, std::min(hi, b.n), stride, pieces[t]);
+                });
+                if (first && prev.valid()) prev.wait();  // the previous batch is on disk
+                for (int t = 0; t < parts; ++t) w.write(pieces[t].data(), pieces[t].size());
+            };
+            // ---- output in input order (main.cpp:485-516); -stdout interleaves the mates of a -p pair
+            if (f.paired && !to_stdout) {
+                emit(out1[fi], 0, 2, true);
+                emit(out2[fi], 1, 2, false);
+            } else {
+                emit(out1[fi], 0, 1, true);  // single, interleaved, or paired to stdout (mate1, mate2, mate1, ...)
+            }
+        };
+        int cur = 0;
+        bool have = produce(sets[cur]);
+        while (have) {
+            BatchSet& st = sets[cur];
+            HostBatch& b = st.b;
+            const int nxt = (cur + 1) % NSETS;
+            std::future<bool> fnext;
+            const bool may_have_more = st.more;
+            if (may_have_more) {
+                if (set_write[nxt].valid()) set_write[nxt].wait();  // its previous contents are written
+                fnext = std::async(std::launch::async, [&, nxt]() { return produce(sets[nxt]); });
+            }
             size_t odd_tail = 0;
-            if (m == RCX_INTERLEAVED && (b.n & 1)) odd_tail = 1;
+            if (mode == RCX_INTERLEAVED && (b.n & 1)) odd_tail = 1;
             if (odd_tail) {
                 // correct the even prefix as pairs, the dangling record single-end
                 HostBatch t = b;
                 t.n = b.n - 1;
                 correct_on_gpus(gpus, RCX_INTERLEAVED, t);
-                HostBatch s = b;
-                s.seq = b.seq + b.off[b.n - 1]; s.qual = b.qual + b.off[b.n - 1];
+                HostBatch sgl = b;
+                sgl.seq = b.seq + b.off[b.n - 1]; sgl.qual = b.qual + b.off[b.n - 1];
                 uint32_t so[2] = {0, b.off[b.n] - b.off[b.n - 1]};
-                s.off = so; s.corr = b.corr + b.n - 1; s.l = b.l + b.n - 1; s.m = b.m + b.n - 1; s.h = b.h + b.n - 1; s.n = 1;
-                correct_on_gpus(gpus, RCX_SINGLE, s);
+                sgl.off = so; sgl.corr = b.corr + b.n - 1; sgl.l = b.l + b.n - 1; sgl.m = b.m + b.n - 1; sgl.h = b.h + b.n - 1; sgl.n = 1;
+                correct_on_gpus(gpus, RCX_SINGLE, sgl);
             } else {
-                correct_on_gpus(gpus, m, b);
+                correct_on_gpus(gpus, mode, b);
             }
             for (size_t r = 0; r < b.n; ++r) {  // UpdateSummary, main.cpp:73-79
                 ++total_reads;
                 if (b.corr[r] > 0) total_corrections += (uint64_t)b.corr[r];
             }
-            // ---- output in input order (main.cpp:485-516); -stdout interleaves the mates of a -p pair
-            auto emit = [&](Writer& w, size_t start, size_t stride) {
-                const size_t recs = (b.n - start + stride - 1) / stride;
-                const int parts = (int)std::min<size_t>((size_t)nfmt, std::max<size_t>(1, recs / 4096));
-                pieces.resize(parts);
-                std::vector<std::thread> th;
-                for (int t = 0; t < parts; ++t) {
-                    const size_t lo = start + stride * (recs * t / parts), hi = start + stride * (recs * (t + 1) / parts);
-                    th.emplace_back([&, t, lo, hi]() { format_records(b, c, f.type, lo, std::min(hi, b.n), stride, pieces[t]); });
-                }
-                for (auto& t : th) t.join();
-                for (int t = 0; t < parts; ++t) w.write(pieces[t].data(), pieces[t].size());
-            };
-            if (f.paired && !to_stdout) {
-                emit(out1[fi], 0, 2);
-                emit(out2[fi], 1, 2);
-            } else {
-                emit(out1[fi], 0, 1);  // single, interleaved, or paired to stdout (mate1, mate2, mate1, ...)
-            }
+            std::shared_future<void> prev = last_write;
+            last_write = std::async(std::launch::async, [&, cur, prev]() { consume(sets[cur], prev); }).share();
+            set_write[cur] = last_write;
+            have = may_have_more ? fnext.get() : false;
+            cur = nxt;
         }
+        if (last_write.valid()) last_write.wait();  // this file's sources go out of scope
     }
     for (auto& w : out1) w.close();
     for (auto& w : out2) w.close();
-    for (auto& g : gpus) rcx_destroy(g.ctx);
+    for (auto& g : gpus) if (rcx_sync(g.ctx)) die_rcx("rcx_sync");
     fprintf(stderr, "Processed %" PRIu64 " reads\n\tCorrected %" PRIu64 " bases.\n", total_reads, total_corrections);
-    return 0;
+    fflush(stdout);
+    fflush(stderr);
+    _exit(0);  // everything is written and closed: skip the teardown of pinned buffers, mappings and CUDA contexts
 }
