@@ -124,3 +124,90 @@ def test_perl_driver_stage3(workdir):
     assert r.returncode == 0, r.stderr.decode()
     assert open(os.path.join(w, "out", "reads_1.cor.fq"), "rb").read() == expected[0]
     assert open(os.path.join(w, "out", "reads_2.cor.fq"), "rb").read() == expected[1]
+
+
+def _variant(workdir, name, data1, data2=None):
+    w = os.path.join(workdir, "irr_" + name)
+    os.makedirs(w, exist_ok=True)
+    p1 = os.path.join(w, "a_1.fq")
+    open(p1, "wb").write(data1)
+    p2 = None
+    if data2 is not None:
+        p2 = os.path.join(w, "a_2.fq")
+        open(p2, "wb").write(data2)
+    return w, p1, p2
+
+
+@pytest.mark.parametrize("case", ["no_final_newline", "ragged_quality", "crlf", "odd_interleaved", "plus_line_text", "regular_t1"])
+def test_parallel_reader_equals_serial_reader(case, workdir):
+    """The binary reads plain FASTQ with a parallel mapped-file reader and hands irregular input to the record-by-record
+    reader that follows the reference's line semantics: both must give the same bytes (and the reference's, where the
+    reference binary is on the box)."""
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir)
+    k = str(meta["k"])
+    d1, d2 = open(fq[0], "rb").read(), open(fq[1], "rb").read()
+    args_extra = []
+    if case == "no_final_newline":
+        d1, d2 = d1[:-1], d2[:-1]
+    elif case == "ragged_quality":
+        lines = d1.split(b"\n")
+        lines[7] = lines[7][:-3]          # second record: quality shorter than the sequence
+        lines[4 * 50 + 3] += b"II"        # another record: longer
+        d1 = b"\n".join(lines)
+    elif case == "crlf":
+        d1, d2 = d1.replace(b"\n", b"\r\n"), d2.replace(b"\n", b"\r\n")
+    elif case == "plus_line_text":
+        lines = d1.split(b"\n")
+        for i in range(2, len(lines) - 1, 4):
+            lines[i] = b"+" + lines[i - 2][1:]
+        d1 = b"\n".join(lines)
+    mode = ["-p"]
+    if case == "odd_interleaved":
+        a, b = d1.split(b"\n"), d2.split(b"\n")
+        inter = []
+        for i in range(0, len(a) - 1, 4):
+            inter += a[i:i + 4] + b[i:i + 4]
+        d1, d2 = b"\n".join(inter[:-4]) + b"\n", None   # drop the last mate: odd number of records
+        mode = ["-i"]
+    w, p1, p2 = _variant(workdir, case, d1, d2)
+    files = mode + [p1] + ([p2] if p2 else [])
+    t = "1" if case == "regular_t1" else "4"
+    outs = {}
+    for tag, env in (("fast", {}), ("serial", {"RCX_SERIAL_IO": "1"})):
+        od = os.path.join(w, "o_" + tag)
+        r = subprocess.run([EXE] + files + ["-c", dump, "-k", k, "-od", od, "-t", t, "-batch", "512"], capture_output=True,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr.decode()
+        outs[tag] = [open(os.path.join(od, f), "rb").read() for f in sorted(os.listdir(od))]
+        outs[tag + "_err"] = T.parse_ref_stderr(r.stderr.decode())
+    assert outs["fast"] == outs["serial"]
+    assert outs["fast_err"] == outs["serial_err"]
+    ref = os.path.join(ROOT, "oracle", "_ref", "rcorrector")
+    if os.path.exists(ref) and case in ("no_final_newline", "plus_line_text", "regular_t1"):
+        od = os.path.join(w, "o_ref")
+        os.makedirs(od, exist_ok=True)
+        r = subprocess.run([ref] + files + ["-c", dump, "-k", k, "-od", od, "-t", "2"], capture_output=True)
+        assert r.returncode == 0
+        assert [open(os.path.join(od, f), "rb").read() for f in sorted(os.listdir(od))] == outs["fast"]
+
+
+def test_dump_parsers_agree(workdir):
+    """Parallel dump loader (regular '>count\\nKMER\\n' files) vs the serial token parser (anything else): same table, same
+    ERROR_RATE, same output."""
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir)
+    k = str(meta["k"])
+    w = os.path.join(workdir, "dumps")
+    os.makedirs(w, exist_ok=True)
+    spaced = os.path.join(w, "spaced.dump")   # same tokens, separated by blanks: only the token parser accepts it
+    open(spaced, "wb").write(open(dump, "rb").read().replace(b"\n", b" ") + b"\n")
+    res = []
+    for tag, dp, env in (("par", dump, {}), ("ser", dump, {"RCX_SERIAL_IO": "1"}), ("spaced", spaced, {})):
+        od = os.path.join(w, tag)
+        r = subprocess.run([EXE, "-p", fq[0], fq[1], "-c", dp, "-k", k, "-od", od, "-t", "4"], capture_output=True,
+                           env=dict(os.environ, RCX_DEBUG_SCALARS="1", **env))
+        assert r.returncode == 0, r.stderr.decode()
+        err = r.stderr.decode()
+        res.append((T.parse_ref_stderr(err), [l for l in err.splitlines() if l.startswith("RCX_DEBUG")],
+                    [open(os.path.join(od, f), "rb").read() for f in sorted(os.listdir(od))]))
+    assert res[0] == res[1] == res[2]
+    assert res[0][2] == expected
