@@ -10,7 +10,9 @@
 #include "rcx_internal.h"
 
 #define TF_THREADS 128
+#ifndef TF_DEPTH
 #define TF_DEPTH 4
+#endif
 #define TF_INVALID 0x80000000u
 #define TF_CMASK 0x7fffffffu
 
