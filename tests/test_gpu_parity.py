@@ -202,3 +202,28 @@ def test_chunked_host_batch_matches_oracle(gpu, workdir, chunk, monkeypatch):
     assert st["kernel_launches"] >= 5 * ((b.n + chunk - 1) // chunk)
     for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
         assert np.array_equal(np.asarray(e), np.asarray(g)), nm
+
+
+def test_million_reads_full_pipeline(gpu, workdir):
+    """A batch large enough to fill the persistent grids many times over and to span several pipeline chunks:
+    1 M single-end reads against a 1.4 M-k-mer table, bit for bit against the oracle (8 host threads, ~10 s)."""
+    k = 23
+    d, bs, b, codes, counts = _load(workdir, "million", k, False, dict(seed=31, ntx=1000, reads=1000000, len=100, err=0.012, nrate=0.003))
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    exp = T.oracle_correct(table, b, k, T.SINGLE, er, bq, 4)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, 4)
+    import os as _os
+    _os.environ["RCX_CHUNK_READS"] = "262144"
+    try:
+        got = gpu.correct(T.SINGLE, b.seq, b.qual, b.off)
+    finally:
+        del _os.environ["RCX_CHUNK_READS"]
+    st = gpu.stats()
+    assert st["unsupported"] == 0 and st["work_items"] > 0 and st["second_pass"] > 0
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
