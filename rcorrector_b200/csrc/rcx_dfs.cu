@@ -308,12 +308,18 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                         else PATH(pos) = (signed char)b;
                         ++trial;
                         ext = 1;
-                        STK(sp, 0) = (unsigned int)kc.code; STK(sp, 1) = (unsigned int)(kc.code >> 32);
-                        STK(sp, 2) = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)(T_ALT0 + b + 1) << 20) | (1u << 24);
-                        STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt | ((unsigned int)ne << 16); STK(sp, 5) = (unsigned int)bn;
-                        STK(sp, 6) = (unsigned int)thr;
-                        STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
-                        ++sp;
+                        // a frame is only needed if another alternative can still pass after this one: otherwise the parent
+                        // has nothing left to do when this child returns (ext != 0 rules out the jump) -- tail call
+                        bool more = false;
+                        for (int b2 = b + 1; b2 < 4; ++b2) more |= !(here_ok && b2 == hb) && dfs_sel4(b2, c0, c1, c2, c3) >= thr;
+                        if (more) {
+                            STK(sp, 0) = (unsigned int)kc.code; STK(sp, 1) = (unsigned int)(kc.code >> 32);
+                            STK(sp, 2) = (unsigned int)(pos + 1) | ((unsigned int)(kc.inv + 1) << 12) | ((unsigned int)(T_ALT0 + b + 1) << 20) | (1u << 24);
+                            STK(sp, 3) = (unsigned int)t; STK(sp, 4) = (unsigned int)fix_cnt | ((unsigned int)ne << 16); STK(sp, 5) = (unsigned int)bn;
+                            STK(sp, 6) = (unsigned int)thr;
+                            STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
+                            ++sp;
+                        }
                         if (SMEM && ne < cap_path) ++ne;  // the substitution joins the current path (the frame keeps the count before it)
                         if (right) rcx_k_append(kc, b, false, k, mask); else rcx_k_prepend(kc, b, false, k, mask);
                         if (!right) t = thr;
