@@ -425,6 +425,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
     // long reads (or RCX_SCAN_WARP=1): the warp-per-read kernels
     const bool thread_scan = rcx_scan_thread_supported(max_len, c->k, d_seq) && !getenv("RCX_SCAN_WARP");
+    sa.compact_fix = (thread_scan && rcx_finalize_thread_supported(max_len, c->k)) ? 1 : 0;
     CUDA_TRY(cudaEventRecord(sl.ev[1], sl.stream));
     if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, sl.stream));
     else CUDA_TRY(rcx_launch_scan(sa, c->sm_count, sl.stream));
@@ -444,6 +445,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         CUDA_TRY(sl.d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
         CUDA_TRY(sl.d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
         ca.posbuf = sa.posbuf; ca.dfs_stack = sl.d_dfs_stack.p; ca.dfs_path = sl.d_dfs_path.p;
+        ca.compact_fix = (thread_scan && rcx_finalize_thread_supported(max_len, c->k)) ? 1 : 0;
         CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, sl.stream, sl.kev, thread_scan));
         sl.kev_valid = true;
         sl.launches = thread_scan ? 5 : 6;  // scan (+ thresholds + triage [+ first preparation]), search, preparation + search of the second pass, finalize

@@ -52,7 +52,13 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
     if (mx < 0) mx = 0;
     int r;
     if (mx < DFS_LUT) r = lut[mx];
-    else { r = rcx_bound_i(mx, er); if (r < 1) r = 1; }
+    else {
+        // GetBound is non-decreasing in c (every rounded operation is monotone), so for a count beyond the table the
+        // result is already known when the table's last entry reaches the cap: no FP64 sqrt for highly expressed k-mers
+        if (upper > 0 && lut[DFS_LUT - 1] >= upper) return upper;
+        r = rcx_bound_i(mx, er);
+        if (r < 1) r = 1;
+    }
     return (upper > r || upper <= 0) ? r : upper;
 }
 
@@ -184,7 +190,16 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 // the post-filters read fix[] from HBM; a read that asked for a second pass may still keep this pass' edits
                 // (no lower plateau found, :1288-1289).  fixbuf is -1 everywhere, so only the edits are written.
                 if (SMEM && (rethreshold || result == RCX_ST_POSTFILTER)) {
-                    for (int e = 0; e < na_base; ++e) { const unsigned int x = A[e]; fix[x & 255u] = (signed char)(x >> 8); }
+                    if (a.compact_fix) {  // thread-per-item finalize: the edit list itself (count, then pos / base pairs) in the read's bytes
+                        if (1 + 2 * na_base <= len && na_base < 128) {
+                            fix[0] = (signed char)na_base;
+                            for (int e = 0; e < na_base; ++e) { const unsigned int x = A[e]; fix[1 + 2 * e] = (signed char)(x & 255u); fix[2 + 2 * e] = (signed char)(x >> 8); }
+                        } else {
+                            edit_overflow = true;
+                        }
+                    } else {
+                        for (int e = 0; e < na_base; ++e) { const unsigned int x = A[e]; fix[x & 255u] = (signed char)(x >> 8); }
+                    }
                 }
                 stage = T_FETCH;
                 continue;

@@ -26,7 +26,7 @@ __host__ __device__ inline TfLayout tf_layout(int max_len, int k) {
     if (kc < 1) kc = 1;
     L.cw = kc | 1;
     L.bw = ((max_len + 3 + 3) & ~3) | 4;  // room for a word-aligned copy; multiple of 4 with an odd number of words (conflict-free across lanes)
-    L.smem = (size_t)TF_THREADS * (sizeof(int) * L.cw + 2 * (size_t)L.bw + 16) + 64;
+    L.smem = (size_t)TF_THREADS * (sizeof(int) * L.cw + (size_t)L.bw + 16) + 64;
     return L;
 }
 
@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
     const TfLayout LY = tf_layout(a.max_len, k);
     unsigned int* cnt_all = reinterpret_cast<unsigned int*>(smem_raw);
     unsigned char* seq_all = reinterpret_cast<unsigned char*>(cnt_all + (size_t)TF_THREADS * LY.cw);
-    signed char* fix_all = reinterpret_cast<signed char*>(seq_all + (size_t)TF_THREADS * LY.bw);
-    TfMeta* meta = reinterpret_cast<TfMeta*>(fix_all + (size_t)TF_THREADS * LY.bw);
+    TfMeta* meta = reinterpret_cast<TfMeta*>(seq_all + (size_t)TF_THREADS * LY.bw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
     const long long nwork = (long long)a.counters[RCX_C_NWORK];
@@ -91,16 +90,13 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
         for (int t = warp; t < nw; t += TF_THREADS / 32) {
             const uint32_t o = meta[t].o;
             const int len = meta[t].len, kc = len - k + 1;
-            const bool post = meta[t].status == RCX_ST_POSTFILTER;
             unsigned int* row = cnt_all + (size_t)t * LY.cw;
             unsigned char* Sw = seq_all + (size_t)t * LY.bw;   // word-aligned copies: the row starts at base (o & ~3)
-            signed char* Xw = fix_all + (size_t)t * LY.bw;
             for (int j = lane; j < kc; j += 32) tf_cp4(row + j, a.counts + o + j);
             const uint32_t ob = o & ~3u;
             const int nwords = (int)(((o + len + 3) & ~3u) - ob) >> 2;
             for (int i = lane; i < nwords; i += 32) {
                 tf_cp4(Sw + 4 * i, a.seq + ob + 4 * i);
-                if (post) tf_cp4(Xw + 4 * i, a.fixbuf + ob + 4 * i);
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -112,7 +108,6 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
         int len = 0, kcnt = 0, result = 0;
         unsigned int* row = cnt_all + (size_t)tid * LY.cw;
         unsigned char* S = seq_all + (size_t)tid * LY.bw;
-        signed char* X = fix_all + (size_t)tid * LY.bw;
         int nvalid = 0, vmin = 0x7fffffff, vmax = 0, med = 0;
         if (have) {
             r = meta[tid].r;
@@ -120,23 +115,37 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
             len = meta[tid].len;
             kcnt = len - k + 1;
             S += o & 3;
-            X += o & 3;
             const int* st = a.state + (w0 + tid) * stride;
             result = meta[tid].status;
-            const bool post_staged = result == RCX_ST_POSTFILTER;
             const int total_fix = st[ST_TOTALFIX], bad_segments = st[ST_BADSEG];
-            (void)post_staged;
             bool changed = false;
             RcxMask<NW> need;  // k-windows whose count must be looked up again
             need.clear();
             if (result == RCX_ST_POSTFILTER) {
-                // ---------------- A.7 post-filters (:1296-1466)
+                // ---------------- A.7 post-filters (:1296-1466).  fix[] arrives as the search kernel's edit list
+                // (count, then pos / base pairs, in the read's fixbuf bytes): every filter works on the few edited positions.
                 const char* q = a.qual + o;
                 const int q0 = q[0];
-                unsigned char P[256];  // ascending positions with a fix on a non-N base (max_len <= 255)
-                int np = 0;
-                for (int i = 0; i < len; ++i)
-                    if (X[i] != -1 && S[i] != 'N') P[np++] = (unsigned char)i;
+                unsigned char P[128], V[128];    // ascending positions with a fix on a non-N base, their bases (0xff = fix removed)
+                unsigned char NP[128], NV[128];  // fixes on literal-N positions (no filter touches them)
+                int np = 0, nn = 0;
+                {
+                    const signed char* fx = a.fixbuf + o;
+                    int cnt = (unsigned char)fx[0];
+                    if (cnt == 0xff) cnt = 0;  // fixbuf is initialised to -1: no edits
+                    for (int e = 0; e < cnt; ++e) {  // insertion by position (segments come in order, a Left search lists its edits downwards)
+                        const unsigned char pe = (unsigned char)fx[1 + 2 * e], be = (unsigned char)fx[2 + 2 * e];
+                        if (S[pe] == 'N') {
+                            int j = nn++;
+                            while (j > 0 && NP[j - 1] > pe) { NP[j] = NP[j - 1]; NV[j] = NV[j - 1]; --j; }
+                            NP[j] = pe; NV[j] = be;
+                        } else {
+                            int j = np++;
+                            while (j > 0 && P[j - 1] > pe) { P[j] = P[j - 1]; V[j] = V[j - 1]; --j; }
+                            P[j] = pe; V[j] = be;
+                        }
+                    }
+                }
                 for (int i = 1; i < np; ++i) {  // pair filter (:1314-1398)
                     const int pa = P[i - 1], pb = P[i];
                     if (q0 != 0 && q[pb] <= Q && q[pa] <= Q) continue;
@@ -166,40 +175,44 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
                         else { if (c < ms) ms = c; }
                     }
                     if (ms != RCX_INF && md != RCX_INF && ms > 1 && md > 1 && ms > md / 2 && ms < 2 * md) {
-                        X[pb] = -1; X[pa] = -1;
+                        V[i] = 0xff; V[i - 1] = 0xff;
                         int j = i - 2;
-                        while (j >= 0 && P[j + 1] - P[j] + 1 <= k) { X[P[j]] = -1; --j; }
-                        while (i + 1 < np && P[i + 1] - P[i] + 1 <= k) { X[P[i + 1]] = -1; ++i; }
+                        while (j >= 0 && P[j + 1] - P[j] + 1 <= k) { V[j] = 0xff; --j; }
+                        while (i + 1 < np && P[i + 1] - P[i] + 1 <= k) { V[i + 1] = 0xff; ++i; }
                     }
                 }
                 if (total_fix > 3 && len > 10) {  // edge filter (:1407-1430)
                     int c = 0;
-                    for (int i = 0; i < 10; ++i) c += S[i] != 'N' && X[i] != -1 && q[i] > Q;
+                    for (int i = 0; i < np; ++i) c += P[i] < 10 && V[i] != 0xff && q[P[i]] > Q;
                     if (c >= 2)
-                        for (int i = 0; i < 10; ++i) if (S[i] != 'N') X[i] = -1;
+                        for (int i = 0; i < np; ++i) if (P[i] < 10) V[i] = 0xff;
                     c = 0;
-                    for (int i = len - 10; i < len; ++i) c += S[i] != 'N' && X[i] != -1 && q[i] > Q;
+                    for (int i = 0; i < np; ++i) c += P[i] >= len - 10 && V[i] != 0xff && q[P[i]] > Q;
                     if (c >= 3)
-                        for (int i = len - 10; i < len; ++i) if (S[i] != 'N') X[i] = -1;
+                        for (int i = 0; i < np; ++i) if (P[i] >= len - 10) V[i] = 0xff;
                 }
-                if (total_fix >= K) {  // density filter (:1432-1455), weights doubled to stay in integers
-                    int sum = 0;
+                if (total_fix >= K) {  // density filter (:1432-1455): weight of the fixes inside any k consecutive positions
+                    int sum = 0, lo = 0;  // (doubled to stay in integers; a window is bounded by its first fix)
                     bool dense = false;
-                    for (int i = 0; i < len; ++i) {
-                        if (X[i] != -1 && S[i] != 'N') sum += q[i] > Q ? 2 : 1;
-                        if (i >= k && X[i - k] != -1 && S[i - k] != 'N') sum -= q[i - k] > Q ? 2 : 1;
-                        if (i >= k - 1 && sum > 2 * K) dense = true;
+                    for (int i = 0; i < np; ++i) {
+                        if (V[i] == 0xff) continue;
+                        sum += q[P[i]] > Q ? 2 : 1;
+                        while (P[i] - P[lo] >= k || V[lo] == 0xff) { if (V[lo] != 0xff) sum -= q[P[lo]] > Q ? 2 : 1; ++lo; }
+                        if (sum > 2 * K) dense = true;
                     }
                     if (dense) result = -1;
                 }
-                if (result == RCX_ST_POSTFILTER) {  // apply (:1468-1479)
+                if (result == RCX_ST_POSTFILTER) {  // apply (:1468-1479): the global read and the staged copy
                     int ret = 0;
-                    for (int i = 0; i < len; ++i)
-                        if (X[i] != -1) {
-                            a.seq[o + i] = "ACGT"[X[i]];
-                            ++ret;
-                            need.set(i - k + 1 > 0 ? i - k + 1 : 0, i < kcnt - 1 ? i : kcnt - 1);  // windows that cover the changed base
-                        }
+                    auto put = [&](int i, int base) {
+                        const char ch = "ACGT"[base];
+                        a.seq[o + i] = ch;
+                        S[i] = (unsigned char)ch;
+                        ++ret;
+                        need.set(i - k + 1 > 0 ? i - k + 1 : 0, i < kcnt - 1 ? i : kcnt - 1);  // windows that cover the changed base
+                    };
+                    for (int i = 0; i < np; ++i) if (V[i] != 0xff) put(P[i], V[i]);
+                    for (int i = 0; i < nn; ++i) put(NP[i], NV[i]);
                     if (ret == 0 && bad_segments > 0) result = -1;
                     else { result = ret; changed = ret > 0; }
                 }
@@ -217,11 +230,10 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
                     unsigned long long F = 0;
                     int run = 0, i = s0;
                     auto append = [&]() {
-                        const unsigned char ch = S[i];
-                        const int fx = X[i];
+                        const unsigned char ch = S[i];  // (the staged copy already holds the corrected bases)
                         const unsigned int idx = (unsigned int)ch - 'A';
-                        const bool ok = fx != -1 || (idx < 26u && ((0x00080045u >> idx) & 1u));
-                        const int code = fx != -1 ? fx : (ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 3);
+                        const bool ok = idx < 26u && ((0x00080045u >> idx) & 1u);
+                        const int code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 3;
                         F = ((F << 2) | (unsigned long long)code) & kmask;
                         run = ok ? run + 1 : 0;
                         ++i;

@@ -43,6 +43,7 @@ struct RcxScanArgs {
     int32_t* state;
     unsigned char* posbuf;
     signed char* fixbuf;
+    int compact_fix;   // only the first fixbuf byte of a read is cleared (edit-list hand-over to the thread-per-item finalize)
 };
 #define RCX_TS_MAX_KCNT 232  // reads with more k-windows use the warp-per-read kernels
 
@@ -75,6 +76,7 @@ struct RcxCorrectArgs {
     unsigned int* dfs_stack; // search scratch: explicit recursion stacks, interleaved by lane
     signed char* dfs_path;   // search scratch: path[] per thread, interleaved by lane
     int dfs_depth, dfs_lpad;
+    int compact_fix;         // fixbuf holds the search kernel's edit list per read (thread-per-item finalize) instead of a dense fix[]
 };
 
 // per-work-item state in HBM (int32 words): 8-word header, then ST_SEGW words per segment

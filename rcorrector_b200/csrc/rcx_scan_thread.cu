@@ -512,9 +512,11 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             for (int j = lane; j < kc; j += 32) a.counts[ot + j] = (int)((rw[j] & TS_CMASK) | ((a.triage && (rw[j] & TS_INVALID)) ? RCX_COUNT_INVALID : 0u));
         }
         if (a.triage) {
-            for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) {
-                a.posbuf[p] = bytes[p - a0] & 31;
-                a.fixbuf[p] = -1;
+            for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) a.posbuf[p] = bytes[p - a0] & 31;
+            if (a.compact_fix) {
+                if (tid < nr) a.fixbuf[offs[tid]] = -1;  // no edits yet: the search kernel leaves its edit list here (first byte = count)
+            } else {
+                for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) a.fixbuf[p] = -1;
             }
         }
     }
