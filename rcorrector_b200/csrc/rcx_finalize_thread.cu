@@ -20,13 +20,13 @@ struct TfLayout {
     int cw, bw;  // words per count row (odd), bytes per base / fix row
     size_t smem;
 };
-__host__ __device__ inline TfLayout tf_layout(int max_len, int k) {
+__host__ __device__ inline TfLayout tf_layout(int max_len, int k, int nt) {
     TfLayout L;
     int kc = max_len - k + 1;
     if (kc < 1) kc = 1;
     L.cw = kc | 1;
     L.bw = ((max_len + 3 + 3) & ~3) | 4;  // room for a word-aligned copy; multiple of 4 with an odd number of words (conflict-free across lanes)
-    L.smem = (size_t)TF_THREADS * (sizeof(int) * L.cw + (size_t)L.bw + 16) + 64;
+    L.smem = (size_t)nt * (sizeof(int) * L.cw + (size_t)L.bw + 16) + 64;
     return L;
 }
 
@@ -57,24 +57,24 @@ struct TfPend {
     int info;  // -1: empty; else window j | base << 10 | flip << 12
 };
 
-template <int NW>
-__global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxCorrectArgs a) {
+template <int NW, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCorrectArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.t.k, K = a.max_fix_per_k, Q = a.bad_qual;
-    const TfLayout LY = tf_layout(a.max_len, k);
+    const TfLayout LY = tf_layout(a.max_len, k, NT);
     unsigned int* cnt_all = reinterpret_cast<unsigned int*>(smem_raw);
-    unsigned char* seq_all = reinterpret_cast<unsigned char*>(cnt_all + (size_t)TF_THREADS * LY.cw);
-    TfMeta* meta = reinterpret_cast<TfMeta*>(seq_all + (size_t)TF_THREADS * LY.bw);
+    unsigned char* seq_all = reinterpret_cast<unsigned char*>(cnt_all + (size_t)NT * LY.cw);
+    TfMeta* meta = reinterpret_cast<TfMeta*>(seq_all + (size_t)NT * LY.bw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
     const long long nwork = (long long)a.counters[RCX_C_NWORK];
-    const long long ntiles = (nwork + TF_THREADS - 1) / TF_THREADS;
+    const long long ntiles = (nwork + NT - 1) / NT;
     const int stride = rcx_state_stride(a.max_len, k);
     unsigned int n_rprobes = 0;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long w0 = tile * TF_THREADS;
-        const int nw = (int)((nwork - w0) < TF_THREADS ? (nwork - w0) : TF_THREADS);
+        const long long w0 = tile * NT;
+        const int nw = (int)((nwork - w0) < NT ? (nwork - w0) : NT);
         __syncthreads();
         // ---- stage: every thread fetches the metadata of its own item, then a warp copies one item at a time with
         // cp.async (global -> shared without a register round trip, so the copies of all items overlap)
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
             meta[tid].status = a.state[(w0 + tid) * stride + ST_STATUS];
         }
         __syncthreads();
-        for (int t = warp; t < nw; t += TF_THREADS / 32) {
+        for (int t = warp; t < nw; t += NT / 32) {
             const uint32_t o = meta[t].o;
             const int len = meta[t].len, kc = len - k + 1;
             unsigned int* row = cnt_all + (size_t)t * LY.cw;
@@ -331,27 +331,27 @@ __global__ void __launch_bounds__(TF_THREADS, 4) rcx_finalize_thread_kernel(RcxC
 
 bool rcx_finalize_thread_supported(int max_len, int k) {
     const int kc = max_len - k + 1;
-    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && tf_layout(max_len, k).smem <= 200 * 1024;
+    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && tf_layout(max_len, k, max_len <= 128 ? TF_THREADS : 64).smem <= 200 * 1024;
 }
 
-template <int NW>
+template <int NW, int NT>
 static cudaError_t launch_finalize_thread_nw(const RcxCorrectArgs& a, int sm_count, cudaStream_t s) {
-    const TfLayout L = tf_layout(a.max_len, a.t.k);
-    cudaError_t e = cudaFuncSetAttribute(rcx_finalize_thread_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    const TfLayout L = tf_layout(a.max_len, a.t.k, NT);
+    cudaError_t e = cudaFuncSetAttribute(rcx_finalize_thread_kernel<NW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_finalize_thread_kernel<NW>, TF_THREADS, L.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_finalize_thread_kernel<NW, NT>, NT, L.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    long long want = (a.n + TF_THREADS - 1) / TF_THREADS;
+    long long want = (a.n + NT - 1) / NT;
     long long grid = (long long)sm_count * per_sm;  // persistent grid (the work-list length lives on the device)
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    rcx_finalize_thread_kernel<NW><<<(unsigned int)grid, TF_THREADS, L.smem, s>>>(a);
+    rcx_finalize_thread_kernel<NW, NT><<<(unsigned int)grid, NT, L.smem, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cudaStream_t s) {
-    if (a.max_len <= 128) return launch_finalize_thread_nw<2>(a, sm_count, s);
-    return launch_finalize_thread_nw<4>(a, sm_count, s);
+    if (a.max_len <= 128) return launch_finalize_thread_nw<2, TF_THREADS>(a, sm_count, s);
+    return launch_finalize_thread_nw<4, 64>(a, sm_count, s);  // 64-item tiles: more blocks fit the shared memory
 }

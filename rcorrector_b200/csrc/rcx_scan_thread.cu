@@ -20,7 +20,7 @@
 // Reads with more than TS_MAX_KCNT windows keep the warp-per-read kernels (rcx_scan.cu, rcx_correct.cu).
 #include "rcx_internal.h"
 
-#define TS_THREADS 128
+#define TS_THREADS 128  // reads per tile for reads up to 128 bases; longer reads use 64-read tiles (more blocks fit the shared memory)
 #ifndef TS_DEPTH
 #define TS_DEPTH 2  // measured 2 / 4 / 8 in flight per thread: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding)
 #endif
@@ -39,18 +39,18 @@ struct TsLayout {
     int bytes_cap;  // staged bases
     size_t smem;
 };
-__host__ __device__ inline TsLayout ts_layout(int max_len, int k) {
+__host__ __device__ inline TsLayout ts_layout(int max_len, int k, int nt) {
     TsLayout L;
     int kc = max_len - k + 1;
     if (kc < 1) kc = 1;
     L.cw = kc | 1;
-    L.bytes_cap = ((TS_THREADS * max_len + 15) & ~15) + 32;
-    L.smem = sizeof(uint32_t) * (TS_THREADS + 4) + sizeof(int) * 16 + sizeof(int) * (size_t)TS_THREADS * L.cw + (size_t)L.bytes_cap;
+    L.bytes_cap = ((nt * max_len + 15) & ~15) + 32;
+    L.smem = sizeof(uint32_t) * (nt + 4) + sizeof(int) * 16 + sizeof(int) * (size_t)nt * L.cw + (size_t)L.bytes_cap;
     return L;
 }
 bool rcx_scan_thread_supported(int max_len, int k, const void* seq) {
     const int kc = max_len - k + 1;
-    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && ((uintptr_t)seq & 15) == 0 && ts_layout(max_len, k).smem <= 200 * 1024;
+    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && ((uintptr_t)seq & 15) == 0 && ts_layout(max_len, k, max_len <= 128 ? TS_THREADS : 64).smem <= 200 * 1024;
 }
 
 struct TsPend {
@@ -135,15 +135,15 @@ __device__ __forceinline__ int ts_select_coop(const unsigned int* warp_rows, int
     return result;
 }
 
-template <int NW>
-__global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanArgs a) {
+template <int NW, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.t.k;
-    const TsLayout LY = ts_layout(a.max_len, k);
+    const TsLayout LY = ts_layout(a.max_len, k, NT);
     uint32_t* offs = reinterpret_cast<uint32_t*>(smem_raw);                       // [T + 1] (+3 pad)
-    int* blk = reinterpret_cast<int*>(offs + TS_THREADS + 4);                     // [16] block scratch
+    int* blk = reinterpret_cast<int*>(offs + NT + 4);                     // [16] block scratch
     unsigned int* cnt_all = reinterpret_cast<unsigned int*>(blk + 16);            // [T][cw]
-    unsigned char* bytes = reinterpret_cast<unsigned char*>(cnt_all + (size_t)TS_THREADS * LY.cw);  // 16-byte aligned (all sizes above are multiples of 16)
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(cnt_all + (size_t)NT * LY.cw);  // 16-byte aligned (all sizes above are multiples of 16)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
     const int loose_thr = (k / 2 > 7) ? k / 2 : 7;
@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
     const int stride = rcx_state_stride(a.max_len, k);
     const int nseg_cap = a.max_len / k + 4;
     unsigned int probes = 0, toobig = 0;
-    const long long ntiles = (a.n + TS_THREADS - 1) / TS_THREADS;
+    const long long ntiles = (a.n + NT - 1) / NT;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long r0 = tile * TS_THREADS;
-        const int nr = (int)((a.n - r0) < TS_THREADS ? (a.n - r0) : TS_THREADS);
+        const long long r0 = tile * NT;
+        const int nr = (int)((a.n - r0) < NT ? (a.n - r0) : NT);
         __syncthreads();  // previous tile fully written out
-        for (int t = tid; t <= nr; t += TS_THREADS) offs[t] = a.off[r0 + t];
+        for (int t = tid; t <= nr; t += NT) offs[t] = a.off[r0 + t];
         __syncthreads();
         const unsigned long long g0 = offs[0], g1 = offs[nr];
         const unsigned long long a0 = g0 & ~15ull;
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             const uint4* src = reinterpret_cast<const uint4*>(a.seq + a0);
             uint4* dst = reinterpret_cast<uint4*>(bytes);
             const int nv = (int)((e16 - a0) >> 4);
-            for (int v = tid; v < nv; v += TS_THREADS) dst[v] = src[v];
-            for (unsigned long long p = e16 + tid; p < g1; p += TS_THREADS) bytes[p - a0] = (unsigned char)a.seq[p];
+            for (int v = tid; v < nv; v += NT) dst[v] = src[v];
+            for (unsigned long long p = e16 + tid; p < g1; p += NT) bytes[p - a0] = (unsigned char)a.seq[p];
         }
         __syncthreads();
 
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
         __syncthreads();
         if (tid == 0) {
             int tot = 0;
-            for (int w = 0; w < TS_THREADS / 32; ++w) { const int c = blk[w]; blk[w] = tot; tot += c; }
+            for (int w = 0; w < NT / 32; ++w) { const int c = blk[w]; blk[w] = tot; tot += c; }
             blk[8] = tot ? (int)atomicAdd(&a.counters[RCX_C_NWORK], (unsigned long long)tot) : 0;
         }
         __syncthreads();
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
         __syncthreads();
 
         // ------------------------------------------------------------------ coalesced write-out: counts[], per-base info, cleared fix[]
-        for (int t = warp; t < nr; t += TS_THREADS / 32) {
+        for (int t = warp; t < nr; t += NT / 32) {
             const uint32_t ot = offs[t];
             const int kc = (int)(offs[t + 1] - ot) - k + 1;
             const unsigned int* rw = cnt_all + (size_t)t * LY.cw;
@@ -512,11 +512,11 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
             for (int j = lane; j < kc; j += 32) a.counts[ot + j] = (int)((rw[j] & TS_CMASK) | ((a.triage && (rw[j] & TS_INVALID)) ? RCX_COUNT_INVALID : 0u));
         }
         if (a.triage) {
-            for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) a.posbuf[p] = bytes[p - a0] & 31;
+            for (unsigned long long p = g0 + tid; p < g1; p += NT) a.posbuf[p] = bytes[p - a0] & 31;
             if (a.compact_fix) {
                 if (tid < nr) a.fixbuf[offs[tid]] = -1;  // no edits yet: the search kernel leaves its edit list here (first byte = count)
             } else {
-                for (unsigned long long p = g0 + tid; p < g1; p += TS_THREADS) a.fixbuf[p] = -1;
+                for (unsigned long long p = g0 + tid; p < g1; p += NT) a.fixbuf[p] = -1;
             }
         }
     }
@@ -526,24 +526,24 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rcx_scan_thread_kernel(RcxScanA
     if (lane == 0 && toobig) atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);  // a count >= 2^29: flagged, not hidden
 }
 
-template <int NW>
+template <int NW, int NT>
 static cudaError_t launch_scan_thread_nw(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
-    const TsLayout L = ts_layout(a.max_len, a.t.k);
-    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    const TsLayout L = ts_layout(a.max_len, a.t.k, NT);
+    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW>, TS_THREADS, L.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW, NT>, NT, L.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    long long want = (a.n + TS_THREADS - 1) / TS_THREADS;
+    long long want = (a.n + NT - 1) / NT;
     long long grid = (long long)sm_count * per_sm;  // persistent grid: a multiple of the SM count
     if (grid > want) grid = want;
-    rcx_scan_thread_kernel<NW><<<(unsigned int)grid, TS_THREADS, L.smem, s>>>(a);
+    rcx_scan_thread_kernel<NW, NT><<<(unsigned int)grid, NT, L.smem, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.max_len <= 128) return launch_scan_thread_nw<2>(a, sm_count, s);
-    return launch_scan_thread_nw<4>(a, sm_count, s);  // max_len <= 255
+    if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS>(a, sm_count, s);
+    return launch_scan_thread_nw<4, 64>(a, sm_count, s);  // max_len <= 255
 }
