@@ -25,13 +25,6 @@
 #include "rcx_internal.h"
 
 #define COR_WARPS 4
-#ifdef RCX_PHASE_TIMERS
-#define PH(i) do { const long long _now = clock64(); ph[ph_cur] += (unsigned long long)(_now - ph_last); ph_last = _now; ph_cur = (i); } while (0)
-#define DBG_INC(x) (++(x))
-#else
-#define PH(i) do { } while (0)
-#define DBG_INC(x) do { } while (0)
-#endif
 #define FRAME_WORDS 12
 
 enum { ST_ENTER = 0, ST_KEEP = 1, ST_ALT0 = 2, ST_JUMP = 6, ST_DONE = 7 };

@@ -216,7 +216,6 @@ __device__ __forceinline__ int rcx_bound_i(int c, double er) {
 
 // out-of-line copies for the (large) correction kernel: its hot loops must stay inside the instruction cache
 static __device__ __noinline__ int rcx_bound_i_ool(int c, double er) { return rcx_bound_i(c, er); }
-static __device__ __noinline__ double rcx_bound_d_ool(int c, double er) { return rcx_bound_d(c, er); }
 static __device__ __noinline__ int rcx_probe_kmer_ool(const RcxTable& t, unsigned long long code) { return rcx_probe_kmer(t, code); }
 
 // ----------------------------------------------------------------------------- per-read bit planes
@@ -308,50 +307,6 @@ __device__ __forceinline__ void rcx_warp_sort(int* s, int n2, int lane) {
         }
     }
 }
-// Warp bitonic sort in REGISTERS (ascending): element e = r * 32 + lane lives in v[r] of `lane`.  Strides below 32
-// are one __shfl_xor per register, strides >= 32 are compare-exchanges between a lane's own registers; no shared
-// memory, no barriers (25 shuffle stages + 3 register stages for 128 keys, ~3x fewer instructions than the
-// shared-memory network above).
-template <int R>
-__device__ __forceinline__ void rcx_regsort(int (&v)[R], int lane) {
-#pragma unroll
-    for (int size = 2; size <= 32 * R; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32) {
-                const int rs = stride >> 5;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((r & rs) == 0) {
-                        const bool up = (((r << 5) & size) == 0);
-                        const int a = v[r], b = v[r | rs];
-                        const int lo = a < b ? a : b, hi = a < b ? b : a;
-                        v[r] = up ? lo : hi;
-                        v[r | rs] = up ? hi : lo;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int e = (r << 5) | lane;
-                    const int p = __shfl_xor_sync(RCX_FULL, v[r], stride);
-                    const bool keep_min = ((e & size) == 0) == ((e & stride) == 0);
-                    v[r] = keep_min ? (v[r] < p ? v[r] : p) : (v[r] > p ? v[r] : p);
-                }
-            }
-        }
-    }
-}
-// element `idx` of a register-sorted array (warp-uniform idx)
-template <int R>
-__device__ __forceinline__ int rcx_regsort_get(const int (&v)[R], int idx) {
-    int x = v[0];
-#pragma unroll
-    for (int r = 1; r < R; ++r)
-        if ((idx >> 5) == r) x = v[r];
-    return __shfl_sync(RCX_FULL, x, idx & 31);
-}
-
 // a bit mask over the positions / k-mers of one read in NW 64-bit registers (all loops unrolled: no dynamic indexing)
 template <int NW>
 struct RcxMask {

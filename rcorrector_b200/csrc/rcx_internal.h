@@ -14,9 +14,8 @@
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
        RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
-       RCX_C_ROUNDS, RCX_C_FF, RCX_C_REGULAR,  // search breakdown (only with -DRCX_PHASE_TIMERS)
-       RCX_C_PHASE0,                            // 8 phase cycle counters (only with -DRCX_PHASE_TIMERS)
-       RCX_C_COUNT = RCX_C_PHASE0 + 8 + 5 };  // + jumps, jump cycles, rescue steps, round cycles, round levels
+       RCX_C_SINK,                               // scratch word of the random-read micro-benchmark
+       RCX_C_COUNT = RCX_C_SINK + 4 };
 
 struct RcxScanArgs {
     RcxTable t;

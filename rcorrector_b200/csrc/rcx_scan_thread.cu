@@ -15,7 +15,7 @@
 // every instruction.  The block keeps the memory side coalesced: the tile's bases are copied HBM -> shared with
 // 16-byte vector loads, each thread's counts live in its own conflict-free shared-memory row (odd stride), and
 // counts[] / per-base info / the cleared fix[] go back to HBM as contiguous block-wide copies.  Table lookups are
-// software-pipelined four deep per thread (512 threads x 4 independent sector requests in flight per SM).
+// software-pipelined per thread (TS_DEPTH = 2: 512 threads x 2 independent sector requests in flight per SM).
 //
 // Reads with more than TS_MAX_KCNT windows keep the warp-per-read kernels (rcx_scan.cu, rcx_correct.cu).
 #include "rcx_internal.h"
@@ -89,23 +89,8 @@ __device__ __forceinline__ int ts_field(const RcxTable& t, const RcxEntryRegs& d
 __device__ __forceinline__ int ts_octave(int v) { return v <= 0 ? 0 : 32 - __clz(v); }
 __device__ __forceinline__ int ts_masked(unsigned int x) { return (x & TS_LOOSE) ? -1 : (int)(x & TS_CMASK); }
 
-// smallest x with #{value <= x} > rank over the row; kind 0: loose-masked counts, kind 1: valid windows with 0 -> 1
-template <int KIND>
-__device__ __forceinline__ int ts_select(const unsigned int* row, int kcnt, int rank, int lo, int hi) {
-    while (lo < hi) {
-        const int mid = lo + (int)(((unsigned int)hi - (unsigned int)lo) >> 1);
-        int c = 0;
-        for (int j = 0; j < kcnt; ++j) {
-            const unsigned int x = row[j];
-            if (KIND == 0) c += ts_masked(x) <= mid;
-            else if (!(x & TS_INVALID)) { int v = (int)(x & TS_CMASK); v = v == 0 ? 1 : v; c += v <= mid; }
-        }
-        if (c > rank) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-// The same selection for the FEW lanes of a warp that need it (reads without a drop, reads that leave at the triage):
+// Selection: smallest x with #{value <= x} > rank over a row; kind 0: loose-masked counts, kind 1: valid windows with 0 -> 1.
+// Only a FEW lanes of a warp need one (reads without a drop, reads that leave at the triage):
 // instead of every lane walking its own row while the others idle, the warp serves the requests one after the other,
 // all 32 lanes counting a slice of the requester's row (conflict-free: consecutive words).  Must be called convergently.
 template <int KIND>
