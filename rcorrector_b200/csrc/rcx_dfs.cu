@@ -62,6 +62,9 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
     return (upper > r || upper <= 0) ? r : upper;
 }
 
+#ifndef DFS_MINLANES
+#define DFS_MINLANES 20  // measured 0 / 6 / 12 / 20 / 24 / 28 / 32: 35.1 / 29.9 / 26.8 / 26.0 / 26.7 / 28.6 / 29.6 ms
+#endif
 #ifndef DFS_MINBLOCKS
 #define DFS_MINBLOCKS 6
 #endif
@@ -217,7 +220,10 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             ne = 0; na = 0;
             stage = T_ENTER;
         }
-        if (stage == T_ENTER) {
+        // Node entries run as an explicit inner loop: lanes whose node has a single child keep walking while the lanes that
+        // need a transition (alternative, pop, next segment, next item) wait after the loop.  When fewer than DFS_MINLANES
+        // lanes are still walking, they pause so that everybody re-enters together after one pass over the transitions.
+        while (stage == T_ENTER) {
             ++n_nodes;
             bool leave = false;
             // step 0 (:211-224 / :453-467)
@@ -304,6 +310,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                         if (!right) t = thr;  // Left hands its threshold down (:546,569)
                         pos = npos; fix_cnt = nfix; bn = nbn; kc = x;
                         stage = T_ENTER;
+                        if (DFS_MINLANES > 0 && __popc(__activemask()) < DFS_MINLANES) break;  // few lanes still chaining: let the others catch up
                         continue;
                     }
                 }
