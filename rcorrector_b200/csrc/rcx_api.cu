@@ -192,7 +192,20 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     // One 32-byte entry per distinct (k-1)-mer context.  A transcriptome / genome has about as many contexts as k-mers
     // (the de Bruijn graph is mostly linear paths); unrelated random k-mers have two each.  Start from contexts ~ n at
     // the target load and grow if the claim pass says otherwise.
-    double load = 0.40;  // entries per sector: ~82 % of the stored contexts sit in their home sector
+    // Entries per sector.  A lookup that does not end at its home sector costs the whole warp a dependent second probe, and
+    // with 32 lanes per warp even a 10 % chance per lane makes that the common case (measured, 10 M reads per step:
+    // load 0.15 / 0.2 / 0.3 / 0.4 / 0.5 -> 61.0 / 62.9 / 67.1 / 71.7 / 79.0 ms).  HBM is what a B200 has plenty of: take
+    // the sparsest of 0.2 / 0.3 / 0.4 whose table stays below a third of the free memory (163 / 109 / 82 bytes per k-mer).
+    double load = 0.40;
+    {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const double cand[3] = {0.20, 0.30, 0.40};
+        for (double cl : cand) {
+            load = cl;
+            if ((double)n * 1.02 / cl * 32.0 <= (double)free_b / 3.0) break;
+        }
+    }
     if (const char* e = getenv("RCX_TABLE_LOAD")) load = atof(e);
     if (!(load >= 0.05 && load <= 0.70)) load = 0.40;
     unsigned long long nlines = (unsigned long long)((double)n * 1.02 / load / 4.0) + 64;
