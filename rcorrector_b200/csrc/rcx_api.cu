@@ -553,13 +553,27 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
     CUDA_TRY(cudaSetDevice(c->device));
     rc = begin_call(c, (uint64_t)n, off[n]);
     if (rc) return rc;
-    int64_t chunk_reads = 1 << 20;
+    int64_t chunk_reads = 2 << 20;  // measured per 10 M-read batch: 1 M / 1.5 M / 2 M / 3 M records -> 81.9 / 75.5 / 75.0 / 85.2 ms
     if (const char* e = getenv("RCX_CHUNK_READS")) chunk_reads = atoll(e);
     if (chunk_reads < 2) chunk_reads = 2;
     chunk_reads &= ~(int64_t)1;
+    // chunk schedule: the first and the last chunk are half-size -- their copies are the ones that cannot hide behind kernels
+    // (more, smaller chunks cost more than they hide: every kernel launch ends with a tail of few busy blocks)
+    std::vector<int64_t> cuts;
+    {
+        bool ramp = n >= 3 * chunk_reads;
+        if (const char* e = getenv("RCX_CHUNK_RAMP")) ramp = ramp && atoi(e) != 0;
+        const int64_t hlf = ramp ? (chunk_reads / 2) & ~(int64_t)1 : 0;
+        int64_t lo = 0;
+        cuts.push_back(0);
+        if (ramp) cuts.push_back(lo += hlf);
+        while (n - hlf - lo > 0) { lo = std::min<int64_t>(n - hlf, lo + chunk_reads); cuts.push_back(lo); }
+        if (ramp) cuts.push_back(n);
+    }
     int si = 0;
-    for (int64_t lo = 0; lo < n; lo += chunk_reads, si = (si + 1) % RCX_NSLOTS) {
-        const int64_t hi = std::min<int64_t>(n, lo + chunk_reads), cn = hi - lo;
+    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci, si = (si + 1) % RCX_NSLOTS) {
+        const int64_t lo = cuts[ci], hi = cuts[ci + 1], cn = hi - lo;
+        if (cn <= 0) continue;
         int32_t max_len = 0;
         rc = scan_lengths(off + lo, cn, &max_len);
         if (rc) return rc;
