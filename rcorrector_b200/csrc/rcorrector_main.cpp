@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <future>
 #include <string>
 #include <thread>
@@ -51,6 +52,17 @@ static void print_help() {  // main.cpp:50-71 (same text: scripts and users read
             "\t-wk FLOAT: the proportion of kmers that are used to estimate weak kmer count threshold (default: 0.95)\n"
             "\t-stdout: output the corrected sequences to stdout (default: not used)\n"
             "\t-verbose: output some correction information to stdout (default: not used)\n");
+}
+
+static double now_s() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static const double g_t0 = now_s();
+static const bool g_timing = getenv("RCX_TIMING") != nullptr;
+static void tmark(const char* what) {
+    if (g_timing) fprintf(stderr, "RCX_TIMING %8.3f s  %s\n", now_s() - g_t0, what);
 }
 
 static void die_rcx(const char* what) {
@@ -649,7 +661,9 @@ int main(int argc, char* argv[]) {
     });
     Dump dump;
     load_dump(dump_path, k, dump, threads);
+    tmark("dump parsed");
     gpus_ready.wait();
+    tmark("CUDA contexts ready");
     {
         std::vector<std::thread> th;
         std::vector<int> rc(ngpu, 0);
@@ -660,6 +674,7 @@ int main(int argc, char* argv[]) {
             if (rc[g]) { fprintf(stderr, "rcx_table_build failed on GPU %d\n", g); exit(1); }
     }
     fprintf(stderr, "Stored %d kmers\n", (int)dump.stored);
+    tmark("table built");
 
     // ---- ERROR_RATE (main.cpp:310-358)
     double error_rate = 0.01;
@@ -719,6 +734,7 @@ int main(int argc, char* argv[]) {
     // formats (in parallel) and writes batch i-1; output order = input order.
     uint64_t total_reads = 0, total_corrections = 0;
     sets_ready.get();
+    tmark("pinned batch buffers ready");
     const int nfmt = std::min(threads, 32);
     const bool fast_io = !getenv("RCX_SERIAL_IO");
     std::shared_future<void> last_write;  // chain of writes: keeps the output in input order
