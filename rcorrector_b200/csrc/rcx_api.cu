@@ -280,6 +280,10 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     unsigned long long part = nsec;
     const unsigned long long afford = (unsigned long long)(free_b * 0.6) / 32;
     if (part > afford) part = std::max<unsigned long long>(afford, 1ull << 16);
+    if (const char* e = getenv("RCX_TABLE_WIN_SECTORS")) {  // tests: force the partitioned path
+        const unsigned long long f = strtoull(e, nullptr, 10);
+        if (f >= 1024 && f < part) part = f;
+    }
     unsigned int* d_win = nullptr;
     CUDA_TRY(cudaMalloc(&d_win, part * 32));
     const unsigned long long big_cap = 1ull << 20;
