@@ -264,12 +264,24 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
         CUDA_TRY(cudaMemcpyAsync(h_stat, d_stat, sizeof h_stat, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const double fill = (double)h_stat[0] / (4.0 * (double)nlines);
-        if (!h_stat[1] && (fill <= load * 1.5 || attempt >= 3)) break;
+        if (!h_stat[1] && (fill <= load * 1.5 || attempt >= 1)) break;  // (after one resize the size is what memory allows)
         // more contexts than assumed: size for what was seen (an aborted pass saw at least 75 % of the sectors)
         cudaFree(e);
         e = nullptr;
         const unsigned long long seen = h_stat[1] ? std::max<unsigned long long>(h_stat[0], 2 * (unsigned long long)n) : h_stat[0];
         nlines = (unsigned long long)((double)seen / load / 4.0) + 64;
+        {   // unrelated k-mers have two contexts each: if the sparse size does not fit, accept a denser table (up to 0.7)
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            double budget = 0.8 * (double)free_b;
+            if (const char* eb = getenv("RCX_TABLE_MAX_BYTES")) budget = atof(eb);  // tests
+            if ((double)nlines * 128.0 > budget) {
+                const unsigned long long fit = (unsigned long long)(budget / 128.0);
+                const unsigned long long need_l = (unsigned long long)((double)seen / 0.70 / 4.0) + 64;
+                if (fit < need_l) return fail(RCX_ERR_NOMEM, "rcx_table_build: the k-mer table does not fit the free device memory");
+                nlines = fit;
+            }
+        }
         if (attempt >= 4) return fail(RCX_ERR_NOMEM, "rcx_table_build: could not size the table");
     }
     // "last record wins" per count slot, one partition of the table at a time (the side array is as large as the

@@ -248,3 +248,24 @@ def test_table_build_in_partitions(gpu, monkeypatch):
     assert gpu.table_info()["entries"] == len(table)
     parts = gpu.lookup(q)
     assert np.array_equal(one, exp) and np.array_equal(parts, exp)
+
+
+def test_table_grows_and_densifies(gpu, monkeypatch):
+    """Unrelated random k-mers have two (k-1)-mer contexts each, twice what the first sizing assumes: the build resizes;
+    when the sparse size exceeds the memory budget it accepts a denser table (load up to 0.7) and still answers exactly."""
+    rng = np.random.default_rng(9)
+    k = 25
+    codes = rng.integers(0, 1 << 50, size=300000, dtype=np.uint64)
+    counts = rng.integers(2, 1000, size=len(codes), dtype=np.int32)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    q = np.concatenate([codes[:100000], rng.integers(0, 1 << 50, size=50000, dtype=np.uint64)])
+    exp = np.array([T.oracle().orc_table_count(table.h, int(x)) for x in q], dtype=np.int32)
+    gpu.build_table(k, codes, counts)
+    sparse_bytes = gpu.table_info()["bytes"]
+    assert np.array_equal(gpu.lookup(q), exp)
+    monkeypatch.setenv("RCX_TABLE_MAX_BYTES", str(int(2 * len(codes) / 0.6 * 32)))   # room for load ~0.6 only
+    gpu.build_table(k, codes, counts)
+    assert gpu.table_info()["bytes"] < sparse_bytes
+    assert gpu.table_info()["entries"] == len(table)
+    assert np.array_equal(gpu.lookup(q), exp)
