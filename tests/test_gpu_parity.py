@@ -269,3 +269,44 @@ def test_table_grows_and_densifies(gpu, monkeypatch):
     assert gpu.table_info()["bytes"] < sparse_bytes
     assert gpu.table_info()["entries"] == len(table)
     assert np.array_equal(gpu.lookup(q), exp)
+
+
+def test_long_reads_use_the_warp_kernels(gpu, workdir):
+    """Reads longer than 255 bases do not fit the thread-per-read kernels' shared-memory rows: they take the
+    warp-per-read scan / preparation / finalize kernels and the dense path[] / fix[] of the search kernel."""
+    k = 27
+    d, bs, b, codes, counts = _load(workdir, "long400", k, True, dict(seed=41, ntx=30, reads=3000, len=400, err=0.015, txmin=600, txmax=3000))
+    assert int(np.diff(b.off.astype(np.int64)).max()) > 255
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    exp = T.oracle_correct(table, b, k, T.INTERLEAVED, er, bq, 4)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, 4)
+    got = gpu.correct(T.INTERLEAVED, b.seq, b.qual, b.off)
+    st = gpu.stats()
+    assert st["kernel_launches"] == 6 and st["unsupported"] == 0
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
+    assert int((exp[1] > 0).sum()) > 0
+
+
+@pytest.mark.parametrize("name,k,paired,maxcor,kw", [CASES[0], CASES[3]], ids=[CASES[0][0], CASES[3][0]])
+def test_warp_kernels_on_short_reads(gpu, workdir, name, k, paired, maxcor, kw, monkeypatch):
+    """RCX_SCAN_WARP=1 sends ordinary reads through the warp-per-read kernels as well (same results)."""
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    mode = T.INTERLEAVED if paired else T.SINGLE
+    exp = T.oracle_correct(table, b, k, mode, er, bq, maxcor)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, maxcor)
+    monkeypatch.setenv("RCX_SCAN_WARP", "1")
+    got = gpu.correct(mode, b.seq, b.qual, b.off)
+    assert gpu.stats()["kernel_launches"] == 6
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        assert np.array_equal(np.asarray(e), np.asarray(g)), nm
