@@ -43,7 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 SYNTH = os.path.join(ROOT, "tools", "bin", "rcx_synth")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "rcorrector")
-METRIC = "reads/s (stage-3 correction, k=23)"
+METRIC = "reads/s (stage-3 correction, k=%d)"
 
 
 def log(*a):
@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=23)
     ap.add_argument("--tx-bases", type=int, default=50_000_000, help="transcriptome size ~= distinct k-mers")
     ap.add_argument("--err", type=float, default=0.01)
+    ap.add_argument("--paired", action="store_true", help="--reads records = reads/2 pairs, mates interleaved (the -p / -i shape)")
+    ap.add_argument("--maxcork", type=int, default=4, help="MAX_FIX_PER_K (-maxcorK)")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="reads in the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workdir", default=None)
@@ -68,21 +70,31 @@ def parse_args():
 
 
 # ----------------------------------------------------------------------------- workload
-def workload_dir(a, seed):
+def workload_dir(a, seed, rseed=None):
     key = "r%d_l%d_k%d_t%d_e%g_s%d" % (a.reads, a.len, a.k, a.tx_bases, a.err, seed)
+    if a.paired:
+        key += "_p"
+    if rseed not in (None, seed):
+        key += "_rs%d" % rseed
     base = a.workdir or ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
     return os.path.join(base, "rcx_bench_" + hashlib.md5(key.encode()).hexdigest()[:10])
 
 
-def synth_cmd(a, seed, d, reads=True, table=False, dump=False, fq_limit=0):
+def synth_cmd(a, seed, d, reads=True, table=False, dump=False, fq_limit=0, rseed=None):
     ntx = max(4, a.tx_bases // 1400)
     cmd = [SYNTH, "-seed", str(seed), "-k", str(a.k), "-ntx", str(ntx), "-txmin", "300", "-txmax", "2500", "-chimera", "0",
-           "-polya", "0.3", "-sigma", "2.6", "-reads", str(a.reads), "-len", str(a.len), "-err", str(a.err),
-           "-nrate", "0.002", "-short", "0.02"]
+           "-polya", "0.3", "-sigma", "2.6", "-reads", str(a.reads // 2 if a.paired else a.reads), "-len", str(a.len),
+           "-err", str(a.err), "-nrate", "0.002", "-short", "0.02"]
+    if a.paired:
+        cmd += ["-paired"]
+    if rseed not in (None, seed):
+        cmd += ["-rseed", str(rseed)]
     if reads:
         cmd += ["-bin", os.path.join(d, "reads")]
     if fq_limit:
-        cmd += ["-fq1", os.path.join(d, "sample.fq"), "-fqlimit", str(fq_limit)]
+        cmd += ["-fq1", os.path.join(d, "sample.fq"), "-fqlimit", str(fq_limit // 2 if a.paired else fq_limit)]
+        if a.paired:
+            cmd += ["-fq2", os.path.join(d, "sample2.fq")]
     if table:
         cmd += ["-table", os.path.join(d, "table")]
     if dump:
@@ -95,14 +107,16 @@ def ensure_tools():
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools")], stdout=sys.stderr)
 
 
-def gen_reads(a, seed):
-    """Per-rank read shard (binary buffers). The transcriptome (hence the table) depends only on a fixed seed."""
+def gen_reads(a, seed, rseed=None):
+    """Per-rank read shard (binary buffers).  The transcriptome (hence the table) depends only on `seed`; `rseed` draws
+    another shard of reads from it (rank r uses rseed = seed + r, so no two GPUs correct the same reads)."""
     ensure_tools()
-    d = workload_dir(a, seed)
+    d = workload_dir(a, seed, rseed)
     os.makedirs(d, exist_ok=True)
-    if not os.path.exists(os.path.join(d, "reads.off")):
+    if not os.path.exists(os.path.join(d, "reads.ok")):
         t0 = time.time()
-        subprocess.check_call(synth_cmd(a, seed, d, reads=True), stdout=sys.stderr)
+        subprocess.check_call(synth_cmd(a, seed, d, reads=True, rseed=rseed), stdout=sys.stderr)
+        open(os.path.join(d, "reads.ok"), "w").close()
         log("[bench] generated %d reads in %.1fs -> %s" % (a.reads, time.time() - t0, d))
     return d
 
@@ -179,15 +193,22 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
 def run_reference_binary(a, d, files, threads, poll=False):
-    """Run oracle/_ref/rcorrector once over `files` (-r each). Returns dict with the timed region
-    ('Bad quality threshold' -> 'Processed') and, when poll=True, per-file completion times."""
+    """Run oracle/_ref/rcorrector once over `files` (-r each, or -p for a (mate1, mate2) tuple). Returns dict with the
+    timed region ('Bad quality threshold' -> 'Processed') and, when poll=True, per-file completion times."""
     outdir = os.path.join(d, "ref_out")
     os.makedirs(outdir, exist_ok=True)
+    cor_name = lambda f: os.path.join(outdir, os.path.basename(f)[: os.path.basename(f).rfind(".")] + ".cor.fq")
     cmd = [REF_BIN]
+    outs, extra_outs = [], []
     for f in files:
-        cmd += ["-r", f]
-    cmd += ["-c", os.path.join(d, "table.dump"), "-k", str(a.k), "-od", outdir, "-t", str(threads)]
-    outs = [os.path.join(outdir, os.path.basename(f)[: os.path.basename(f).rfind(".")] + ".cor.fq") for f in files]
+        if isinstance(f, tuple):
+            cmd += ["-p", f[0], f[1]]
+            outs.append(cor_name(f[1]))  # the mate-2 record of a pair is written last
+            extra_outs.append(cor_name(f[0]))
+        else:
+            cmd += ["-r", f]
+            outs.append(cor_name(f))
+    cmd += ["-c", os.path.join(d, "table.dump"), "-k", str(a.k), "-od", outdir, "-t", str(threads), "-maxcorK", str(a.maxcork)]
     t_launch = time.time()
     p = subprocess.Popen(cmd, stderr=subprocess.PIPE, stdout=subprocess.DEVNULL)
     marks = {}
@@ -249,7 +270,7 @@ def run_reference_binary(a, d, files, threads, poll=False):
             done.append(t_done)
         done[-1] = marks["end"]
         res["done"] = done
-    for o in outs:
+    for o in outs + extra_outs:
         try:
             os.remove(o)
         except OSError:
@@ -258,13 +279,15 @@ def run_reference_binary(a, d, files, threads, poll=False):
 
 
 def reference_sample_files(a, d, count):
-    src = os.path.join(d, "sample.fq")
     files = []
     for i in range(count):
-        f = os.path.join(d, "sample_%02d.fq" % i)
-        if not os.path.exists(f):
-            os.link(src, f)
-        files.append(f)
+        fs = []
+        for src, tag in (("sample.fq", "s"), ("sample2.fq", "t"))[: 2 if a.paired else 1]:
+            f = os.path.join(d, "sample_%s%02d.fq" % (tag, i))
+            if not os.path.exists(f):
+                os.link(os.path.join(d, src), f)
+            fs.append(f)
+        files.append(tuple(fs) if a.paired else fs[0])
     return files
 
 
@@ -295,7 +318,7 @@ def main_reference(a):
     dt = max(t1 - t0, 1e-9)
     value = per_file * a.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": METRIC % a.k, "value": value, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": workload_config(a, extra={"step": "bounded sample: %d reads per step, full-size table" % per_file}),
@@ -311,8 +334,18 @@ def main_reference(a):
 
 
 def workload_config(a, extra=None):
-    c = {"workload": "configs[1]: %d synthetic single-end %d bp reads, k=%d, ~%d distinct k-mers, read-sharded" % (a.reads, a.len, a.k, a.tx_bases),
-         "reads_per_gpu": a.reads, "read_len": a.len, "k": a.k, "table_kmers": a.tx_bases, "error_rate_injected": a.err,
+    if not a.paired and a.len == 100 and a.k == 23:
+        shape = "configs[1]"
+    elif a.paired and a.k == 23:
+        shape = "configs[2]-shaped (scaled)"
+    elif a.k == 31:
+        shape = "configs[4]-shaped (scaled)"
+    else:
+        shape = "custom"
+    c = {"workload": "%s: %d synthetic %s %d bp reads, k=%d, ~%d distinct k-mers, read-sharded (every GPU its own shard of reads)" % (
+             shape, a.reads, "paired-end (interleaved)" if a.paired else "single-end", a.len, a.k, a.tx_bases),
+         "reads_per_gpu": a.reads, "read_len": a.len, "k": a.k, "paired": bool(a.paired), "max_fix_per_k": a.maxcork,
+         "table_kmers": a.tx_bases, "error_rate_injected": a.err,
          "l2_policy": "inputs (>= 2 GB reads + >= 1.6 GB table per step) far exceed the 126 MB L2"}
     if extra:
         c.update(extra)
@@ -324,7 +357,9 @@ def main_ours(a):
     import torch
     import torch.distributed as dist
 
-    from rcorrector_b200 import SINGLE, Corrector
+    from rcorrector_b200 import INTERLEAVED, SINGLE, Corrector
+
+    mode = INTERLEAVED if a.paired else SINGLE
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -344,7 +379,8 @@ def main_ours(a):
     cor = Corrector(local)
     # ---- table: rank 0 generates/loads, NCCL broadcast, local insert on every GPU
     if rank == 0:
-        td = gen_table(a, 1, want_dump=not a.no_cpu_baseline, fq_limit=0 if a.no_cpu_baseline else a.cpu_sample)
+        want_cpu = not a.no_cpu_baseline and world == 1  # the dump and the FASTQ sample only feed the CPU leg (N = 1)
+        td = gen_table(a, 1, want_dump=want_cpu, fq_limit=a.cpu_sample if want_cpu else 0)
         codes = np.fromfile(os.path.join(td, "table.codes"), dtype=np.uint64)
         counts = np.fromfile(os.path.join(td, "table.counts"), dtype=np.int32)
         nk = len(codes)
@@ -368,15 +404,10 @@ def main_ours(a):
         cor.build_table(a.k, codes, counts)
     info = cor.table_info()
     er, bq = 0.01, ord("0")
-    cor.set_params(a.k, er, bq, 4)
+    cor.set_params(a.k, er, bq, a.maxcork)
 
-    # ---- reads: every rank its own shard (different seed => different reads, same transcriptome seed 1)
-    # (weak scaling needs equal work per GPU: rank 0 generates the shard once, every rank loads the same files)
-    if rank == 0:
-        gen_reads(a, 1)
-    if world > 1:
-        dist.barrier()
-    rd = workload_dir(a, 1)
+    # ---- reads: every rank its own shard of the same size (read seed 1 + rank, transcriptome seed 1): weak scaling
+    rd = gen_reads(a, 1, 1 + rank)
     seq_h = np.fromfile(os.path.join(rd, "reads.seq"), dtype=np.uint8)
     qual_h = np.fromfile(os.path.join(rd, "reads.qual"), dtype=np.uint8)
     off_h = np.fromfile(os.path.join(rd, "reads.off"), dtype=np.uint32)
@@ -406,10 +437,10 @@ def main_ours(a):
     def step_device():
         with torch.cuda.stream(stream):
             d_seq.copy_(d_seq0, non_blocking=True)  # restore the uncorrected reads (correction is in place)
-        cor.correct_device(SINGLE, n, d_seq, d_qual, d_off, total, max_len, *d_res)
+        cor.correct_device(mode, n, d_seq, d_qual, d_off, total, max_len, *d_res)
 
     def step_e2e():
-        cor.correct(SINGLE, seq_p, qual_p, off_p, out=(out_seq, *out_i))
+        cor.correct(mode, seq_p, qual_p, off_p, out=(out_seq, *out_i))
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -487,7 +518,7 @@ def main_ours(a):
     if st["unsupported"]:
         raise SystemExit("bench: %d reads needed a third A.4 pass (unsupported)" % st["unsupported"])
     line = {
-        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": METRIC % a.k, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(a, {"table_entries": info["entries"], "table_bytes": info["bytes"]}),
         "mbase_per_s": value * a.len / 1e6,

@@ -21,9 +21,8 @@
 #include "rcx_internal.h"
 
 #define TS_THREADS 128  // reads per tile for reads up to 128 bases; longer reads use 64-read tiles (more blocks fit the shared memory)
-#ifndef TS_DEPTH
-#define TS_DEPTH 2  // measured 2 / 4 / 8 in flight per thread: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding)
-#endif
+// TS_DEPTH (template parameter DEPTH): sector requests in flight per thread.  Measured for 100-bp reads (128-read tiles,
+// 512 threads per SM) 2 / 4 / 8: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding) -> 2.
 #define TS_LOOSE 0x80000000u   // flag bits stored with a count in shared memory
 #define TS_STRICT 0x40000000u
 #define TS_INVALID 0x20000000u
@@ -120,7 +119,7 @@ __device__ __forceinline__ int ts_select_coop(const unsigned int* warp_rows, int
     return result;
 }
 
-template <int NW, int NT>
+template <int NW, int NT, int TS_DEPTH>
 __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.t.k;
@@ -511,24 +510,29 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
     if (lane == 0 && toobig) atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);  // a count >= 2^29: flagged, not hidden
 }
 
-template <int NW, int NT>
+template <int NW, int NT, int DEPTH>
 static cudaError_t launch_scan_thread_nw(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
     const TsLayout L = ts_layout(a.max_len, a.t.k, NT);
-    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW, NT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW, NT>, NT, L.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW, NT, DEPTH>, NT, L.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long want = (a.n + NT - 1) / NT;
     long long grid = (long long)sm_count * per_sm;  // persistent grid: a multiple of the SM count
     if (grid > want) grid = want;
-    rcx_scan_thread_kernel<NW, NT><<<(unsigned int)grid, NT, L.smem, s>>>(a);
+    rcx_scan_thread_kernel<NW, NT, DEPTH><<<(unsigned int)grid, NT, L.smem, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS>(a, sm_count, s);
-    return launch_scan_thread_nw<4, 64>(a, sm_count, s);  // max_len <= 255
+    static const int long_variant = getenv("RCX_TS_LONG") ? atoi(getenv("RCX_TS_LONG")) : 0;  // measurement knob
+    if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS, 2>(a, sm_count, s);
+    // max_len <= 255
+    if (long_variant == 1) return launch_scan_thread_nw<4, 64, 4>(a, sm_count, s);
+    if (long_variant == 2) return launch_scan_thread_nw<4, 128, 2>(a, sm_count, s);
+    if (long_variant == 3) return launch_scan_thread_nw<4, 128, 4>(a, sm_count, s);
+    return launch_scan_thread_nw<4, 64, 2>(a, sm_count, s);
 }

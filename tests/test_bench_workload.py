@@ -1,0 +1,57 @@
+"""CPU checks of bench.py's host side: the workload generator's shard semantics (one transcriptome, one table, a
+different shard of reads per rank) and the reference arm's JSON line on a tiny workload, single-end and paired.
+No GPU, no compute through librcx."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import rcx_testlib as T
+
+ROOT = T.ROOT
+
+
+def _synth(wd, name, *extra):
+    if not os.path.exists(T.SYNTH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools")])
+    p = os.path.join(wd, name)
+    subprocess.check_call([T.SYNTH, "-seed", "1", "-ntx", "40", "-reads", "800", "-len", "100", "-k", "23", "-bin", p, "-table", p + "_t"] + list(extra),
+                          stderr=subprocess.DEVNULL)
+    return {x: np.fromfile(p + ext, dtype=dt) for x, ext, dt in
+            (("seq", ".seq", np.uint8), ("off", ".off", np.uint32), ("codes", "_t.codes", np.uint64), ("counts", "_t.counts", np.int32))}
+
+
+def test_read_shards_share_the_table(workdir):
+    a = _synth(workdir, "s_a")
+    b = _synth(workdir, "s_b", "-rseed", "2")
+    c = _synth(workdir, "s_c", "-rseed", "1")
+    assert np.array_equal(a["codes"], b["codes"]) and np.array_equal(a["counts"], b["counts"])  # same transcriptome, same table
+    assert len(a["off"]) == len(b["off"])
+    assert not np.array_equal(a["seq"][:2000], b["seq"][:2000])  # another shard of reads
+    assert np.array_equal(a["seq"], c["seq"]) and np.array_equal(a["off"], c["off"])  # -rseed defaults to -seed
+
+
+def test_paired_shard_is_interleaved(workdir):
+    p = _synth(workdir, "s_p", "-paired")
+    assert len(p["off"]) - 1 == 1600  # 800 pairs -> 1600 records, mates at 2i, 2i+1
+    lens = np.diff(p["off"].astype(np.int64))
+    assert (lens[1::2] == 100).all()  # only mate 1 is ever truncated
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_reference_arm_line(workdir, paired):
+    if not os.path.exists(T.REF_BIN):
+        pytest.skip("oracle/_ref/rcorrector not built")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--reads", "20000", "--tx-bases", "150000",
+           "--cpu-sample", "1000", "--steps", "2", "--warmup", "1", "--workdir", os.path.join(workdir, "bw")]
+    if paired:
+        cmd += ["--paired", "--len", "150"]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    assert line["impl"] == "reference" and line["unit"] == "reads/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["config"]["paired"] is paired

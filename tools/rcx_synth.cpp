@@ -12,6 +12,7 @@
 // prefix of the binary buffers.
 //
 // Outputs (all optional):
+//   -rseed S    seed of the reads only (default: -seed): another shard of reads from the same transcriptome
 //   -fq1 F [-fq2 F] [-fqlimit M]  FASTQ text (first M reads/pairs only)
 //   -bin P      P.seq P.qual (concatenated, no separators) P.off (uint32[n+1]);
 //               paired reads are interleaved mate1,mate2,...
@@ -54,6 +55,7 @@ static inline uint64_t mix(uint64_t a, uint64_t b) {
 
 struct Opts {
     uint64_t seed = 1;
+    uint64_t rseed = 0;  // reads only (0: same as seed): different shards of reads from the same transcriptome
     long ntx = 50;
     int txmin = 300, txmax = 2500;
     double polya = 0.3, paralog = 0.0, repeat = 0.0, chimera = 0.2, sigma = 2.0;
@@ -75,6 +77,7 @@ int main(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
         auto is = [&](const char* s) { return !strcmp(argv[i], s); };
         if (is("-seed")) o.seed = strtoull(argv[++i], 0, 10);
+        else if (is("-rseed")) o.rseed = strtoull(argv[++i], 0, 10);
         else if (is("-ntx")) o.ntx = atol(argv[++i]);
         else if (is("-txmin")) o.txmin = atoi(argv[++i]);
         else if (is("-txmax")) o.txmax = atoi(argv[++i]);
@@ -101,6 +104,7 @@ int main(int argc, char** argv) {
         else { fprintf(stderr, "rcx_synth: unknown option %s\n", argv[i]); return 1; }
     }
     if (o.len < 1 || o.len > 1000 || o.k < 1 || o.k > 32) { fprintf(stderr, "bad -len/-k\n"); return 1; }
+    if (!o.rseed) o.rseed = o.seed;
     if (o.txmin < o.len) o.txmin = o.len;
     if (o.txmax < o.txmin) o.txmax = o.txmin;
     int nthreads = o.threads > 0 ? o.threads : (int)std::thread::hardware_concurrency();
@@ -163,7 +167,7 @@ int main(int argc, char** argv) {
         off.assign(nrec + 1, 0);
         // pass 1: lengths (cheap, deterministic per read index)
         auto read_len = [&](long pair_idx, int mate) -> int {
-            Rng r(mix(o.seed ^ 0x5EED, (uint64_t)pair_idx));
+            Rng r(mix(o.rseed ^ 0x5EED, (uint64_t)pair_idx));
             double u = r.uni();
             if (mate == 0 && u < o.shortfrac) return 15 + (int)(r.uni() * (o.len - 15 + 1));
             return o.len;
@@ -182,7 +186,7 @@ int main(int argc, char** argv) {
         auto worker = [&](long lo, long hi) {
             std::string frag, m2;
             for (long i = lo; i < hi; ++i) {
-                Rng r(mix(o.seed ^ 0xF00D, (uint64_t)i));
+                Rng r(mix(o.rseed ^ 0xF00D, (uint64_t)i));
                 double x = r.uni() * tot;
                 long t = std::lower_bound(cum.begin(), cum.end(), x) - cum.begin();
                 if (t >= T) t = T - 1;
