@@ -365,6 +365,7 @@ def main_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL_DEBUG=VERSION/WARN prints a banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -468,6 +469,7 @@ def main_ours(a):
     ms_dev = timed(step_device, a.steps, a.warmup)
     st = cor.stats()  # counters + per-kernel CUDA-event times of the last device step
     ms_e2e = timed(step_e2e, a.steps, a.warmup)
+    st_e2e = cor.stats()  # the last host-buffer call: per-phase CUDA-event times summed over its chunks
     clocks = sampler.stop() if sampler else None
 
     # parity spot check inside the bench (size-independent property): both arms give identical results
@@ -523,7 +525,10 @@ def main_ours(a):
         "data": "synthetic", "config": workload_config(a, {"table_entries": info["entries"], "table_bytes": info["bytes"]}),
         "mbase_per_s": value * a.len / 1e6,
         "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": int(2 * total + 4 * (n + 1)) * world, "d2h_bytes_per_step": int(total + 16 * n) * world},
+                "h2d_bytes_per_step": int(2 * total + 4 * (n + 1)) * world, "d2h_bytes_per_step": int(total + 16 * n) * world,
+                # summed over the chunks of the last call; chunks overlap, so the sum exceeds ms_per_step (a copy's time includes
+                # its wait for the copy engine)
+                "chunk_sums_ms": {k: round(float(st_e2e["ms_" + k]), 2) for k in ("h2d", "scan", "dfs", "finalize", "d2h", "total")}},
         "gpu_launches": int(st["kernel_launches"]) * a.steps * world,  # 6 kernels per step per GPU in the timed region of `value` (the e2e region launches the same 6)
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic.get(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),

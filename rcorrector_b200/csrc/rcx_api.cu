@@ -51,8 +51,9 @@ struct DevBuf {
 
 // One pipeline slot = everything one batch (or one chunk of a host batch) needs on the device: a stream, the staging
 // buffers, the intermediates of the hot path and the events that time it.  Host batches are cut into chunks that cycle
-// through RCX_NSLOTS slots so that the PCIe copies of one chunk overlap the kernels of another.
-#define RCX_NSLOTS 3
+// through the slots so that the PCIe copies of one chunk overlap the kernels of another.  Buffers grow on first use, so
+// a slot that is never used costs nothing.
+#define RCX_NSLOTS 6
 struct RcxSlot {
     cudaStream_t stream = nullptr;
     DevBuf<char> d_seq, d_qual;
@@ -95,6 +96,8 @@ struct rcx_ctx {
     rcx_params params{};
     bool have_params = false;
     RcxSlot slot[RCX_NSLOTS];
+    int nslots = 3;  // slots a host batch cycles through (RCX_SLOTS)
+    int chain = 0;   // RCX_CHAIN: 1 = a chunk's kernels start when the previous chunk has reached its finalize kernel, 2 = when it is done
     rcx_stats stats{};
 };
 
@@ -126,6 +129,8 @@ extern "C" int rcx_create(int device, rcx_ctx** out) {
         for (auto& ev : sl.kev) CUDA_TRY(cudaEventCreate(&ev));
     }
     c->stream = c->slot[0].stream;
+    if (const char* e = getenv("RCX_SLOTS")) c->nslots = std::max(2, std::min(RCX_NSLOTS, atoi(e)));
+    if (const char* e = getenv("RCX_CHAIN")) c->chain = atoi(e);
     *out = c;
     return RCX_OK;
 }
@@ -569,7 +574,12 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
     CUDA_TRY(cudaSetDevice(c->device));
     rc = begin_call(c, (uint64_t)n, off[n]);
     if (rc) return rc;
-    int64_t chunk_reads = 2 << 20;  // measured per 10 M-read batch: 1 M / 1.5 M / 2 M / 3 M records -> 81.9 / 75.5 / 75.0 / 85.2 ms
+    // Chunks are sized in BASES: what a chunk costs (copies, kernels) follows its bases, not its records.  Measured per 10 M
+    // 100-bp reads: 1 M / 1.5 M / 2 M / 3 M records -> 81.9 / 75.5 / 75.0 / 85.2 ms; per 6 M 150-bp reads: 1 M / 1.5 M / 2 M /
+    // 3 M records -> 81.9 / 82.2 / 96.8 / 102.0 ms (profiles/r01_u_e2e_chunks.md).
+    double chunk_bases = 208e6;  // = the 2 Mi-record chunks the 100-bp workload was tuned with
+    if (const char* e = getenv("RCX_CHUNK_BASES")) chunk_bases = atof(e);
+    int64_t chunk_reads = (int64_t)(chunk_bases / std::max(1.0, (double)off[n] / (double)n));
     if (const char* e = getenv("RCX_CHUNK_READS")) chunk_reads = atoll(e);
     if (chunk_reads < 2) chunk_reads = 2;
     chunk_reads &= ~(int64_t)1;
@@ -587,7 +597,8 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
         if (ramp) cuts.push_back(n);
     }
     int si = 0;
-    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci, si = (si + 1) % RCX_NSLOTS) {
+    RcxSlot* prev = nullptr;
+    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci, si = (si + 1) % c->nslots) {
         const int64_t lo = cuts[ci], hi = cuts[ci + 1], cn = hi - lo;
         if (cn <= 0) continue;
         int32_t max_len = 0;
@@ -609,6 +620,9 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
         CUDA_TRY(cudaMemcpyAsync(sl.d_seq.p + lead, seq_in + b0, span, cudaMemcpyHostToDevice, sl.stream));
         CUDA_TRY(cudaMemcpyAsync(sl.d_qual.p + lead, qual + b0, span, cudaMemcpyHostToDevice, sl.stream));
         CUDA_TRY(cudaMemcpyAsync(sl.d_off.p, off + lo, ((size_t)cn + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.stream));
+        if (prev && c->chain == 1 && prev->kev_valid) CUDA_TRY(cudaStreamWaitEvent(sl.stream, prev->kev[5], 0));
+        if (prev && c->chain == 2) CUDA_TRY(cudaStreamWaitEvent(sl.stream, prev->ev[3], 0));
+        prev = &sl;
         rc = launch_pipeline(c, sl, mode, cn, sl.d_seq.p + lead - b0, sl.d_qual.p + lead - b0, sl.d_off.p, b0, b1, max_len, sl.d_corr.p,
                              sl.d_l.p, sl.d_m.p, sl.d_h.p, true);
         if (rc) return rc;

@@ -22,7 +22,8 @@
 
 #define TS_THREADS 128  // reads per tile for reads up to 128 bases; longer reads use 64-read tiles (more blocks fit the shared memory)
 // TS_DEPTH (template parameter DEPTH): sector requests in flight per thread.  Measured for 100-bp reads (128-read tiles,
-// 512 threads per SM) 2 / 4 / 8: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding) -> 2.
+// 512 threads per SM) 2 / 4 / 8: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding) -> 2; for 150-bp
+// reads (64-read tiles, 320 threads per SM) 2 / 4: 28.2 / 29.0 ms per 6 M reads -> 2 (profiles/r01_u_e2e_chunks.md).
 #define TS_LOOSE 0x80000000u   // flag bits stored with a count in shared memory
 #define TS_STRICT 0x40000000u
 #define TS_INVALID 0x20000000u
@@ -528,11 +529,6 @@ static cudaError_t launch_scan_thread_nw(const RcxScanArgs& a, int sm_count, cud
 
 cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
     if (a.n <= 0) return cudaSuccess;
-    static const int long_variant = getenv("RCX_TS_LONG") ? atoi(getenv("RCX_TS_LONG")) : 0;  // measurement knob
     if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS, 2>(a, sm_count, s);
-    // max_len <= 255
-    if (long_variant == 1) return launch_scan_thread_nw<4, 64, 4>(a, sm_count, s);
-    if (long_variant == 2) return launch_scan_thread_nw<4, 128, 2>(a, sm_count, s);
-    if (long_variant == 3) return launch_scan_thread_nw<4, 128, 4>(a, sm_count, s);
-    return launch_scan_thread_nw<4, 64, 2>(a, sm_count, s);
+    return launch_scan_thread_nw<4, 64, 2>(a, sm_count, s);  // max_len <= 255 (4 in flight measured on 150-bp reads: 28.2 -> 29.0 ms)
 }
