@@ -81,7 +81,11 @@ __host__ __device__ inline int dfs_cap_path(int max_len, int k, int K) {
     c += 8;  // the child that exceeds maxFixCnt is entered before it returns; up to 5 N positions; slack
     return c < max_len ? c : max_len;
 }
-__host__ __device__ inline int dfs_row_entries(int max_len, int k, int K) { return (3 * dfs_cap_path(max_len, k, K)) | 1; }  // path + accepted (2x), odd
+// Shared memory holds only the edits of the CURRENT path (touched at every substitution and every pop); the accepted edits
+// of the read (2 x cap entries, written at the few terminals that improve on the best path, read once at the end) live in
+// the lane-interleaved global scratch, so the rows no longer limit the blocks per SM for long reads or a large -maxcorK
+// (150 bp: 4 -> 6 blocks; k = 31 with -maxcorK 8: 3 -> 6).
+__host__ __device__ inline int dfs_row_entries(int max_len, int k, int K) { return dfs_cap_path(max_len, k, K) | 1; }  // odd: rows spread over the banks
 template <bool SMEM>
 __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(RcxCorrectArgs a) {
     __shared__ int lut[DFS_LUT];
@@ -104,7 +108,8 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     signed char* path = a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;  // dense path[] (long reads only)
     const int cap_path = dfs_cap_path(a.max_len, k, a.max_fix_per_k);
     unsigned short* E = dfs_rows + (size_t)threadIdx.x * dfs_row_entries(a.max_len, k, a.max_fix_per_k);  // edits on the current path
-    unsigned short* A = E + cap_path;                                                                        // accepted edits of the read
+    // accepted edits of the read (SMEM mode): address rebuilt at the few uses instead of a pointer kept live across the walk
+#define A(e) (reinterpret_cast<unsigned short*>(a.dfs_path + ((((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5) * (long long)a.dfs_lpad << 5)) + (threadIdx.x & 31))[(e) * 32]
     int ne = 0, na = 0, na_base = 0;
     bool edit_overflow = false;
 #define STK(f, w) stack[((f) * DFS_FRAME + (w)) * 32]
@@ -196,12 +201,12 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     if (a.compact_fix) {  // thread-per-item finalize: the edit list itself (count, then pos / base pairs) in the read's bytes
                         if (1 + 2 * na_base <= len && na_base < 128) {
                             fix[0] = (signed char)na_base;
-                            for (int e = 0; e < na_base; ++e) { const unsigned int x = A[e]; fix[1 + 2 * e] = (signed char)(x & 255u); fix[2 + 2 * e] = (signed char)(x >> 8); }
+                            for (int e = 0; e < na_base; ++e) { const unsigned int x = A(e); fix[1 + 2 * e] = (signed char)(x & 255u); fix[2 + 2 * e] = (signed char)(x >> 8); }
                         } else {
                             edit_overflow = true;
                         }
                     } else {
-                        for (int e = 0; e < na_base; ++e) { const unsigned int x = A[e]; fix[x & 255u] = (signed char)(x >> 8); }
+                        for (int e = 0; e < na_base; ++e) { const unsigned int x = A(e); fix[x & 255u] = (signed char)(x >> 8); }
                     }
                 }
                 stage = T_FETCH;
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     if (fc < max_fix) trial = -(max_fix - fc + 1) * RCX_MAX_TRIAL;
                     const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
                     if (SMEM) {  // the edits of this path replace the segment's previously accepted ones
-                        if (na_base + ne <= 2 * cap_path) { for (int e = 0; e < ne; ++e) A[na_base + e] = E[e]; na = ne; }
+                        if (na_base + ne <= 2 * cap_path) { for (int e = 0; e < ne; ++e) A(na_base + e) = E[e]; na = ne; }
                         else edit_overflow = true;
                     } else {
                         for (int i = lo; i <= hi; ++i) fix[i] = PATH(i);
@@ -431,6 +436,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     }
 #undef STK
 #undef PATH
+#undef A
     // counters: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
         n_nodes += __shfl_xor_sync(RCX_FULL, n_nodes, o);
@@ -463,7 +469,8 @@ void rcx_dfs_geometry(int sm_count, int max_len, int k, int K, int* grid, int* d
     int kc = max_len - k + 1;
     if (kc < 1) kc = 1;
     *depth = kc + 3;
-    *lpad = max_len + 2;
+    // bytes per thread of the lane-interleaved scratch: the dense path[] of long reads, or the accepted edit list (2 x cap 16-bit entries)
+    *lpad = dfs_smem_rows(max_len) ? 4 * dfs_cap_path(max_len, k, K) + 4 : max_len + 2;
 }
 size_t rcx_dfs_stack_words(int grid, int depth) { return (size_t)grid * (DFS_THREADS / 32) * depth * DFS_FRAME * 32; }
 size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREADS / 32) * lpad * 32; }
