@@ -1,3 +1,7 @@
+# Compare variant libraries in one call.  Build them first, e.g.:
+#   cd rcorrector_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -DDFS_MINBLOCKS=7 -c rcx_dfs.cu -o ../../build/rcx_dfs_mb7.o
+#   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/librcx_mb7.so <the other .o files> ../../build/rcx_dfs_mb7.o -lcudart
+# (r01_y: 7 / 8 search blocks per SM measured equal / slower than 6)
 OUT=gpurun_out/r01_y; mkdir -p $OUT
 A="--no-cpu-baseline --steps 3 --warmup 3"
 Q="--reads 4000000 --len 150 --k 31 --err 0.04 --maxcork 8 --tx-bases 50000000 --no-cpu-baseline --steps 3 --warmup 3"
