@@ -110,6 +110,13 @@ inline std::string output_stem(const std::string& in) {
     return in.substr(s + 1);
 }
 
+// Reads.h:138-157: <od>/<stem>.cor.fq (FASTQ, type 1) or .cor.fa (FASTA), plus ".gz" when the input path ends in "gz"
+inline std::string output_path(const std::string& od, const std::string& in, int type) {
+    std::string s = od + "/" + output_stem(in) + (type == 1 ? ".cor.fq" : ".cor.fa");
+    if (ends_with_gz(in)) s += ".gz";
+    return s;
+}
+
 // Block reader over a plain or gzip file that hands out lines (without the '\n').
 class LineReader {
    public:

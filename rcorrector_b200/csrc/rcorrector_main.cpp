@@ -94,12 +94,7 @@ static int sniff_type(const std::string& path) {  // Reads.h:108-132
     return p[0] == '@' ? 1 : 0;
 }
 
-static std::string out_name(const std::string& od, const std::string& in, int type) {  // Reads.h:138-157
-    std::string stem = rcxio::output_stem(in);
-    std::string s = od + "/" + stem + (type == 1 ? ".cor.fq" : ".cor.fa");
-    if (rcxio::ends_with_gz(in)) s += ".gz";
-    return s;
-}
+static std::string out_name(const std::string& od, const std::string& in, int type) { return rcxio::output_path(od, in, type); }
 
 // ---------------------------------------------------------------------------------------------- dump loading
 struct Dump {
