@@ -81,7 +81,7 @@ struct ReadFile {
 static int sniff_type(const std::string& path) {  // Reads.h:108-132
     LineReader r;
     if (!r.open(path)) {
-        fprintf(stderr, "ERROR: Could not open file %s\n", path.c_str());
+        fprintf(stderr, "ERROR: Could not access file %s\n", path.c_str());  // File.h:71,93
         exit(1);
     }
     const char* p;
@@ -628,8 +628,12 @@ int main(int argc, char* argv[]) {
     // the reference opens (truncates) every output when the file is added (Reads.h:159-160)
     std::vector<Writer> out1(files.size()), out2(files.size());
     for (size_t i = 0; i < files.size(); ++i) {
-        if (!out1[i].open(files[i].out_path, to_stdout) || (files[i].paired && !out2[i].open(files[i].mate_out_path, to_stdout))) {
-            fprintf(stderr, "ERROR: Could not open file %s\n", files[i].out_path.c_str());
+        if (!out1[i].open(files[i].out_path, to_stdout)) {
+            fprintf(stderr, "ERROR: Could not access file %s\n", files[i].out_path.c_str());  // File.h:71,93
+            exit(1);
+        }
+        if (files[i].paired && !out2[i].open(files[i].mate_out_path, to_stdout)) {
+            fprintf(stderr, "ERROR: Could not access file %s\n", files[i].mate_out_path.c_str());
             exit(1);
         }
     }
@@ -738,7 +742,7 @@ int main(int argc, char* argv[]) {
         const ReadFile& f = files[fi];
         Source s1, s2;
         if (!s1.open(f.path, f.type, fast_io) || (f.paired && !s2.open(f.mate_path, sniff_type(f.mate_path), fast_io))) {
-            fprintf(stderr, "ERROR: Could not open file %s\n", f.path.c_str());
+            fprintf(stderr, "ERROR: Could not access file %s\n", f.path.c_str());
             exit(1);
         }
         if (f.paired && s1.fast != s2.fast) {  // both mates through the same reader

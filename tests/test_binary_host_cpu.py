@@ -80,3 +80,133 @@ def test_argv_surface(double_exe, workdir):
     r = subprocess.run([double_exe] + args, capture_output=True)
     assert r.returncode == 0, r.stderr.decode()
     assert open(os.path.join(od, meta["outputs"][0][:-3]), "rb").read() == expected[0]
+
+
+@pytest.mark.skipif(not os.path.exists(T.REF_BIN), reason="oracle/_ref/rcorrector not built")
+@pytest.mark.parametrize("gz", [False, True])
+def test_fasta_input_matches_the_reference(double_exe, workdir, gz):
+    """FASTA in -> <name>.cor.fa out (two lines per record, tags on the id line, no quality).  The reference's
+    own FASTA path only works with -t >= 2 (its -t 1 path dereferences a NULL quality pointer): compare there."""
+    import gzip
+
+    meta, fq, dump, expected = T.load_golden("single_repeat_n", workdir + "_cpu")
+    lines = open(fq[0], "rb").read().split(b"\n")
+    fa = []
+    for i in range(0, len(lines) - 1, 4):
+        fa += [b">" + lines[i][1:], lines[i + 1]]
+    w = os.path.join(workdir + "_cpu", "fasta_gz" if gz else "fasta")
+    os.makedirs(w, exist_ok=True)
+    path = os.path.join(w, "x.fa.gz" if gz else "x.fa")
+    with (gzip.open if gz else open)(path, "wb") as f:
+        f.write(b"\n".join(fa) + b"\n")
+    res = []
+    for tag, exe in (("ref", T.REF_BIN), ("ours", double_exe)):
+        od = os.path.join(w, "o_" + tag)
+        r = subprocess.run([exe, "-r", path, "-c", dump, "-k", str(meta["k"]), "-od", od, "-t", "2"] + meta["extra"], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        out = os.path.join(od, "x.cor.fa.gz" if gz else "x.cor.fa")
+        res.append(((gzip.open if gz else open)(out, "rb").read(), r.stderr))
+    assert res[0][0] == res[1][0] and len(res[0][0]) > 0
+    assert res[0][1] == res[1][1]  # Stored / rate / "Bad quality threshold is '\0'" / Processed lines, byte for byte
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The process surface against the reference binary itself (SURVEY §8b.1): same return code, same stderr bytes, same
+# stdout bytes, same output file names and (decompressed) contents — on the scenarios a user can reach from the command
+# line.  Not reproduced, by decision (DESIGN.md §9): inputs on which the reference's output depends on stale buffer
+# contents (blank lines inside a FASTQ file, a truncated last record), -t 0 (the reference then processes no reads), -k
+# above 32 (the reference runs on with an overflowing mask; we refuse like run_rcorrector.pl does), -verbose traces.
+def _surface_files(w):
+    import gzip
+    import shutil
+
+    m1, fq1, dump1, _ = T.load_golden("paired_k23", w)
+    m2, fq2, dump2, _ = T.load_golden("single_repeat_n", w)
+    m3, fq3, dump3, _ = T.load_golden("paired_maxcor1", w)
+
+    def cp(src, name):
+        d = os.path.join(w, name)
+        if not os.path.exists(d):
+            shutil.copy(src, d)
+        return d
+
+    f = dict(a1=cp(fq1[0], "a_1.fq"), a2=cp(fq1[1], "a_2.fq"), b1=cp(fq3[0], "b_1.fq"), b2=cp(fq3[1], "b_2.fq"), s=cp(fq2[0], "s.fq"),
+             dump=dump1, dump2=dump2, nope=os.path.join(w, "nope.fq"), nodump=os.path.join(w, "nope.dump"))
+    lines = open(f["a2"], "rb").read().split(b"\n")
+    f["short2"] = os.path.join(w, "short_2.fq")
+    open(f["short2"], "wb").write(b"\n".join(lines[:400]) + b"\n")
+    f["empty"] = os.path.join(w, "empty.fq")
+    open(f["empty"], "wb").close()
+    f["a2gz"] = os.path.join(w, "a_2.fq.gz")
+    open(f["a2gz"], "wb").write(gzip.compress(open(f["a2"], "rb").read()))
+    d = open(dump1, "rb").read().split(b"\n")
+    f["odd_dump"] = os.path.join(w, "odd.dump")  # a count-1 record, a k-mer with N, a duplicate key with another count
+    open(f["odd_dump"], "wb").write(b"\n".join(d[:200] + [b">1", d[1], b">5", b"ACGTNACGTACGTACGTACGTACG", b">7", d[1]] + d[200:]))
+    sl = open(f["s"], "rb").read().split(b"\n")
+    fa = []
+    for i in range(0, len(sl) - 1, 4):
+        fa += [b">" + sl[i][1:], sl[i + 1]]
+    f["fa"] = os.path.join(w, "x.fa")
+    open(f["fa"], "wb").write(b"\n".join(fa) + b"\n")
+    return f
+
+
+SURFACE = {
+    "two_pairs": "-p {a1} {a2} -p {b1} {b2} -c {dump} -k 23 -od @OD -t 2",
+    "pair_then_single": "-p {a1} {a2} -r {s} -c {dump} -k 23 -od @OD -t 2",
+    "single_then_pair": "-r {s} -p {a1} {a2} -c {dump} -k 23 -od @OD -t 2",
+    "two_singles_stdout": "-r {s} -r {a1} -c {dump} -k 23 -od @OD -t 2 -stdout",
+    "stdout_pair": "-p {a1} {a2} -c {dump} -k 23 -od @OD -stdout -t 2",
+    "options_after_files": "-r {s} -k 23 -c {dump} -od @OD",
+    "same_file_twice": "-r {s} -r {s} -c {dump} -k 23 -od @OD",
+    "pair_plain_and_gz": "-p {a1} {a2gz} -c {dump} -k 23 -od @OD -t 2",
+    "unpaired_short_mate2": "-p {a1} {short2} -c {dump} -k 23 -od @OD -t 2",
+    "unpaired_short_mate1": "-p {short2} {a2} -c {dump} -k 23 -od @OD -t 2",
+    "empty_file": "-r {empty} -c {dump} -k 23 -od @OD",
+    "missing_file": "-r {nope} -c {dump} -k 23 -od @OD",
+    "missing_dump": "-r {s} -c {nodump} -k 23 -od @OD",
+    "not_a_read_file": "-r {dump} -c {dump} -k 23 -od @OD",
+    "od_nested_missing": "-r {s} -c {dump} -k 23 -od @OD/x/y",
+    "no_args": "",
+    "help": "-h",
+    "unknown_flag": "-r {s} -zzz -c {dump}",
+    "wk_half": "-r {a1} -c {dump} -k 23 -od @OD -wk 0.5",
+    "wk_zero": "-r {a1} -c {dump} -k 23 -od @OD -wk 0",
+    "wk_one": "-r {a1} -c {dump} -k 23 -od @OD -wk 1",
+    "maxcor_is_dead": "-r {a1} -c {dump} -k 23 -od @OD -maxcor 1",
+    "maxcorK_0": "-r {a1} -c {dump} -k 23 -od @OD -maxcorK 0",
+    "maxcorK_20": "-r {a1} -c {dump} -k 23 -od @OD -maxcorK 20",
+    "many_threads": "-p {a1} {a2} -c {dump} -k 23 -od @OD -t 64",
+    "k_smaller_than_dump": "-p {a1} {a2} -c {dump} -k 21 -od @OD",
+    "k_5": "-r {a1} -c {dump} -k 5 -od @OD",
+    "dump_oddities": "-p {a1} {a2} -c {odd_dump} -k 23 -od @OD",
+    "empty_dump": "-r {a1} -c {empty} -k 23 -od @OD",
+    "fasta_interleaved": "-i {fa} -c {dump2} -k 23 -od @OD -t 2",
+}
+
+
+@pytest.mark.skipif(not os.path.exists(T.REF_BIN), reason="oracle/_ref/rcorrector not built")
+@pytest.mark.parametrize("case", sorted(SURFACE))
+def test_process_surface_matches_the_reference(double_exe, workdir, case):
+    import gzip
+
+    w = os.path.join(workdir + "_cpu", "surface")
+    os.makedirs(w, exist_ok=True)
+    f = _surface_files(w)
+    res = []
+    for tag, exe in (("ref", T.REF_BIN), ("ours", double_exe)):
+        od = os.path.join(w, "%s_%s" % (case, tag))
+        args = [a.replace("@OD", od) for a in SURFACE[case].format(**f).split()]
+        r = subprocess.run([exe] + args, capture_output=True, cwd=w)
+        files = {}
+        if os.path.isdir(od):
+            for name in sorted(os.listdir(od)):
+                p = os.path.join(od, name)
+                if os.path.isfile(p):
+                    data = open(p, "rb").read()
+                    files[name] = gzip.decompress(data) if name.endswith(".gz") and data else data
+        res.append((r.returncode, r.stderr.replace(od.encode(), b"@OD"), r.stdout, files))
+    assert res[0][0] == res[1][0], (res[0][1], res[1][1])
+    assert res[0][1] == res[1][1]
+    assert res[0][2] == res[1][2]
+    assert res[0][3] == res[1][3]
