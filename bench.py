@@ -352,8 +352,24 @@ def workload_config(a, extra=None):
     return c
 
 
+class StdoutToStderr:
+    """stdout carries the one JSON line only: until restore(), file descriptor 1 points at stderr, so whatever libraries
+    (NCCL prints a version banner on stdout when NCCL_DEBUG is set) or child processes write there lands on stderr."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ----------------------------------------------------------------------------- our arm
 def main_ours(a):
+    guard = StdoutToStderr()
     import torch
     import torch.distributed as dist
 
@@ -365,7 +381,6 @@ def main_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL_DEBUG=VERSION/WARN prints a banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -548,6 +563,7 @@ def main_ours(a):
             line["cpu_baseline"] = cpu_baseline(a, td)
         except Exception as e:  # keep the GPU numbers even if the CPU leg fails
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
+    guard.restore()
     print(json.dumps(line))
     return 0
 

@@ -55,3 +55,12 @@ def test_reference_arm_line(workdir, paired):
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["config"]["paired"] is paired
+
+
+def test_stdout_carries_only_the_json_line(workdir):
+    """bench.py points file descriptor 1 at stderr until its one JSON line is due (NCCL's version banner, child processes)."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; g = bench.StdoutToStderr(); os.system('echo from-a-child'); "
+            "print('from-python'); g.restore(); print('{\"ok\": 1}')" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
+    assert r.stdout == '{"ok": 1}\n'
+    assert "from-a-child" in r.stderr and "from-python" in r.stderr
