@@ -199,15 +199,32 @@ class LineReader {
     size_t beg_ = 0, end_ = 0;
 };
 
+// Output file.  Plain files are written through a file descriptor so that the formatted pieces of a batch can be written
+// by several threads at once (reserve() hands out the file offsets in output order, write_at() is a positional write);
+// gzip files (level 1, File.h:62-66) and stdout stay sequential streams.
 class Writer {
    public:
     bool open(const std::string& path, bool to_stdout) {  // File.h:38-75
         if (to_stdout) { f_ = stdout; own_ = false; return true; }
         if (ends_with_gz(path)) { g_ = gzopen(path.c_str(), "w1"); if (g_) gzbuffer(g_, 1 << 20); return g_ != nullptr; }
-        f_ = fopen(path.c_str(), "w");
-        return f_ != nullptr;
+        fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);  // what fopen(path, "w") does
+        pos_ = 0;
+        return fd_ >= 0;
+    }
+    bool can_scatter() const { return fd_ >= 0; }
+    // the next n bytes of the file belong to the caller; call in output order
+    uint64_t reserve(uint64_t n) { const uint64_t at = pos_; pos_ += n; return at; }
+    // positional write (any thread); false on an I/O error
+    bool write_at(uint64_t at, const char* p, size_t n) const {
+        while (n) {
+            const ssize_t w = ::pwrite(fd_, p, n, (off_t)at);
+            if (w <= 0) return false;
+            p += w; at += (uint64_t)w; n -= (size_t)w;
+        }
+        return true;
     }
     void write(const char* p, size_t n) {
+        if (fd_ >= 0) { write_at(reserve(n), p, n); return; }
         if (g_) gzwrite(g_, p, (unsigned)n);
         else fwrite(p, 1, n, f_);
     }
@@ -215,14 +232,18 @@ class Writer {
         if (g_) gzclose(g_);
         if (f_ && own_) fclose(f_);
         else if (f_) fflush(f_);
+        if (fd_ >= 0) ::close(fd_);
         g_ = nullptr;
         f_ = nullptr;
+        fd_ = -1;
     }
     ~Writer() { close(); }
 
    private:
     FILE* f_ = nullptr;
     gzFile g_ = nullptr;
+    int fd_ = -1;
+    uint64_t pos_ = 0;
     bool own_ = true;
 };
 

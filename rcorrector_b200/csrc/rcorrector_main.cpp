@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +62,14 @@ static double now_s() {
 }
 static const double g_t0 = now_s();
 static const bool g_timing = getenv("RCX_TIMING") != nullptr;
+// RCX_TIMING: seconds spent per pipeline stage, summed over the batches (the stages of different batches overlap)
+static std::atomic<long long> g_us_read{0}, g_us_correct{0}, g_us_format{0}, g_us_write{0};
+struct StageTimer {
+    std::atomic<long long>& acc;
+    double t0;
+    explicit StageTimer(std::atomic<long long>& a) : acc(a), t0(g_timing ? now_s() : 0) {}
+    ~StageTimer() { if (g_timing) acc += (long long)((now_s() - t0) * 1e6); }
+};
 static void tmark(const char* what) {
     if (g_timing) fprintf(stderr, "RCX_TIMING %8.3f s  %s\n", now_s() - g_t0, what);
 }
@@ -359,6 +368,13 @@ static bool read_record(LineReader& r, int type, HostBatch& b, Chunk& c, const s
 // Reads.h:360-421 OutputBatch for records [lo, hi) of the batch (stride/start select one mate of an interleaved batch)
 static void format_records(const HostBatch& b, const Chunk& c, int type, size_t lo, size_t hi, size_t stride, std::string& out) {
     out.clear();
+    if (lo < hi) {  // one allocation: ids + twice the bases + at most 64 bytes of tags and separators per record
+        const size_t nrec = (hi - lo + stride - 1) / stride;
+        const size_t bases = (size_t)(b.off[hi] - b.off[lo]);
+        const size_t idb = c.ext_ids ? nrec * (size_t)(c.id_len[lo] + 16) : (size_t)(c.id_off[hi] - c.id_off[lo]);
+        const size_t want = idb + 2 * bases + 64 * nrec;
+        if (out.capacity() < want) out.reserve(want + want / 8);
+    }
     char num[16];
     for (size_t r = lo; r < hi; r += stride) {
         if (c.ext_ids) out.append(c.id_ptr[r], c.id_len[r]);
@@ -651,6 +667,7 @@ int main(int argc, char* argv[]) {
         HostBatch b;
         Chunk c;
         bool more = true;  // the file may have further records after this batch
+        std::vector<std::string> pieces[2];  // formatted output per mate file and formatting thread (capacity kept across batches)
     };
     std::vector<BatchSet> sets(NSETS);
     std::future<void> sets_ready = std::async(std::launch::async, [&]() {
@@ -679,6 +696,7 @@ int main(int argc, char* argv[]) {
     double error_rate = 0.01;
     if (rcx_estimate_error_rate(gpus[0].ctx, dump.codes.data(), dump.rate_records, wk, &error_rate)) die_rcx("rcx_estimate_error_rate");
     fprintf(stderr, "Weak kmer threshold rate: %lf (estimated from %.3lf/1 of the chosen kmers)\n", error_rate, wk);
+    tmark("error rate estimated");
     if (getenv("RCX_DEBUG_SCALARS")) fprintf(stderr, "RCX_DEBUG error_rate=%.17g\n", error_rate);
     { std::vector<uint64_t>().swap(dump.codes); std::vector<int32_t>().swap(dump.counts); }
 
@@ -719,6 +737,7 @@ int main(int argc, char* argv[]) {
         bad_qual = (int)(char)(t2 < t1 ? t2 : t1);
     }
     fprintf(stderr, "Bad quality threshold is '%c'\n", bad_qual);
+    tmark("bad quality threshold found");
 
     rcx_params params;
     params.k = k;
@@ -752,6 +771,7 @@ int main(int argc, char* argv[]) {
         const int mode = (f.paired || f.interleaved) ? RCX_INTERLEAVED : RCX_SINGLE;
         // stage 1: fill a batch set; returns false when the file is exhausted and the set is empty
         auto produce = [&](BatchSet& st) -> bool {
+            StageTimer timer(g_us_read);
             HostBatch& b = st.b;
             Chunk& c = st.c;
             b.n = 0;
@@ -796,27 +816,59 @@ int main(int argc, char* argv[]) {
             st.more = more;
             return b.n > 0;
         };
-        // stage 3: format + write
+        // stage 3: format + write.  Formatting runs on `nfmt` threads into per-thread buffers that keep their capacity from
+        // batch to batch; plain files are then written by the same threads with positional writes at offsets reserved in
+        // batch order (the batches' writes themselves may overlap); gzip files and stdout are sequential streams, written in
+        // batch order.
         auto consume = [&, fi](BatchSet& st, std::shared_future<void> prev) {
             HostBatch& b = st.b;
             Chunk& c = st.c;
-            auto emit = [&](Writer& w, size_t start, size_t stride, bool first) {
-                const size_t recs = (b.n - start + stride - 1) / stride;
-                const int parts = (int)std::min<size_t>((size_t)nfmt, std::max<size_t>(1, recs / 4096));
-                std::vector<std::string> pieces(parts);
-                rcxio::parallel_for(parts, [&](int t) {
-                    const size_t lo = start + stride * (recs * t / parts), hi = start + stride * (recs * (t + 1) / parts);
-                    format_records(b, c, f.type, lo, std::min(hi, b.n), stride, pieces[t]);
-                });
-                if (first && prev.valid()) prev.wait();  // the previous batch is on disk
-                for (int t = 0; t < parts; ++t) w.write(pieces[t].data(), pieces[t].size());
+            struct Part { Writer* w; size_t start, stride, recs; int parts; std::vector<std::string>* pieces; };
+            Part part[2];
+            int nparts = 0;
+            auto plan = [&](Writer& w, size_t start, size_t stride, int which) {
+                Part& p = part[nparts++];
+                p.w = &w; p.start = start; p.stride = stride;
+                p.recs = b.n > start ? (b.n - start + stride - 1) / stride : 0;
+                p.parts = (int)std::min<size_t>((size_t)nfmt, std::max<size_t>(1, p.recs / 4096));
+                p.pieces = &st.pieces[which];
+                if ((int)p.pieces->size() < p.parts) p.pieces->resize(p.parts);
             };
             // ---- output in input order (main.cpp:485-516); -stdout interleaves the mates of a -p pair
             if (f.paired && !to_stdout) {
-                emit(out1[fi], 0, 2, true);
-                emit(out2[fi], 1, 2, false);
+                plan(out1[fi], 0, 2, 0);
+                plan(out2[fi], 1, 2, 1);
             } else {
-                emit(out1[fi], 0, 1, true);  // single, interleaved, or paired to stdout (mate1, mate2, mate1, ...)
+                plan(out1[fi], 0, 1, 0);  // single, interleaved, or paired to stdout (mate1, mate2, mate1, ...)
+            }
+            {
+                StageTimer timer(g_us_format);
+                for (int q = 0; q < nparts; ++q) {
+                    Part& p = part[q];
+                    rcxio::parallel_for(p.parts, [&](int t) {
+                        const size_t lo = p.start + p.stride * (p.recs * t / p.parts), hi = p.start + p.stride * (p.recs * (t + 1) / p.parts);
+                        format_records(b, c, f.type, lo, std::min(hi, b.n), p.stride, (*p.pieces)[t]);
+                    });
+                }
+            }
+            if (prev.valid()) prev.wait();  // the previous batch has reserved its place (plain files) / is written (streams)
+            StageTimer timer(g_us_write);
+            for (int q = 0; q < nparts; ++q) {
+                Part& p = part[q];
+                if (p.w->can_scatter()) {
+                    std::vector<uint64_t> at(p.parts);
+                    for (int t = 0; t < p.parts; ++t) at[t] = p.w->reserve((*p.pieces)[t].size());
+                    std::atomic<int> failed{0};
+                    rcxio::parallel_for(p.parts, [&](int t) {
+                        if (!p.w->write_at(at[t], (*p.pieces)[t].data(), (*p.pieces)[t].size())) failed = 1;
+                    });
+                    if (failed) {
+                        fprintf(stderr, "ERROR: Could not write the output of %s\n", f.path.c_str());
+                        exit(1);
+                    }
+                } else {
+                    for (int t = 0; t < p.parts; ++t) p.w->write((*p.pieces)[t].data(), (*p.pieces)[t].size());
+                }
             }
         };
         int cur = 0;
@@ -833,6 +885,7 @@ int main(int argc, char* argv[]) {
             }
             size_t odd_tail = 0;
             if (mode == RCX_INTERLEAVED && (b.n & 1)) odd_tail = 1;
+            const double t_correct0 = g_timing ? now_s() : 0;
             if (odd_tail) {
                 // correct the even prefix as pairs, the dangling record single-end
                 HostBatch t = b;
@@ -846,6 +899,7 @@ int main(int argc, char* argv[]) {
             } else {
                 correct_on_gpus(gpus, mode, b);
             }
+            if (g_timing) g_us_correct += (long long)((now_s() - t_correct0) * 1e6);
             for (size_t r = 0; r < b.n; ++r) {  // UpdateSummary, main.cpp:73-79
                 ++total_reads;
                 if (b.corr[r] > 0) total_corrections += (uint64_t)b.corr[r];
@@ -862,6 +916,10 @@ int main(int argc, char* argv[]) {
     for (auto& w : out2) w.close();
     for (auto& g : gpus) if (rcx_sync(g.ctx)) die_rcx("rcx_sync");
     fprintf(stderr, "Processed %" PRIu64 " reads\n\tCorrected %" PRIu64 " bases.\n", total_reads, total_corrections);
+    tmark("done");
+    if (g_timing)
+        fprintf(stderr, "RCX_TIMING stage sums: read %.3f s, correct %.3f s, format %.3f s, write %.3f s\n", g_us_read.load() * 1e-6,
+                g_us_correct.load() * 1e-6, g_us_format.load() * 1e-6, g_us_write.load() * 1e-6);
     fflush(stdout);
     fflush(stderr);
     _exit(0);  // everything is written and closed: skip the teardown of pinned buffers, mappings and CUDA contexts
