@@ -199,19 +199,48 @@ class LineReader {
     size_t beg_ = 0, end_ = 0;
 };
 
-// Output file.  Plain files are written through a file descriptor so that the formatted pieces of a batch can be written
-// by several threads at once (reserve() hands out the file offsets in output order, write_at() is a positional write);
-// gzip files (level 1, File.h:62-66) and stdout stay sequential streams.
+// One complete gzip member (RFC 1952) holding p[0..n) at `level`.  A gzip file is a concatenation of members, so the
+// pieces of a batch can be compressed by several threads and written back to back: gzread / gzgets (what the reference reads
+// its input with), gzip -d and every other reader see the concatenation of the pieces.
+inline bool gzip_member(const char* p, size_t n, int level, std::string& out) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, (uLong)n) + 64);
+    zs.next_out = (Bytef*)&out[0];
+    size_t out_left = out.size(), done = 0;
+    int rc = Z_OK;
+    do {
+        const size_t in_now = std::min<size_t>(n - done, (size_t)1 << 30);  // avail_in / avail_out are 32-bit
+        const size_t out_now = std::min<size_t>(out_left, (size_t)1 << 30);
+        zs.next_in = (Bytef*)(p + done);
+        zs.avail_in = (uInt)in_now;
+        zs.avail_out = (uInt)out_now;
+        rc = deflate(&zs, done + in_now == n ? Z_FINISH : Z_NO_FLUSH);
+        done += in_now - zs.avail_in;
+        out_left -= out_now - zs.avail_out;
+        if (rc == Z_STREAM_ERROR || (rc == Z_BUF_ERROR && out_left == 0)) { deflateEnd(&zs); return false; }
+    } while (rc != Z_STREAM_END);
+    out.resize(out.size() - out_left);
+    deflateEnd(&zs);
+    return true;
+}
+
+// Output file.  Files are written through a file descriptor so that the pieces of a batch can be written by several
+// threads at once: reserve() hands out the file offsets in output order, write_at() is a positional write.  For *.gz
+// outputs (File.h:51-66: a path ending in "gz" is written through zlib at level 1) the pieces are gzip members, compressed
+// by the threads that formatted them.  stdout stays a sequential stream.
 class Writer {
    public:
     bool open(const std::string& path, bool to_stdout) {  // File.h:38-75
-        if (to_stdout) { f_ = stdout; own_ = false; return true; }
-        if (ends_with_gz(path)) { g_ = gzopen(path.c_str(), "w1"); if (g_) gzbuffer(g_, 1 << 20); return g_ != nullptr; }
-        fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);  // what fopen(path, "w") does
+        if (to_stdout) { f_ = stdout; return true; }
+        gz_ = ends_with_gz(path);
+        fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);  // what fopen(path, "w") / gzopen(path, "w1") create
         pos_ = 0;
         return fd_ >= 0;
     }
     bool can_scatter() const { return fd_ >= 0; }
+    bool gz() const { return gz_; }  // pieces handed to reserve() / write_at() must be gzip members (gzip_member(), level 1)
     // the next n bytes of the file belong to the caller; call in output order
     uint64_t reserve(uint64_t n) { const uint64_t at = pos_; pos_ += n; return at; }
     // positional write (any thread); false on an I/O error
@@ -223,28 +252,35 @@ class Writer {
         }
         return true;
     }
+    // sequential write of uncompressed bytes
     void write(const char* p, size_t n) {
-        if (fd_ >= 0) { write_at(reserve(n), p, n); return; }
-        if (g_) gzwrite(g_, p, (unsigned)n);
-        else fwrite(p, 1, n, f_);
+        if (fd_ < 0) { fwrite(p, 1, n, f_); return; }
+        if (gz_) {
+            std::string z;
+            if (n && gzip_member(p, n, 1, z)) write_at(reserve(z.size()), z.data(), z.size());
+            return;
+        }
+        write_at(reserve(n), p, n);
     }
     void close() {
-        if (g_) gzclose(g_);
-        if (f_ && own_) fclose(f_);
-        else if (f_) fflush(f_);
-        if (fd_ >= 0) ::close(fd_);
-        g_ = nullptr;
+        if (f_) fflush(f_);
+        if (fd_ >= 0) {
+            if (gz_ && pos_ == 0) {  // gzopen + gzclose without data leave an empty member, not an empty file
+                std::string z;
+                if (gzip_member("", 0, 1, z)) write_at(reserve(z.size()), z.data(), z.size());
+            }
+            ::close(fd_);
+        }
         f_ = nullptr;
         fd_ = -1;
     }
     ~Writer() { close(); }
 
    private:
-    FILE* f_ = nullptr;
-    gzFile g_ = nullptr;
+    FILE* f_ = nullptr;  // stdout
     int fd_ = -1;
+    bool gz_ = false;
     uint64_t pos_ = 0;
-    bool own_ = true;
 };
 
 // One chunk of records of ONE input file, in the layout the C ABI takes.

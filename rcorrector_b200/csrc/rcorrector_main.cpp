@@ -654,53 +654,10 @@ int main(int argc, char* argv[]) {
         }
     }
 
-    // ---- GPUs and table
-    // CUDA context creation and the pinned batch buffers overlap the parsing of the dump
-    std::vector<Gpu> gpus(ngpu);
-    std::future<void> gpus_ready = std::async(std::launch::async, [&]() {
-        for (int g = 0; g < ngpu; ++g)
-            if (rcx_create(g, &gpus[g].ctx)) die_rcx("rcx_create");
-    });
-    // the three pinned batch buffers are allocated while the dump is parsed (pinning memory is slow)
-    const int NSETS = 3;
-    struct BatchSet {
-        HostBatch b;
-        Chunk c;
-        bool more = true;  // the file may have further records after this batch
-        std::vector<std::string> pieces[2];  // formatted output per mate file and formatting thread (capacity kept across batches)
-    };
-    std::vector<BatchSet> sets(NSETS);
-    std::future<void> sets_ready = std::async(std::launch::async, [&]() {
-        gpus_ready.wait();
-        const size_t cap_bases = batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u;
-        for (auto& st : sets) st.b.alloc(batch_reads, cap_bases);
-    });
-    Dump dump;
-    load_dump(dump_path, k, dump, threads);
-    tmark("dump parsed");
-    gpus_ready.wait();
-    tmark("CUDA contexts ready");
-    {
-        std::vector<std::thread> th;
-        std::vector<int> rc(ngpu, 0);
-        for (int g = 0; g < ngpu; ++g)
-            th.emplace_back([&, g]() { rc[g] = rcx_table_build(gpus[g].ctx, k, dump.codes.data(), dump.counts.data(), dump.codes.size(), 0); });
-        for (auto& t : th) t.join();
-        for (int g = 0; g < ngpu; ++g)
-            if (rc[g]) { fprintf(stderr, "rcx_table_build failed on GPU %d\n", g); exit(1); }
-    }
-    fprintf(stderr, "Stored %d kmers\n", (int)dump.stored);
-    tmark("table built");
-
-    // ---- ERROR_RATE (main.cpp:310-358)
-    double error_rate = 0.01;
-    if (rcx_estimate_error_rate(gpus[0].ctx, dump.codes.data(), dump.rate_records, wk, &error_rate)) die_rcx("rcx_estimate_error_rate");
-    fprintf(stderr, "Weak kmer threshold rate: %lf (estimated from %.3lf/1 of the chosen kmers)\n", error_rate, wk);
-    tmark("error rate estimated");
-    if (getenv("RCX_DEBUG_SCALARS")) fprintf(stderr, "RCX_DEBUG error_rate=%.17g\n", error_rate);
-    { std::vector<uint64_t>().swap(dump.codes); std::vector<int32_t>().swap(dump.counts); }
-
-    // ---- badQualityThreshold (main.cpp:88-128): first 1e6 records of the first Reads object
+    // ---- badQualityThreshold (main.cpp:88-128): first 1e6 records of the first Reads object.  Independent of the table, so the
+    // pass over the reads (a serial inflate for *.gz input) runs while the dump is parsed and the table is built; its line is
+    // printed where the reference prints it.
+    std::future<int> bad_qual_future = std::async(std::launch::async, [&files]() -> int {
     int bad_qual = 0;
     if (!files.empty() && files[0].type == 1) {
         int first[300], last[300];
@@ -736,6 +693,57 @@ int main(int argc, char* argv[]) {
         t2 = i;
         bad_qual = (int)(char)(t2 < t1 ? t2 : t1);
     }
+    return bad_qual;
+    });
+
+    // ---- GPUs and table
+    // CUDA context creation and the pinned batch buffers overlap the parsing of the dump
+    std::vector<Gpu> gpus(ngpu);
+    std::future<void> gpus_ready = std::async(std::launch::async, [&]() {
+        for (int g = 0; g < ngpu; ++g)
+            if (rcx_create(g, &gpus[g].ctx)) die_rcx("rcx_create");
+    });
+    // the three pinned batch buffers are allocated while the dump is parsed (pinning memory is slow)
+    const int NSETS = 3;
+    struct BatchSet {
+        HostBatch b;
+        Chunk c;
+        bool more = true;  // the file may have further records after this batch
+        std::vector<std::string> pieces[2];   // formatted output per mate file and formatting thread (capacity kept across batches)
+        std::vector<std::string> zpieces[2];  // the same as gzip members, for *.gz outputs
+    };
+    std::vector<BatchSet> sets(NSETS);
+    std::future<void> sets_ready = std::async(std::launch::async, [&]() {
+        gpus_ready.wait();
+        const size_t cap_bases = batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u;
+        for (auto& st : sets) st.b.alloc(batch_reads, cap_bases);
+    });
+    Dump dump;
+    load_dump(dump_path, k, dump, threads);
+    tmark("dump parsed");
+    gpus_ready.wait();
+    tmark("CUDA contexts ready");
+    {
+        std::vector<std::thread> th;
+        std::vector<int> rc(ngpu, 0);
+        for (int g = 0; g < ngpu; ++g)
+            th.emplace_back([&, g]() { rc[g] = rcx_table_build(gpus[g].ctx, k, dump.codes.data(), dump.counts.data(), dump.codes.size(), 0); });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < ngpu; ++g)
+            if (rc[g]) { fprintf(stderr, "rcx_table_build failed on GPU %d\n", g); exit(1); }
+    }
+    fprintf(stderr, "Stored %d kmers\n", (int)dump.stored);
+    tmark("table built");
+
+    // ---- ERROR_RATE (main.cpp:310-358)
+    double error_rate = 0.01;
+    if (rcx_estimate_error_rate(gpus[0].ctx, dump.codes.data(), dump.rate_records, wk, &error_rate)) die_rcx("rcx_estimate_error_rate");
+    fprintf(stderr, "Weak kmer threshold rate: %lf (estimated from %.3lf/1 of the chosen kmers)\n", error_rate, wk);
+    tmark("error rate estimated");
+    if (getenv("RCX_DEBUG_SCALARS")) fprintf(stderr, "RCX_DEBUG error_rate=%.17g\n", error_rate);
+    { std::vector<uint64_t>().swap(dump.codes); std::vector<int32_t>().swap(dump.counts); }
+
+    const int bad_qual = bad_qual_future.get();
     fprintf(stderr, "Bad quality threshold is '%c'\n", bad_qual);
     tmark("bad quality threshold found");
 
@@ -770,6 +778,7 @@ int main(int argc, char* argv[]) {
         }
         const int mode = (f.paired || f.interleaved) ? RCX_INTERLEAVED : RCX_SINGLE;
         // stage 1: fill a batch set; returns false when the file is exhausted and the set is empty
+        std::atomic<bool> unpaired{false};  // set by stage 1 when one file of a -p pair ends before the other
         auto produce = [&](BatchSet& st) -> bool {
             StageTimer timer(g_us_read);
             HostBatch& b = st.b;
@@ -797,8 +806,17 @@ int main(int argc, char* argv[]) {
                 if (!read_record(r1, f.type, b, c, f.path)) { more = false; break; }
                 if (f.paired) {
                     if (!read_record(r2, f.type, b, c, f.mate_path)) {
-                        fprintf(stderr, "ERROR: The files are not paired!\n");  // main.cpp:463-466
-                        exit(1);
+                        // main.cpp:463-466.  The error is raised by the main loop once the batches before it are written
+                        // (the reference, too, has written its earlier batches by then); the dangling mate is dropped.
+                        unpaired = true;
+                        b.n -= 1;
+                        b.bases = b.off[b.n];
+                        c.id_off.pop_back();
+                        c.ids.resize(c.id_off.back());
+                        if (c.qual_text_off.size() > b.n + 1) { c.qual_text_off.resize(b.n + 1); c.qual_text.resize(c.qual_text_off.back()); }
+                        c.n = b.n;
+                        more = false;
+                        break;
                     }
                 } else if (f.interleaved) {
                     if (!read_record(r1, f.type, b, c, f.path)) {
@@ -811,7 +829,7 @@ int main(int argc, char* argv[]) {
             }
             if (f.paired && !more) {
                 const char* p; size_t n; bool nl;
-                if (r2.getline(p, n, nl)) { fprintf(stderr, "ERROR: The files are not paired!\n"); exit(1); }
+                if (!unpaired && r2.getline(p, n, nl)) unpaired = true;  // the second file is the longer one
             }
             st.more = more;
             return b.n > 0;
@@ -823,7 +841,7 @@ int main(int argc, char* argv[]) {
         auto consume = [&, fi](BatchSet& st, std::shared_future<void> prev) {
             HostBatch& b = st.b;
             Chunk& c = st.c;
-            struct Part { Writer* w; size_t start, stride, recs; int parts; std::vector<std::string>* pieces; };
+            struct Part { Writer* w; size_t start, stride, recs; int parts; std::vector<std::string>* pieces; std::vector<std::string>* out; };
             Part part[2];
             int nparts = 0;
             auto plan = [&](Writer& w, size_t start, size_t stride, int which) {
@@ -832,7 +850,9 @@ int main(int argc, char* argv[]) {
                 p.recs = b.n > start ? (b.n - start + stride - 1) / stride : 0;
                 p.parts = (int)std::min<size_t>((size_t)nfmt, std::max<size_t>(1, p.recs / 4096));
                 p.pieces = &st.pieces[which];
+                p.out = w.gz() ? &st.zpieces[which] : p.pieces;  // what goes to the file
                 if ((int)p.pieces->size() < p.parts) p.pieces->resize(p.parts);
+                if ((int)p.out->size() < p.parts) p.out->resize(p.parts);
             };
             // ---- output in input order (main.cpp:485-516); -stdout interleaves the mates of a -p pair
             if (f.paired && !to_stdout) {
@@ -848,6 +868,13 @@ int main(int argc, char* argv[]) {
                     rcxio::parallel_for(p.parts, [&](int t) {
                         const size_t lo = p.start + p.stride * (p.recs * t / p.parts), hi = p.start + p.stride * (p.recs * (t + 1) / p.parts);
                         format_records(b, c, f.type, lo, std::min(hi, b.n), p.stride, (*p.pieces)[t]);
+                        if (p.w->gz()) {  // one gzip member per piece, level 1 like the reference's gzopen(.., "w1")
+                            if ((*p.pieces)[t].empty()) (*p.out)[t].clear();
+                            else if (!rcxio::gzip_member((*p.pieces)[t].data(), (*p.pieces)[t].size(), 1, (*p.out)[t])) {
+                                fprintf(stderr, "ERROR: Could not compress the output of %s\n", f.path.c_str());
+                                exit(1);
+                            }
+                        }
                     });
                 }
             }
@@ -857,10 +884,10 @@ int main(int argc, char* argv[]) {
                 Part& p = part[q];
                 if (p.w->can_scatter()) {
                     std::vector<uint64_t> at(p.parts);
-                    for (int t = 0; t < p.parts; ++t) at[t] = p.w->reserve((*p.pieces)[t].size());
+                    for (int t = 0; t < p.parts; ++t) at[t] = p.w->reserve((*p.out)[t].size());
                     std::atomic<int> failed{0};
                     rcxio::parallel_for(p.parts, [&](int t) {
-                        if (!p.w->write_at(at[t], (*p.pieces)[t].data(), (*p.pieces)[t].size())) failed = 1;
+                        if (!p.w->write_at(at[t], (*p.out)[t].data(), (*p.out)[t].size())) failed = 1;
                     });
                     if (failed) {
                         fprintf(stderr, "ERROR: Could not write the output of %s\n", f.path.c_str());
@@ -911,6 +938,10 @@ int main(int argc, char* argv[]) {
             cur = nxt;
         }
         if (last_write.valid()) last_write.wait();  // this file's sources go out of scope
+        if (unpaired) {
+            fprintf(stderr, "ERROR: The files are not paired!\n");  // main.cpp:463-466
+            exit(1);
+        }
     }
     for (auto& w : out1) w.close();
     for (auto& w : out2) w.close();
