@@ -13,10 +13,13 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -117,9 +120,14 @@ inline std::string output_path(const std::string& od, const std::string& in, int
     return s;
 }
 
-// Block reader over a plain or gzip file that hands out lines (without the '\n').
+// Block reader over a plain or gzip file that hands out lines (without the '\n').  A gzip file is inflated by a thread of
+// its own, a few blocks ahead of the consumer: inflating is the slowest step of reading *.gz input (and cannot be split
+// inside one stream), so it should at least overlap the parsing — and the two files of a -p pair inflate side by side.
 class LineReader {
    public:
+    LineReader() = default;
+    LineReader(const LineReader&) = delete;
+    LineReader& operator=(const LineReader&) = delete;
     // serial reading of an already mapped file from byte `pos` (the parallel reader hands irregular input over here)
     void open_mem(const char* data, size_t size, size_t pos) {
         close();
@@ -134,13 +142,23 @@ class LineReader {
         gz_ = ends_with_gz(path);
         if (gz_) {
             g_ = gzopen(path.c_str(), "r");
-            if (g_) gzbuffer(g_, 1 << 20);
-            return g_ != nullptr;
+            if (!g_) return false;
+            gzbuffer(g_, 1 << 20);
+            inflater_ = std::thread([this]() { inflate_ahead(); });
+            return true;
         }
         f_ = fopen(path.c_str(), "r");
         return f_ != nullptr;
     }
     void close() {
+        if (inflater_.joinable()) {
+            { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+            cv_.notify_all();
+            inflater_.join();
+        }
+        blocks_.clear();
+        stop_ = false;
+        inflate_done_ = false;
         if (f_) fclose(f_);
         if (g_) gzclose(g_);
         f_ = nullptr;
@@ -148,6 +166,7 @@ class LineReader {
         mem_ = nullptr;
         beg_ = end_ = 0;
         eof_ = false;
+        gz_ = false;
     }
     ~LineReader() { close(); }
     // returns false at end of file; `had_nl` tells whether the line ended with '\n'
@@ -178,16 +197,44 @@ class LineReader {
     }
 
    private:
+    static constexpr size_t kBlock = 4u << 20;  // inflated bytes per hand-over
+    static constexpr size_t kAhead = 8;         // blocks the inflater may be ahead
+    void inflate_ahead() {  // the gzip file's own thread
+        for (;;) {
+            std::vector<char> blk(kBlock);
+            const int got = gzread(g_, blk.data(), (unsigned)blk.size());
+            std::unique_lock<std::mutex> lk(mu_);
+            if (got <= 0) { inflate_done_ = true; cv_.notify_all(); return; }
+            blk.resize((size_t)got);
+            cv_.wait(lk, [this]() { return stop_ || blocks_.size() < kAhead; });
+            if (stop_) return;
+            blocks_.push_back(std::move(blk));
+            cv_.notify_all();
+        }
+    }
     void fill() {
         if (beg_ > 0) {
             memmove(buf_.data(), buf_.data() + beg_, end_ - beg_);
             end_ -= beg_;
             beg_ = 0;
         }
+        if (gz_) {
+            std::vector<char> blk;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this]() { return !blocks_.empty() || inflate_done_; });
+                if (blocks_.empty()) { eof_ = true; return; }
+                blk = std::move(blocks_.front());
+                blocks_.pop_front();
+            }
+            cv_.notify_all();
+            if (buf_.size() - end_ < blk.size()) buf_.resize(end_ + blk.size() + (8u << 20));
+            memcpy(buf_.data() + end_, blk.data(), blk.size());
+            end_ += blk.size();
+            return;
+        }
         if (buf_.size() - end_ < (1u << 20)) buf_.resize(buf_.size() + (8u << 20));
-        long got;
-        if (gz_) got = gzread(g_, buf_.data() + end_, (unsigned)(buf_.size() - end_));
-        else got = (long)fread(buf_.data() + end_, 1, buf_.size() - end_, f_);
+        const long got = (long)fread(buf_.data() + end_, 1, buf_.size() - end_, f_);
         if (got <= 0) eof_ = true;
         else end_ += (size_t)got;
     }
@@ -197,6 +244,12 @@ class LineReader {
     bool gz_ = false, eof_ = false;
     std::vector<char> buf_ = std::vector<char>(8u << 20);
     size_t beg_ = 0, end_ = 0;
+    // gzip: blocks inflated ahead by inflater_
+    std::thread inflater_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::vector<char>> blocks_;
+    bool stop_ = false, inflate_done_ = false;
 };
 
 // One complete gzip member (RFC 1952) holding p[0..n) at `level`.  A gzip file is a concatenation of members, so the
