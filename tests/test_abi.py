@@ -64,3 +64,26 @@ def test_host_binary_cli_surface():
     assert r.returncode == 0 and b"Unknown argument: -bogus" in r.stderr
     r = subprocess.run([exe, "-c", "/nonexistent/dump", "-r", "x.fq"], capture_output=True)
     assert r.returncode == 1 and b"Could not open file /nonexistent/dump" in r.stderr
+
+
+def test_product_binary_fails_loudly_without_gpu(workdir):
+    """The shipped binary links librcx.so only (never the oracle or the test double): on a machine without a CUDA device a
+    valid command line ends with exit code 1 and the library's message, not with output files from some CPU path."""
+    import subprocess
+
+    import torch
+
+    import rcx_testlib as T
+
+    exe = os.path.join(ROOT, "rcorrector_b200", "bin", "rcorrector")
+    if not os.path.exists(exe):
+        pytest.skip("bin/rcorrector not built")
+    out = os.popen("ldd %s 2>/dev/null" % exe).read()
+    assert "librcx.so" in out and "oracle" not in out
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible: the failure path is not reachable")
+    meta, fq, dump, expected = T.load_golden("single_repeat_n", workdir)
+    od = os.path.join(workdir, "nogpu_out")
+    r = subprocess.run([exe, "-r", fq[0], "-c", dump, "-k", str(meta["k"]), "-od", od], capture_output=True)
+    assert r.returncode == 1 and b"no CUDA device" in r.stderr
+    assert all(os.path.getsize(os.path.join(od, f)) == 0 for f in os.listdir(od))
