@@ -288,7 +288,7 @@ class Writer {
     bool open(const std::string& path, bool to_stdout) {  // File.h:38-75
         if (to_stdout) { f_ = stdout; return true; }
         gz_ = ends_with_gz(path);
-        fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);  // what fopen(path, "w") / gzopen(path, "w1") create
+        fd_ = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);  // the file fopen(path, "w") / gzopen(path, "w1") create (mapped for writing)
         pos_ = 0;
         return fd_ >= 0;
     }
@@ -296,6 +296,18 @@ class Writer {
     bool gz() const { return gz_; }  // pieces handed to reserve() / write_at() must be gzip members (gzip_member(), level 1)
     // the next n bytes of the file belong to the caller; call in output order
     uint64_t reserve(uint64_t n) { const uint64_t at = pos_; pos_ += n; return at; }
+    // Grow the file to cover everything reserved so far and map [at, at + n) of it for the writing threads (memcpy into
+    // the mapping takes its page faults on the thread that copies; positional writes to ONE file serialise on the inode
+    // lock).  Returns nullptr when the file cannot be grown or mapped (the caller falls back to write_at()).
+    char* map(uint64_t at, uint64_t n, void*& base, size_t& len) const {
+        if (n == 0 || fd_ < 0 || ftruncate(fd_, (off_t)pos_) != 0) return nullptr;
+        const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE), lo = at & ~(page - 1);
+        len = (size_t)(at + n - lo);
+        base = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, (off_t)lo);
+        if (base == MAP_FAILED) { base = nullptr; return nullptr; }
+        return (char*)base + (at - lo);
+    }
+    static void unmap(void* base, size_t len) { if (base) munmap(base, len); }
     // positional write (any thread); false on an I/O error
     bool write_at(uint64_t at, const char* p, size_t n) const {
         while (n) {

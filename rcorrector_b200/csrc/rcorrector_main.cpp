@@ -884,11 +884,17 @@ int main(int argc, char* argv[]) {
                 Part& p = part[q];
                 if (p.w->can_scatter()) {
                     std::vector<uint64_t> at(p.parts);
-                    for (int t = 0; t < p.parts; ++t) at[t] = p.w->reserve((*p.out)[t].size());
+                    uint64_t total = 0;
+                    for (int t = 0; t < p.parts; ++t) { at[t] = p.w->reserve((*p.out)[t].size()); total += (*p.out)[t].size(); }
                     std::atomic<int> failed{0};
+                    void* mbase = nullptr;
+                    size_t mlen = 0;
+                    char* dst = (p.parts > 1 && !getenv("RCX_NO_MMAP_OUT")) ? p.w->map(at[0], total, mbase, mlen) : nullptr;
                     rcxio::parallel_for(p.parts, [&](int t) {
-                        if (!p.w->write_at(at[t], (*p.out)[t].data(), (*p.out)[t].size())) failed = 1;
+                        if (dst) memcpy(dst + (at[t] - at[0]), (*p.out)[t].data(), (*p.out)[t].size());
+                        else if (!p.w->write_at(at[t], (*p.out)[t].data(), (*p.out)[t].size())) failed = 1;
                     });
+                    Writer::unmap(mbase, mlen);
                     if (failed) {
                         fprintf(stderr, "ERROR: Could not write the output of %s\n", f.path.c_str());
                         exit(1);
