@@ -19,13 +19,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import rcx_testlib as T  # noqa: E402
 
 
+LONG = False
+LONG_LENGTHS = [256, 300, 400, 512, 640, 800, 1000, 1023]  # the reference's MAX_READ_LENGTH is 1024 including the NUL
+
+
 def one_case(rng, wd, idx):
     k = rng.choice([11, 13, 15, 17, 19, 21, 23, 23, 23, 25, 27, 29, 31, 31, 32])
     paired = rng.random() < 0.5
-    length = rng.choice([k + 5, 50, 75, 100, 100, 125, 150, 150, 200, 250])
+    length = rng.choice(LONG_LENGTHS if LONG else [k + 5, 50, 75, 100, 100, 125, 150, 150, 200, 250])
     if length < k + 2:
         length = k + 2
-    kw = dict(seed=rng.randrange(1, 1 << 30), ntx=rng.choice([3, 8, 20, 40]), reads=rng.choice([300, 800, 2000]), len=length,
+    kw = dict(seed=rng.randrange(1, 1 << 30), ntx=rng.choice([3, 8, 20, 40]), reads=rng.choice([100, 300] if LONG else [300, 800, 2000]), len=length,
               err=rng.choice([0.0, 0.003, 0.01, 0.02, 0.04, 0.08]), nrate=rng.choice([0.0, 0.002, 0.01, 0.03]),
               paralog=rng.choice([0.0, 0.0, 0.3, 0.6]), repeat=rng.choice([0.0, 0.0, 0.3, 0.6]), polya=rng.choice([0.0, 0.3, 0.9]),
               short=rng.choice([0.0, 0.02, 0.2]), sigma=rng.choice([0.5, 2.0, 3.0]), txmin=max(length, 300))
@@ -70,7 +74,10 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--keep", default=None)
+    ap.add_argument("--long", action="store_true", help="reads of 256..1023 bases (the warp-per-read kernels' range)")
     a = ap.parse_args()
+    global LONG
+    LONG = a.long
     if not os.path.exists(T.REF_BIN):
         sys.exit("oracle/_ref/rcorrector not built (make -C oracle ref)")
     rng = random.Random(a.seed)
