@@ -20,7 +20,7 @@ import rcx_testlib as T  # noqa: E402
 
 
 LONG = False
-LONG_LENGTHS = [256, 300, 400, 512, 640, 800, 1000, 1023]  # the reference's MAX_READ_LENGTH is 1024 including the NUL
+LONG_LENGTHS = [256, 300, 400, 512, 640, 800, 1000]  # rcx_synth generates up to 1000 bases (the reference allows 1023)
 
 
 def one_case(rng, wd, idx):
