@@ -532,12 +532,27 @@ static bool fill_batch_fast(Source& A, Source* B2, bool interleaved, HostBatch& 
     return true;
 }
 
+// The CUDA path counts the reads it cannot reproduce exactly (include/rcx.h: rcx_stats.unsupported — a third pass of the
+// correction loop, a k-mer count of 2^29 or more, more substitutions on one search path than its edit row holds).  None
+// has been seen on real or synthetic data; if one ever is, the run stops here instead of writing output that may differ from
+// the reference's.
+static void check_supported(rcx_ctx* ctx) {
+    rcx_stats st;
+    if (rcx_get_stats(ctx, &st)) die_rcx("rcx_get_stats");
+    if (st.unsupported) {
+        fprintf(stderr, "ERROR: %llu reads of this batch need a case the GPU path does not reproduce (see rcx_stats.unsupported)\n",
+                (unsigned long long)st.unsupported);
+        exit(1);
+    }
+}
+
 static void correct_on_gpus(std::vector<Gpu>& gpus, int mode, HostBatch& b) {
     const size_t n = b.n;
     if (n == 0) return;
     const size_t G = gpus.size();
     if (G == 1) {
         if (rcx_correct_batch(gpus[0].ctx, mode, (int64_t)n, b.seq, b.qual, b.off, b.seq, b.corr, b.l, b.m, b.h)) die_rcx("rcx_correct_batch");
+        check_supported(gpus[0].ctx);
         return;
     }
     // contiguous record-index shards, both mates of a pair on the same GPU
@@ -562,6 +577,7 @@ static void correct_on_gpus(std::vector<Gpu>& gpus, int mode, HostBatch& b) {
             fprintf(stderr, "rcx_correct_batch: %s\n", e.c_str());
             exit(1);
         }
+    for (auto& g : gpus) check_supported(g.ctx);
 }
 
 int main(int argc, char* argv[]) {

@@ -82,6 +82,12 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
 }
 
 extern "C" int rcx_sync(rcx_ctx*) { return RCX_OK; }
+extern "C" int rcx_get_stats(rcx_ctx* c, rcx_stats* out) {
+    if (!c || !out) return RCX_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (const char* e = getenv("RCX_DOUBLE_UNSUPPORTED")) out->unsupported = (uint64_t)atoll(e);  // tests: the binary must stop
+    return RCX_OK;
+}
 extern "C" void* rcx_host_alloc(uint64_t bytes) { return malloc(bytes ? bytes : 1); }
 extern "C" void rcx_host_free(void* p) { free(p); }
 

@@ -274,3 +274,13 @@ def test_gz_output_is_written_as_parallel_members(double_exe, workdir):
     assert r.returncode == 0, r.stderr.decode()
     data = open(os.path.join(od, "none.cor.fq.gz"), "rb").read()
     assert len(data) > 0 and isinstance(gzip.decompress(data), bytes)
+
+
+def test_binary_stops_on_reads_the_gpu_path_does_not_reproduce(double_exe, workdir):
+    """rcx_stats.unsupported > 0 after a batch: the binary exits 1 with a message instead of writing output that may differ."""
+    meta, fq, dump, expected = T.load_golden("single_repeat_n", workdir + "_cpu")
+    od = os.path.join(workdir + "_cpu", "unsupported")
+    r = subprocess.run([double_exe, "-r", fq[0], "-c", dump, "-k", str(meta["k"]), "-od", od] + meta["extra"], capture_output=True,
+                       env=dict(os.environ, RCX_DOUBLE_UNSUPPORTED="3"))
+    assert r.returncode == 1 and b"3 reads of this batch need a case the GPU path does not reproduce" in r.stderr
+    assert os.path.getsize(os.path.join(od, meta["outputs"][0][:-3])) == 0
