@@ -51,6 +51,11 @@ def test_dump_parsers(workdir):
     G.test_dump_parsers_agree(workdir + "_cpu")
 
 
+def test_perl_driver_stage3(workdir):
+    """run_rcorrector.pl -stage 3 (copied from /root/reference at test time, where that exists) drives the binary unchanged."""
+    G.test_perl_driver_stage3(workdir + "_cpu")
+
+
 @pytest.mark.parametrize("gpus,batch,threads", [(2, 64, 1), (3, 50, 5), (5, 1 << 20, 2), (8, 2, 3)])
 def test_batch_sharding_over_contexts(double_exe, workdir, gpus, batch, threads):
     """-gpus N: every pipeline batch is cut into contiguous record-range shards with both mates of a pair on one context
