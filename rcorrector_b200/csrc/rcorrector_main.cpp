@@ -731,7 +731,10 @@ int main(int argc, char* argv[]) {
     std::vector<BatchSet> sets(NSETS);
     std::future<void> sets_ready = std::async(std::launch::async, [&]() {
         gpus_ready.wait();
-        const size_t cap_bases = batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u;
+        // bases per batch: 160 per record (records of 100-150 bases fill the record budget first), at most 3 GB, and never
+        // less than a few maximal reads (tiny -batch values are used by tests)
+        size_t cap_bases = batch_reads * 160 < (size_t)3000000000u ? batch_reads * 160 : (size_t)3000000000u;
+        if (cap_bases < (size_t)16 * (RCX_MAX_READ_LENGTH + 1)) cap_bases = (size_t)16 * (RCX_MAX_READ_LENGTH + 1);
         for (auto& st : sets) st.b.alloc(batch_reads, cap_bases);
     });
     Dump dump;

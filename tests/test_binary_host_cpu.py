@@ -289,3 +289,24 @@ def test_binary_stops_on_reads_the_gpu_path_does_not_reproduce(double_exe, workd
                        env=dict(os.environ, RCX_DOUBLE_UNSUPPORTED="3"))
     assert r.returncode == 1 and b"3 reads of this batch need a case the GPU path does not reproduce" in r.stderr
     assert os.path.getsize(os.path.join(od, meta["outputs"][0][:-3])) == 0
+
+
+@pytest.mark.parametrize("batch", [2, 4, 8, 16])
+def test_tiny_batches_with_long_reads(double_exe, workdir, batch):
+    """-batch below 16 with reads of up to 1 022 bases (found by tools/fuzz_binary_vs_ref.py: the batch buffers were sized from
+    the record budget alone)."""
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir + "_cpu")
+    w = os.path.join(workdir + "_cpu", "tiny_%d" % batch)
+    os.makedirs(w, exist_ok=True)
+    lines = open(fq[0], "rb").read().split(b"\n")
+    long_seq = (lines[1] * 12)[:1022]
+    lines[5], lines[7] = long_seq, b"I" * len(long_seq)
+    src = os.path.join(w, "x.fq")
+    open(src, "wb").write(b"\n".join(lines[:4 * 40]) + b"\n")
+    outs = []
+    for tag, b in (("tiny", str(batch)), ("big", "65536")):
+        od = os.path.join(w, "o_" + tag)
+        r = subprocess.run([double_exe, "-r", src, "-c", dump, "-k", str(meta["k"]), "-od", od, "-batch", b, "-t", "2"], capture_output=True)
+        assert r.returncode == 0 and b"Processed 40 reads" in r.stderr, r.stderr.decode()
+        outs.append(open(os.path.join(od, "x.cor.fq"), "rb").read())
+    assert outs[0] == outs[1] and outs[0].count(b"\n") == 160
