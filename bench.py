@@ -357,14 +357,25 @@ class StdoutToStderr:
     (NCCL prints a version banner on stdout when NCCL_DEBUG is set) or child processes write there lands on stderr."""
 
     def __init__(self):
-        sys.stdout.flush()
-        self.saved = os.dup(1)
-        os.dup2(2, 1)
+        self.saved = None
+        try:
+            sys.stdout.flush()
+            saved = os.dup(1)
+            try:
+                os.dup2(2, 1)
+                self.saved = saved
+            except OSError:
+                os.close(saved)
+        except OSError:
+            pass  # no usable stderr: leave stdout alone
 
     def restore(self):
+        if self.saved is None:
+            return
         sys.stdout.flush()
         os.dup2(self.saved, 1)
         os.close(self.saved)
+        self.saved = None
 
 
 # ----------------------------------------------------------------------------- our arm
