@@ -470,6 +470,13 @@ static bool fill_batch_fast(Source& A, Source* B2, bool interleaved, HostBatch& 
             na = nb = m;
         }
     }
+    if (!B2 && interleaved && (na & 1)) {
+        // mates must stay in one batch: an odd count is only right when these records end the file exactly (a dangling
+        // record, corrected single-end); with bytes left over (a last record without its final newline) the pair is
+        // split between the readers otherwise -- leave the odd record to the serial reader as well
+        const size_t end = A.reg_lo + (size_t)A.nl[4 * na - 1] + 1;
+        if (end < A.mf.size) na -= 1;
+    }
     if (na == 0) return !(A.pos < A.mf.size) ? true : false;  // leftover bytes without 4 complete lines: serial reader
     const size_t stride = B2 ? 2 : 1;
     const size_t n = na * stride;

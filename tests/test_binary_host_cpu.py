@@ -310,3 +310,22 @@ def test_tiny_batches_with_long_reads(double_exe, workdir, batch):
         assert r.returncode == 0 and b"Processed 40 reads" in r.stderr, r.stderr.decode()
         outs.append(open(os.path.join(od, "x.cor.fq"), "rb").read())
     assert outs[0] == outs[1] and outs[0].count(b"\n") == 160
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_interleaved_file_without_final_newline_keeps_its_last_pair(double_exe, workdir, threads):
+    """Found by tools/fuzz_binary_vs_ref.py (seed 9, case 191; kept as tests/golden/host_interleaved_no_final_newline): the
+    mapped-file reader took the complete records (an odd number) and left the last, newline-less record to the serial reader,
+    so the mates of the last pair were corrected without each other."""
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir + "_cpu")
+    fx = os.path.join(T.GOLDEN, "host_interleaved_no_final_newline")
+    exp = open(os.path.join(fx, "expected.cor.fq"), "rb").read()
+    w = os.path.join(workdir + "_cpu", "inter_nonl_" + threads)
+    os.makedirs(w, exist_ok=True)
+    for tag, env, batch in (("fast", {}, "1048576"), ("fast_tiny", {}, "8"), ("serial", {"RCX_SERIAL_IO": "1"}, "1048576")):
+        od = os.path.join(w, tag)
+        r = subprocess.run([double_exe, "-i", os.path.join(fx, "input.fq"), "-c", dump, "-k", str(meta["k"]), "-od", od, "-t", threads,
+                            "-batch", batch], capture_output=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr.decode()
+        assert b"Processed 16 reads" in r.stderr and b"Corrected 32 bases" in r.stderr
+        assert open(os.path.join(od, "input.cor.fq"), "rb").read() == exp
