@@ -34,8 +34,7 @@ def test_binary_campaign_smoke(workdir):
     os.makedirs(top)
     exe = F.build_double(top)
     meta, fq, dump, _ = T.load_golden("paired_k23", top)
-    b = T.read_fastq(fq[0])
-    base = [(b.ids[i], b.seq[b.off[i]:b.off[i + 1]].tobytes(), b.qual[b.off[i]:b.off[i + 1]].tobytes()) for i in range(b.n)]
+    base = F.load_pairs(fq)
     rng = random.Random(20261017)
     for i in range(30):
         wd = os.path.join(top, "c%03d" % i)

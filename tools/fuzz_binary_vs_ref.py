@@ -34,6 +34,13 @@ def build_double(d):
     return exe
 
 
+def load_pairs(fq):
+    """[(mate1, mate2)] with mate = (id, seq, qual) bytes, from the two files of a paired fixture."""
+    bs = [T.read_fastq(f) for f in fq]
+    rec = lambda b, i: (b.ids[i], b.seq[b.off[i]:b.off[i + 1]].tobytes(), b.qual[b.off[i]:b.off[i + 1]].tobytes())
+    return [(rec(bs[0], i), rec(bs[1], i)) for i in range(bs[0].n)]
+
+
 def mutate_records(rng, recs, style):
     """recs: list of (id, seq, qual) bytes.  Returns file bytes."""
     out = []
@@ -68,12 +75,13 @@ def one_case(rng, exe, base_recs, dump, k, wd):
     args, files = [], []
     for fno in range(nfiles):
         mates = []
+        cnt = n if not inter else n - (n % 2)
+        cnt = max(cnt, 2 if inter else 1)
+        pick = [rng.randrange(len(base_recs)) for _ in range(cnt)]  # real mate pairs, so that the pair threshold matters
         for mate in range(2 if paired else 1):
             recs = []
-            cnt = n if not inter else n - (n % 2)
-            cnt = max(cnt, 2 if inter else 1)
             for i in range(cnt):
-                rid, seq, qual = base_recs[rng.randrange(len(base_recs))]
+                rid, seq, qual = base_recs[pick[i // 2]][i % 2] if inter else base_recs[pick[i]][mate]
                 L = rng.choice([len(seq), len(seq), len(seq), 1, 5, k - 1, k, k + 1, 60])
                 L = min(L, len(seq))
                 s, q = seq[:L], qual[:L]
@@ -83,7 +91,7 @@ def one_case(rng, exe, base_recs, dump, k, wd):
                     s = s[:2] + b"N" + s[3:]
                 recs.append((random_id(rng, i, mate), s, q))
             if rng.random() < 0.05 and not style["fasta"]:  # one long read
-                big = (base_recs[0][1] * 12)[: rng.choice([512, 1000, 1022])]  # 1022: the longest line the reference's 1024-byte fgets buffer takes whole
+                big = (base_recs[0][0][1] * 12)[: rng.choice([512, 1000, 1022])]  # 1022: the longest line the reference's 1024-byte fgets buffer takes whole
                 recs[0] = (recs[0][0], big, b"I" * len(big))
             data = mutate_records(rng, recs, style)
             ext = (".fa" if style["fasta"] else rng.choice([".fq", ".fastq"])) + (".gz" if gz else "")
@@ -128,8 +136,7 @@ def main():
     exe = build_double(top)
     meta, fq, dump, _ = T.load_golden("paired_k23", top)
     k = meta["k"]
-    b = T.read_fastq(fq[0])
-    base_recs = [(b.ids[i], b.seq[b.off[i]:b.off[i + 1]].tobytes(), b.qual[b.off[i]:b.off[i + 1]].tobytes()) for i in range(b.n)]
+    base_recs = load_pairs(fq)
     rng = random.Random(a.seed)
     bad = 0
     for i in range(a.cases):
