@@ -73,7 +73,11 @@ def one_case(rng, exe, base_recs, dump, k, wd):
     gz = rng.random() < 0.3
     nfiles = rng.choice([1, 1, 1, 2])
     args, files = [], []
+    first_kind = (paired, inter)
     for fno in range(nfiles):
+        if fno > 0 and rng.random() < 0.5:  # a command line may mix -r, -p and -i files
+            paired = rng.random() < 0.4
+            inter = (not paired) and rng.random() < 0.4
         mates = []
         cnt = n if not inter else n - (n % 2)
         cnt = max(cnt, 2 if inter else 1)
@@ -103,9 +107,14 @@ def one_case(rng, exe, base_recs, dump, k, wd):
     t = rng.choice(["1", "2", "3", "5"])
     if style["fasta"] and t == "1":
         t = "2"  # the reference's FASTA path crashes with -t 1
+    paired, inter = first_kind
     common = ["-c", dump, "-k", str(k), "-t", t]
     if rng.random() < 0.2:
         common += ["-stdout"]
+    if rng.random() < 0.2:
+        common += ["-maxcorK", str(rng.choice([1, 2, 3, 6, 8]))]
+    if rng.random() < 0.1:
+        common += ["-wk", str(rng.choice([0.1, 0.5, 0.99]))]
     res = []
     for tag, binary, extra in (("ref", T.REF_BIN, []), ("ours", exe, ["-batch", str(rng.choice([2, 8, 64, 1000, 1 << 20]))])):
         od = os.path.join(wd, "out_" + tag)
