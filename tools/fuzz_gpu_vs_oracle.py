@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--long", action="store_true")
+    ap.add_argument("--wild-quals", action="store_true")
     a = ap.parse_args()
     F.LONG = a.long
     from rcorrector_b200 import Corrector
@@ -59,6 +60,8 @@ def main():
         wd = tempfile.mkdtemp(prefix="rcxgpufuzz_")
         try:
             d = T.synth(wd, "g%04d" % i, k=k, paired=paired, **kw)
+            if a.wild_quals:
+                F.wild_quals(rng, d["fq"])
             bs = [T.read_fastq(f) for f in d["fq"]]
             b = T.interleave(*bs) if paired else bs[0]
             codes, counts = T.dump_to_arrays(d["dump"], k)

@@ -20,7 +20,26 @@ import rcx_testlib as T  # noqa: E402
 
 
 LONG = False
+WILD_QUALS = False
 LONG_LENGTHS = [256, 300, 400, 512, 640, 800, 1000]  # rcx_synth generates up to 1000 bases (the reference allows 1023)
+
+
+def wild_quals(rng, files):
+    """The generator's qualities stay inside a narrow band: rewrite part of them with the whole printable range."""
+    for f in files:
+        lines = open(f, "rb").read().split(b"\n")
+        for i in range(3, len(lines), 4):
+            r = rng.random()
+            n = len(lines[i])
+            if r < 0.25:
+                lines[i] = bytes(rng.randrange(33, 127) for _ in range(n))
+            elif r < 0.35:
+                lines[i] = bytes(rng.choice(b"!\"#$%") for _ in range(n))
+            elif r < 0.45:
+                lines[i] = bytes(rng.choice(b"~}|IJ") for _ in range(n))
+            elif r < 0.5 and n > 4:
+                lines[i] = b"!" * 2 + lines[i][2:-2] + b"~" * 2
+        open(f, "wb").write(b"\n".join(lines))
 
 
 def one_case(rng, wd, idx):
@@ -45,6 +64,8 @@ def one_case(rng, wd, idx):
         extra += ["-wk", str(wk)]
     name = "f%04d" % idx
     d = T.synth(wd, name, k=k, paired=paired, **kw)
+    if WILD_QUALS:
+        wild_quals(rng, d["fq"])
     err, outs = T.run_reference(d["fq"], d["dump"], k, os.path.join(wd, "out_" + name), threads=rng.choice([1, 3]), extra=extra)
     info = T.parse_ref_stderr(err)
     bs = [T.read_fastq(f) for f in d["fq"]]
@@ -74,10 +95,12 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--keep", default=None)
-    ap.add_argument("--long", action="store_true", help="reads of 256..1023 bases (the warp-per-read kernels' range)")
+    ap.add_argument("--long", action="store_true", help="reads of 256..1000 bases (the warp-per-read kernels' range)")
+    ap.add_argument("--wild-quals", action="store_true", help="rewrite part of the quality strings with the whole printable range")
     a = ap.parse_args()
-    global LONG
+    global LONG, WILD_QUALS
     LONG = a.long
+    WILD_QUALS = a.wild_quals
     if not os.path.exists(T.REF_BIN):
         sys.exit("oracle/_ref/rcorrector not built (make -C oracle ref)")
     rng = random.Random(a.seed)
