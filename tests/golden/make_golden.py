@@ -36,20 +36,44 @@ def gz(src, dst):
         shutil.copyfileobj(f, g)
 
 
+# BASELINE.json configs[0]: the reference's bundled paired sample (data files, not source), k = 23, with the exact-count
+# dump Jellyfish would give (tools/rcx_kmercount).  md5 of the outputs: SURVEY §8c / BASELINE.md §2.
+SAMPLE = ("sample_k23", 23, True, [], None)
+SAMPLE_FILES = ["/root/reference/Sample/sample_read1.fq", "/root/reference/Sample/sample_read2.fq"]
+SAMPLE_MD5 = ["d67b929e0ce992bddd34525c78df8fe5", "40724361c10ba362ea15d1ae0b6b59dc"]
+
+
+def sample_inputs(wd):
+    T.ensure_tools()
+    fq = []
+    for i, src in enumerate(SAMPLE_FILES):
+        dst = os.path.join(wd, "reads_%d.fq" % (i + 1))  # the fixture loader expects reads_*.fq / reads.dump
+        shutil.copy(src, dst)
+        fq.append(dst)
+    dump = os.path.join(wd, "reads.dump")
+    T.run([T.KMERCOUNT, "-k", "23", "-o", dump] + fq)
+    return {"fq": fq, "dump": dump}
+
+
 def main():
     if not os.path.exists(T.REF_BIN):
         raise SystemExit("build oracle/_ref first (make -C oracle ref; needs /root/reference)")
-    for name, k, paired, extra, kw in CASES:
+    only = sys.argv[1:]
+    for name, k, paired, extra, kw in CASES + [SAMPLE]:
+        if only and name not in only:
+            continue
         out = os.path.join(HERE, name)
         shutil.rmtree(out, ignore_errors=True)
         os.makedirs(out)
         with tempfile.TemporaryDirectory() as wd:
-            d = T.synth(wd, "reads", k=k, paired=paired, **kw)
+            d = sample_inputs(wd) if kw is None else T.synth(wd, "reads", k=k, paired=paired, **kw)
             err, outs = T.run_reference(d["fq"], d["dump"], k, os.path.join(wd, "out"), threads=1, extra=extra)
             err4, outs4 = T.run_reference(d["fq"], d["dump"], k, os.path.join(wd, "out4"), threads=4, extra=extra)
             for a, b in zip(outs, outs4):
                 assert open(a, "rb").read() == open(b, "rb").read(), "-t 1 and -t 4 differ"
             info = T.parse_ref_stderr(err)
+            if kw is None:
+                assert [T.md5(open(f, "rb").read()) for f in outs] == SAMPLE_MD5, "bundled sample: md5 differs from SURVEY 8c"
             for f in d["fq"]:
                 gz(f, os.path.join(out, os.path.basename(f) + ".gz"))
             gz(d["dump"], os.path.join(out, "reads.dump.gz"))
