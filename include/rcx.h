@@ -82,6 +82,10 @@ void rcx_destroy(rcx_ctx* ctx);
  * this context's GPU (e.g. the landing buffers of an NCCL broadcast). */
 int rcx_table_build(rcx_ctx* ctx, int k, const uint64_t* fwd_codes, const int32_t* counts, uint64_t n,
                     int src_on_device);
+/* The same table on every context of `ctxs` (several GPUs of one host; the Put loop of main.cpp:295-307 once per GPU):
+ * the host arrays cross PCIe once, to the first context's GPU, and go on device to device (peer copies over NVLink /
+ * NVSwitch, binomial tree) before every GPU inserts locally.  Host pointers. */
+int rcx_table_build_multi(rcx_ctx** ctxs, int nctx, int k, const uint64_t* fwd_codes, const int32_t* counts, uint64_t n);
 /* Store::GetCount (Store.h:59-66) for n valid forward codes; host pointers. */
 int rcx_table_lookup(rcx_ctx* ctx, const uint64_t* fwd_codes, int32_t* counts_out, uint64_t n);
 /* number of distinct canonical k-mers stored, 32-byte sectors allocated (one (k-1)-mer context each), bytes of HBM */
@@ -100,7 +104,22 @@ int rcx_set_params(rcx_ctx* ctx, const rcx_params* p);
 int rcx_correct_batch(rcx_ctx* ctx, int mode, int64_t n, const char* seq_in, const char* qual,
                       const uint32_t* off, char* seq_out, int32_t* correction, int32_t* l, int32_t* m,
                       int32_t* h);
-/* Same with DEVICE pointers on the context's GPU; `seq` is corrected in place
+/* The same batch through a COMPACT host interface, for callers that keep their own copy of the reads (the drop-in binary's
+ * reader, bench.py's e2e arm): PCIe is what a multi-GPU host runs out of first, so only what the path consumes crosses it.
+ *  - quality: ErrorCorrection reads it only as "qual[i] > badQualityThreshold" (the three post-filters,
+ *    ErrorCorrection.cpp:1314-1316,1407-1455) and "qual[0] != 0" (has quality at all, :1314).  qual_bits holds one bit per
+ *    base of the batch: bit (i & 7) of byte i >> 3 = (signed char)qual[i] > bad_qual for batch base i (off[] indexes bases
+ *    as in rcx_correct_batch); has_qual = 0 for FASTA input (qual_bits may then be null).  The threshold folded into the
+ *    bits must be the bad_qual given to rcx_set_params.
+ *  - result: correction / l / m / h per record as above, and instead of the corrected bases the applied substitutions:
+ *    record r with correction[r] > 0 owns correction[r] consecutive entries of edits[], after those of the records before
+ *    it; entry = position in the read | base << 10 (A0 C1 G2 T3), in no particular order inside a record.  *n_edits = total
+ *    entries = sum of the positive correction[r]; RCX_ERR_ARG (with *n_edits set) if edits_cap is too small.
+ * Per 100-bp read this moves ~117 bytes up and ~18 down instead of 204 up and 116 down. */
+int rcx_correct_batch_compact(rcx_ctx* ctx, int mode, int64_t n, const char* seq, const uint8_t* qual_bits, int has_qual,
+                              const uint32_t* off, int32_t* correction, int32_t* l, int32_t* m, int32_t* h, uint16_t* edits,
+                              uint64_t edits_cap, uint64_t* n_edits);
+/* Same as rcx_correct_batch with DEVICE pointers on the context's GPU; `seq` is corrected in place
  * (as the reference does with _Read::seq).  total_bases = off[n] and max_len =
  * the longest read, both known to the caller that built the batch.
  * Asynchronous on the context's stream: call rcx_sync() before reading results. */

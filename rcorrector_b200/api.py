@@ -17,8 +17,8 @@ SINGLE, INTERLEAVED = 0, 1
 
 # every symbol include/rcx.h declares
 SYMBOLS = [
-    "rcx_abi_version", "rcx_last_error", "rcx_create", "rcx_destroy", "rcx_table_build", "rcx_table_lookup",
-    "rcx_table_info", "rcx_set_params", "rcx_correct_batch", "rcx_correct_batch_device", "rcx_sync",
+    "rcx_abi_version", "rcx_last_error", "rcx_create", "rcx_destroy", "rcx_table_build", "rcx_table_build_multi", "rcx_table_lookup",
+    "rcx_table_info", "rcx_set_params", "rcx_correct_batch", "rcx_correct_batch_compact", "rcx_correct_batch_device", "rcx_sync",
     "rcx_scan_batch", "rcx_get_stats", "rcx_debug_counters", "rcx_measure_random_read", "rcx_stream", "rcx_host_alloc", "rcx_host_free", "rcx_estimate_error_rate",
 ]
 
@@ -61,10 +61,12 @@ def load_library():
     lib.rcx_destroy.argtypes = [vp]
     lib.rcx_destroy.restype = None
     lib.rcx_table_build.argtypes = [vp, C.c_int, vp, vp, u64, C.c_int]
+    lib.rcx_table_build_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, vp, u64]
     lib.rcx_table_lookup.argtypes = [vp, vp, vp, u64]
     lib.rcx_table_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     lib.rcx_set_params.argtypes = [vp, C.POINTER(RcxParams)]
     lib.rcx_correct_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.rcx_correct_batch_compact.argtypes = [vp, C.c_int, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
     lib.rcx_correct_batch_device.argtypes = [vp, C.c_int, i64, vp, vp, vp, u64, i32, vp, vp, vp, vp]
     lib.rcx_sync.argtypes = [vp]
     lib.rcx_scan_batch.argtypes = [vp, i64, vp, vp, vp, vp]
@@ -163,6 +165,19 @@ class Corrector:
                                                _ptr(l), _ptr(m), _ptr(h)))
         return so, corr, l, m, h
 
+    def correct_compact(self, mode, seq, qual_bits, off, out=None, has_qual=True):
+        """Compact host interface: one quality bit per base in (see quality_bits()), applied edits out instead of sequences.
+        Returns (correction, l, m, h, edits[:n_edits])."""
+        n = len(off) - 1
+        if out is None:
+            out = (np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32),
+                   np.zeros(max(len(seq) // 4, 1024), dtype=np.uint16))
+        corr, l, m, h, edits = out
+        ne = C.c_uint64()
+        self._check(self.lib.rcx_correct_batch_compact(self.h, mode, n, _ptr(seq), _ptr(qual_bits), 1 if has_qual else 0, _ptr(off),
+                                                       _ptr(corr), _ptr(l), _ptr(m), _ptr(h), _ptr(edits), len(edits), C.byref(ne)))
+        return corr, l, m, h, edits[: ne.value]
+
     def correct_device(self, mode, n, seq, qual, off, total_bases, max_len, corr, l, m, h):
         """Device pointers / torch CUDA tensors; seq corrected in place; asynchronous (call sync())."""
         self._check(self.lib.rcx_correct_batch_device(self.h, mode, n, _ptr(seq), _ptr(qual), _ptr(off), total_bases,
@@ -195,3 +210,21 @@ class Corrector:
 
     def stream(self):
         return self.lib.rcx_stream(self.h)
+
+
+def quality_bits(qual, bad_qual):
+    """The quality bit plane rcx_correct_batch_compact takes: bit (i & 7) of byte i >> 3 = (signed char)qual[i] > bad_qual."""
+    q = np.ascontiguousarray(qual, dtype=np.uint8).view(np.int8)
+    return np.packbits(q > bad_qual, bitorder="little")
+
+
+def apply_edits(seq, off, corr, edits):
+    """What a caller of the compact interface does with its own copy of the reads: record r owns corr[r] entries of
+    `edits` (when positive) after those of the records before it; entry = position | base << 10."""
+    out = np.array(seq, dtype=np.uint8, copy=True)
+    c = np.maximum(np.asarray(corr, dtype=np.int64), 0)
+    start = np.repeat(np.asarray(off[:-1], dtype=np.int64), c)
+    e = np.asarray(edits, dtype=np.uint16).astype(np.int64)
+    assert len(e) == len(start)
+    out[start + (e & 1023)] = np.frombuffer(b"ACGT", dtype=np.uint8)[e >> 10]
+    return out

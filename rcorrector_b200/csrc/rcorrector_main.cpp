@@ -74,6 +74,14 @@ static void tmark(const char* what) {
     if (g_timing) fprintf(stderr, "RCX_TIMING %8.3f s  %s\n", now_s() - g_t0, what);
 }
 
+// outputs opened so far: removed again when the run has to stop half way (a truncated *.cor.fq looks like a result)
+static std::vector<std::string> g_out_paths;
+static std::string g_od_created;
+static void remove_partial_outputs() {
+    for (auto& p : g_out_paths) unlink(p.c_str());
+    if (!g_od_created.empty()) rmdir(g_od_created.c_str());  // (only if this run created it and it is empty)
+}
+
 static void die_rcx(const char* what) {
     fprintf(stderr, "%s: %s\n", what, rcx_last_error());
     exit(1);
@@ -547,9 +555,11 @@ static void check_supported(rcx_ctx* ctx) {
     rcx_stats st;
     if (rcx_get_stats(ctx, &st)) die_rcx("rcx_get_stats");
     if (st.unsupported) {
-        fprintf(stderr, "ERROR: %llu reads of this batch need a case the GPU path does not reproduce (see rcx_stats.unsupported)\n",
-                (unsigned long long)st.unsupported);
-        exit(1);
+        fprintf(stderr, "ERROR: %llu reads of this batch need a case the GPU path does not reproduce (see rcx_stats.unsupported); "
+                        "no output is kept\n", (unsigned long long)st.unsupported);
+        fflush(stderr);
+        remove_partial_outputs();
+        _exit(1);  // (formatting / writing threads of earlier batches may still be running)
     }
 }
 
@@ -603,7 +613,7 @@ int main(int argc, char* argv[]) {
         if (!strcmp("-r", argv[i])) { ++i; continue; }
         else if (!strcmp("-p", argv[i])) { i += 2; continue; }
         else if (!strcmp("-i", argv[i])) { ++i; continue; }
-        else if (!strcmp("-od", argv[i])) { mkdir(argv[i + 1], 0700); od = argv[i + 1]; ++i; }
+        else if (!strcmp("-od", argv[i])) { if (mkdir(argv[i + 1], 0700) == 0) g_od_created = argv[i + 1]; od = argv[i + 1]; ++i; }
         else if (!strcmp("-c", argv[i])) { dump_path = argv[i + 1]; ++i; }
         else if (!strcmp("-k", argv[i])) { k = atoi(argv[i + 1]); ++i; }
         else if (!strcmp("-t", argv[i])) { threads = atoi(argv[i + 1]); ++i; }
@@ -671,10 +681,12 @@ int main(int argc, char* argv[]) {
             fprintf(stderr, "ERROR: Could not access file %s\n", files[i].out_path.c_str());  // File.h:71,93
             exit(1);
         }
+        if (!to_stdout) g_out_paths.push_back(files[i].out_path);
         if (files[i].paired && !out2[i].open(files[i].mate_out_path, to_stdout)) {
             fprintf(stderr, "ERROR: Could not access file %s\n", files[i].mate_out_path.c_str());
             exit(1);
         }
+        if (!to_stdout && files[i].paired) g_out_paths.push_back(files[i].mate_out_path);
     }
 
     // ---- badQualityThreshold (main.cpp:88-128): first 1e6 records of the first Reads object.  Independent of the table, so the
@@ -749,14 +761,10 @@ int main(int argc, char* argv[]) {
     tmark("dump parsed");
     gpus_ready.wait();
     tmark("CUDA contexts ready");
-    {
-        std::vector<std::thread> th;
-        std::vector<int> rc(ngpu, 0);
-        for (int g = 0; g < ngpu; ++g)
-            th.emplace_back([&, g]() { rc[g] = rcx_table_build(gpus[g].ctx, k, dump.codes.data(), dump.counts.data(), dump.codes.size(), 0); });
-        for (auto& t : th) t.join();
-        for (int g = 0; g < ngpu; ++g)
-            if (rc[g]) { fprintf(stderr, "rcx_table_build failed on GPU %d\n", g); exit(1); }
+    {   // one upload over PCIe, device-to-device copies to the other GPUs (NVLink), local inserts in parallel
+        std::vector<rcx_ctx*> ctxs;
+        for (auto& g : gpus) ctxs.push_back(g.ctx);
+        if (rcx_table_build_multi(ctxs.data(), ngpu, k, dump.codes.data(), dump.counts.data(), dump.codes.size())) die_rcx("rcx_table_build");
     }
     fprintf(stderr, "Stored %d kmers\n", (int)dump.stored);
     tmark("table built");

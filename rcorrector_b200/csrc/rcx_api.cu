@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rcx.h"
@@ -65,6 +66,11 @@ struct RcxSlot {
     DevBuf<signed char> d_fixbuf, d_dfs_path;
     DevBuf<unsigned char> d_posbuf;
     DevBuf<unsigned int> d_dfs_stack;
+    // compact host interface: quality bits in, gathered edits out
+    DevBuf<unsigned char> d_qbits, d_temp;
+    DevBuf<uint32_t> d_scan;
+    DevBuf<uint16_t> d_edits;
+    bool edits_pending = false;  // the chunk's edits still wait on the device for their place in the caller's stream
     unsigned long long* d_counters = nullptr;
     unsigned long long* h_counters = nullptr;  // pinned landing area of the counters
     cudaEvent_t ev[6]{};
@@ -76,6 +82,7 @@ struct RcxSlot {
         d_seq.release(); d_qual.release(); d_off.release(); d_counts.release(); d_thr.release(); d_corr.release(); d_l.release();
         d_m.release(); d_h.release(); d_flags.release(); d_worklist.release(); d_worklist2.release(); d_state.release();
         d_fixbuf.release(); d_dfs_path.release(); d_posbuf.release(); d_dfs_stack.release();
+        d_qbits.release(); d_temp.release(); d_scan.release(); d_edits.release();
     }
 };
 
@@ -99,6 +106,10 @@ struct rcx_ctx {
     int nslots = 3;  // slots a host batch cycles through (RCX_SLOTS)
     int chain = 0;   // RCX_CHAIN: 1 = a chunk's kernels start when the previous chunk has reached its finalize kernel, 2 = when it is done
     rcx_stats stats{};
+    // the compact call in progress: where the chunks' edits go (harvest appends them in chunk order)
+    uint16_t* cur_edits = nullptr;
+    uint64_t cur_edits_cap = 0, cur_edits_n = 0;
+    bool cur_edits_overflow = false;
 };
 
 extern "C" int rcx_abi_version(void) { return RCX_ABI_VERSION; }
@@ -355,6 +366,90 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     return RCX_OK;
 }
 
+// The same table on several GPUs of one host (the drop-in binary's -gpus N): the (code, count) arrays cross PCIe ONCE, to
+// the first context's GPU, and travel on device to device (binomial tree of peer copies: NVLink / NVSwitch where the GPUs
+// have it); every GPU then inserts locally, in parallel.
+extern "C" int rcx_table_build_multi(rcx_ctx** ctxs, int nctx, int k, const uint64_t* fwd_codes, const int32_t* counts, uint64_t n) {
+    if (!ctxs || nctx < 1) return fail(RCX_ERR_ARG, "rcx_table_build_multi: no contexts");
+    for (int g = 0; g < nctx; ++g)
+        if (!ctxs[g]) return fail(RCX_ERR_ARG, "rcx_table_build_multi: null context");
+    if (nctx == 1 || n == 0) {
+        for (int g = 0; g < nctx; ++g) {
+            const int rc = rcx_table_build(ctxs[g], k, fwd_codes, counts, n, 0);
+            if (rc) return rc;
+        }
+        return RCX_OK;
+    }
+    if (!fwd_codes || !counts) return fail(RCX_ERR_ARG, "rcx_table_build_multi: null input arrays");
+    std::vector<unsigned long long*> d_codes(nctx, nullptr);
+    std::vector<int32_t*> d_counts(nctx, nullptr);
+    auto release = [&]() {
+        for (int g = 0; g < nctx; ++g) {
+            cudaSetDevice(ctxs[g]->device);
+            if (d_codes[g]) cudaFree(d_codes[g]);
+            if (d_counts[g]) cudaFree(d_counts[g]);
+        }
+    };
+    bool staged = true;
+    for (int g = 0; g < nctx && staged; ++g) {
+        cudaSetDevice(ctxs[g]->device);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || n * 12 > free_b / 4 ||  // keep room for the table and its build
+            cudaMalloc(&d_codes[g], n * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&d_counts[g], n * sizeof(int32_t)) != cudaSuccess)
+            staged = false;
+        for (int p = 0; p < nctx && staged; ++p)
+            if (p != g) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ctxs[g]->device, ctxs[p]->device);
+                if (can && cudaDeviceEnablePeerAccess(ctxs[p]->device, 0) != cudaSuccess) cudaGetLastError();  // (already enabled)
+            }
+    }
+    cudaGetLastError();
+    if (!staged) {  // records too large to stage next to the table: every GPU streams them from the host
+        release();
+        std::vector<std::thread> th;
+        std::vector<int> rcs(nctx, 0);
+        std::vector<std::string> errs(nctx);
+        for (int g = 0; g < nctx; ++g)
+            th.emplace_back([&, g]() { rcs[g] = rcx_table_build(ctxs[g], k, fwd_codes, counts, n, 0); if (rcs[g]) errs[g] = g_err; });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < nctx; ++g) if (rcs[g]) return fail(rcs[g], errs[g]);
+        return RCX_OK;
+    }
+    cudaError_t e = cudaSetDevice(ctxs[0]->device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_codes[0], fwd_codes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctxs[0]->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_counts[0], counts, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctxs[0]->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctxs[0]->stream);
+    for (int have = 1; have < nctx && e == cudaSuccess; have *= 2) {  // GPUs [0, have) hold the records: each feeds one more
+        for (int g = 0; g < have && g + have < nctx && e == cudaSuccess; ++g) {
+            const int src = g, dst = g + have;
+            e = cudaSetDevice(ctxs[src]->device);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d_codes[dst], ctxs[dst]->device, d_codes[src], ctxs[src]->device, n * sizeof(uint64_t), ctxs[src]->stream);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d_counts[dst], ctxs[dst]->device, d_counts[src], ctxs[src]->device, n * sizeof(int32_t), ctxs[src]->stream);
+        }
+        for (int g = 0; g < have && e == cudaSuccess; ++g) {
+            e = cudaSetDevice(ctxs[g]->device);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctxs[g]->stream);
+        }
+    }
+    if (e != cudaSuccess) {
+        release();
+        return fail(RCX_ERR_CUDA, std::string("rcx_table_build_multi: ") + cudaGetErrorString(e));
+    }
+    std::vector<std::thread> th;
+    std::vector<int> rcs(nctx, 0);
+    std::vector<std::string> errs(nctx);
+    for (int g = 0; g < nctx; ++g)
+        th.emplace_back([&, g]() {
+            rcs[g] = rcx_table_build(ctxs[g], k, (const uint64_t*)d_codes[g], d_counts[g], n, 1);
+            if (rcs[g]) errs[g] = g_err;
+        });
+    for (auto& t : th) t.join();
+    release();
+    for (int g = 0; g < nctx; ++g) if (rcs[g]) return fail(rcs[g], errs[g]);
+    return RCX_OK;
+}
+
 static RcxTable table_of(const rcx_ctx* c) {
     RcxTable t;
     t.e = c->entries_dev;
@@ -432,7 +527,7 @@ static int scan_lengths(const uint32_t* off, int64_t n, int32_t* max_len) {
 // chunk's first offset): the kernels index them with the ABSOLUTE offsets of `d_off`.
 static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d_seq, const char* d_qual, const uint32_t* d_off,
                            uint64_t first_base, uint64_t end_base, int32_t max_len, int32_t* d_corr, int32_t* d_l, int32_t* d_m,
-                           int32_t* d_h, bool correct) {
+                           int32_t* d_h, bool correct, const unsigned char* d_qbits = nullptr, int has_qual = 1, bool emit_edits = false) {
     const uint64_t span = end_base - first_base;
     const uint64_t lead = first_base & 15;  // keeps every virtual base 16-byte aligned
     CUDA_TRY(sl.d_counts.ensure(span + 32));
@@ -471,6 +566,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         ca.t = sa.t;
         ca.seq = d_seq; ca.qual = d_qual; ca.off = d_off; ca.n = n; ca.max_len = max_len; ca.mode = mode;
         ca.max_fix_per_k = c->params.max_fix_per_k; ca.error_rate = c->params.error_rate; ca.bad_qual = c->params.bad_qual;
+        ca.qbits = d_qbits; ca.has_qual = has_qual; ca.emit_edits = emit_edits ? 1 : 0;
         ca.counts = sa.counts; ca.thr = sl.d_thr.p; ca.flags = sl.d_flags.p;
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = sl.d_counters;
         ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
@@ -483,6 +579,14 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, sl.stream, sl.kev, thread_scan));
         sl.kev_valid = true;
         sl.launches = thread_scan ? 5 : 6;  // scan (+ thresholds + triage [+ first preparation]), search, preparation + search of the second pass, finalize
+        if (emit_edits) {  // applied edits of the changed reads, in record order (prefix sum + gather: 2 library + 1 own launch)
+            const size_t tb = rcx_edits_temp_bytes(n);
+            CUDA_TRY(sl.d_temp.ensure(tb));
+            CUDA_TRY(sl.d_scan.ensure((size_t)n + 1));
+            CUDA_TRY(sl.d_edits.ensure(span + 64));  // a read cannot have more edits than bases
+            CUDA_TRY(rcx_launch_edits_gather(d_corr, d_off, n, ca.fixbuf, ca.compact_fix, sl.d_scan.p, sl.d_temp.p, tb, sl.d_edits.p, sl.d_counters, sl.stream));
+            sl.launches += 1;
+        }
     }
     CUDA_TRY(cudaEventRecord(sl.ev[3], sl.stream));
     return RCX_OK;
@@ -493,6 +597,16 @@ static int harvest(rcx_ctx* c, RcxSlot& sl) {
     if (!sl.pending) return RCX_OK;
     CUDA_TRY(cudaStreamSynchronize(sl.stream));
     const unsigned long long* h = sl.h_counters;
+    if (sl.edits_pending) {  // this chunk's edits follow those of the chunks before it (harvests run in chunk order)
+        const uint64_t ne = h[RCX_C_NEDITS];
+        if (c->cur_edits && c->cur_edits_n + ne <= c->cur_edits_cap) {
+            if (ne) CUDA_TRY(cudaMemcpyAsync(c->cur_edits + c->cur_edits_n, sl.d_edits.p, ne * sizeof(uint16_t), cudaMemcpyDeviceToHost, sl.stream));
+        } else {
+            c->cur_edits_overflow = true;
+        }
+        c->cur_edits_n += ne;
+        sl.edits_pending = false;
+    }
     c->stats.scan_probes += h[RCX_C_SCAN_PROBES];
     c->stats.search_probes += h[RCX_C_SEARCH_PROBES];
     c->stats.rescan_probes += h[RCX_C_RESCAN_PROBES];
@@ -500,6 +614,10 @@ static int harvest(rcx_ctx* c, RcxSlot& sl) {
     c->stats.work_items += h[RCX_C_NWORK];
     c->stats.second_pass += h[RCX_C_NWORK2];
     c->stats.unsupported += h[RCX_C_UNSUPPORTED];
+    {   // test hook (tests/test_gpu_golden.py): RCX_TEST_FORCE_UNSUPPORTED=n flags the n-th harvested batch of the process
+        static int forced = getenv("RCX_TEST_FORCE_UNSUPPORTED") ? atoi(getenv("RCX_TEST_FORCE_UNSUPPORTED")) : 0;
+        if (forced > 0 && --forced == 0) c->stats.unsupported += 1;
+    }
     c->stats.kernel_launches += (uint64_t)sl.launches;
     auto ms = [&](cudaEvent_t a, cudaEvent_t b) {
         float v = 0;
@@ -562,15 +680,19 @@ extern "C" int rcx_correct_batch_device(rcx_ctx* c, int mode, int64_t n, char* s
 // Host batch: cut into chunks of whole records (pairs stay together) that cycle through the slots, so that the
 // host -> device copy of chunk i+1 and the device -> host copy of chunk i-1 overlap the kernels of chunk i
 // (needs pinned host buffers to be truly asynchronous: rcx_host_alloc).  Results do not depend on the chunking.
-extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* seq_in, const char* qual, const uint32_t* off,
-                                 char* seq_out, int32_t* correction, int32_t* l, int32_t* m, int32_t* h) {
-    int rc = check_ready(c, "rcx_correct_batch");
+// `compact`: quality arrives as one bit per base (qbits; may be null when has_qual == 0), no sequence goes back; the applied
+// edits are appended to c->cur_edits instead.
+static int correct_host(rcx_ctx* c, const char* who, int mode, int64_t n, const char* seq_in, const char* qual, const unsigned char* qbits,
+                        int has_qual, bool compact, const uint32_t* off, char* seq_out, int32_t* correction, int32_t* l, int32_t* m,
+                        int32_t* h) {
+    int rc = check_ready(c, who);
     if (rc) return rc;
-    if (n < 0 || (mode != RCX_SINGLE && mode != RCX_INTERLEAVED)) return fail(RCX_ERR_ARG, "rcx_correct_batch: bad n or mode");
-    if (mode == RCX_INTERLEAVED && (n & 1)) return fail(RCX_ERR_ARG, "rcx_correct_batch: interleaved batch needs an even n");
+    if (n < 0 || (mode != RCX_SINGLE && mode != RCX_INTERLEAVED)) return fail(RCX_ERR_ARG, std::string(who) + ": bad n or mode");
+    if (mode == RCX_INTERLEAVED && (n & 1)) return fail(RCX_ERR_ARG, std::string(who) + ": interleaved batch needs an even n");
     if (n == 0) return RCX_OK;
-    if (!seq_in || !qual || !off || !seq_out || !correction || !l || !m || !h) return fail(RCX_ERR_ARG, "rcx_correct_batch: null pointer");
-    if (off[0] != 0) return fail(RCX_ERR_ARG, "rcx_correct_batch: off[0] must be 0");
+    if (!seq_in || !off || !correction || !l || !m || !h || (!compact && (!qual || !seq_out)) || (compact && has_qual && !qbits))
+        return fail(RCX_ERR_ARG, std::string(who) + ": null pointer");
+    if (off[0] != 0) return fail(RCX_ERR_ARG, std::string(who) + ": off[0] must be 0");
     CUDA_TRY(cudaSetDevice(c->device));
     rc = begin_call(c, (uint64_t)n, off[n]);
     if (rc) return rc;
@@ -609,8 +731,10 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
         rc = harvest(c, sl);  // the slot's previous chunk (also makes its buffers reusable)
         if (rc) return rc;
         const uint64_t b0 = off[lo], b1 = off[hi], span = b1 - b0, lead = b0 & 15;
+        const uint64_t q0 = b0 >> 3, q1 = (b1 + 7) >> 3;  // bytes of the quality bit plane that cover the chunk
         CUDA_TRY(sl.d_seq.ensure(span + 96));
-        CUDA_TRY(sl.d_qual.ensure(span + 96));
+        if (!compact) CUDA_TRY(sl.d_qual.ensure(span + 96));
+        else if (qbits) CUDA_TRY(sl.d_qbits.ensure(q1 - q0 + 16));
         CUDA_TRY(sl.d_off.ensure((size_t)cn + 1));
         CUDA_TRY(sl.d_corr.ensure((size_t)cn));
         CUDA_TRY(sl.d_l.ensure((size_t)cn));
@@ -618,16 +742,19 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
         CUDA_TRY(sl.d_h.ensure((size_t)cn));
         CUDA_TRY(cudaEventRecord(sl.ev[0], sl.stream));
         CUDA_TRY(cudaMemcpyAsync(sl.d_seq.p + lead, seq_in + b0, span, cudaMemcpyHostToDevice, sl.stream));
-        CUDA_TRY(cudaMemcpyAsync(sl.d_qual.p + lead, qual + b0, span, cudaMemcpyHostToDevice, sl.stream));
+        if (!compact) CUDA_TRY(cudaMemcpyAsync(sl.d_qual.p + lead, qual + b0, span, cudaMemcpyHostToDevice, sl.stream));
+        else if (qbits) CUDA_TRY(cudaMemcpyAsync(sl.d_qbits.p, qbits + q0, q1 - q0, cudaMemcpyHostToDevice, sl.stream));
         CUDA_TRY(cudaMemcpyAsync(sl.d_off.p, off + lo, ((size_t)cn + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.stream));
         if (prev && c->chain == 1 && prev->kev_valid) CUDA_TRY(cudaStreamWaitEvent(sl.stream, prev->kev[5], 0));
         if (prev && c->chain == 2) CUDA_TRY(cudaStreamWaitEvent(sl.stream, prev->ev[3], 0));
         prev = &sl;
-        rc = launch_pipeline(c, sl, mode, cn, sl.d_seq.p + lead - b0, sl.d_qual.p + lead - b0, sl.d_off.p, b0, b1, max_len, sl.d_corr.p,
-                             sl.d_l.p, sl.d_m.p, sl.d_h.p, true);
+        rc = launch_pipeline(c, sl, mode, cn, sl.d_seq.p + lead - b0, compact ? nullptr : sl.d_qual.p + lead - b0, sl.d_off.p, b0, b1, max_len,
+                             sl.d_corr.p, sl.d_l.p, sl.d_m.p, sl.d_h.p, true, compact ? (qbits ? sl.d_qbits.p - q0 : nullptr) : nullptr,
+                             compact ? (qbits ? has_qual : 0) : 1, compact);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(sl.ev[4], sl.stream));
-        CUDA_TRY(cudaMemcpyAsync(seq_out + b0, sl.d_seq.p + lead, span, cudaMemcpyDeviceToHost, sl.stream));
+        if (!compact) CUDA_TRY(cudaMemcpyAsync(seq_out + b0, sl.d_seq.p + lead, span, cudaMemcpyDeviceToHost, sl.stream));
+        sl.edits_pending = compact;
         CUDA_TRY(cudaMemcpyAsync(correction + lo, sl.d_corr.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
         CUDA_TRY(cudaMemcpyAsync(l + lo, sl.d_l.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
         CUDA_TRY(cudaMemcpyAsync(m + lo, sl.d_m.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
@@ -635,10 +762,34 @@ extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* se
         rc = finish_enqueue(sl);
         if (rc) return rc;
     }
-    for (auto& sl : c->slot) {
-        rc = harvest(c, sl);
+    for (int j = 0; j < c->nslots; ++j) {  // oldest chunk first: `si` is the slot the next chunk would have taken
+        rc = harvest(c, c->slot[(si + j) % c->nslots]);
         if (rc) return rc;
     }
+    for (int j = 0; j < c->nslots; ++j) CUDA_TRY(cudaStreamSynchronize(c->slot[j].stream));  // (the edits of the last chunks)
+    return RCX_OK;
+}
+
+extern "C" int rcx_correct_batch(rcx_ctx* c, int mode, int64_t n, const char* seq_in, const char* qual, const uint32_t* off,
+                                 char* seq_out, int32_t* correction, int32_t* l, int32_t* m, int32_t* h) {
+    if (c) { c->cur_edits = nullptr; c->cur_edits_cap = c->cur_edits_n = 0; c->cur_edits_overflow = false; }
+    return correct_host(c, "rcx_correct_batch", mode, n, seq_in, qual, nullptr, 1, false, off, seq_out, correction, l, m, h);
+}
+
+extern "C" int rcx_correct_batch_compact(rcx_ctx* c, int mode, int64_t n, const char* seq, const uint8_t* qual_bits, int has_qual,
+                                         const uint32_t* off, int32_t* correction, int32_t* l, int32_t* m, int32_t* h, uint16_t* edits,
+                                         uint64_t edits_cap, uint64_t* n_edits) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_correct_batch_compact: null context");
+    if (!edits && edits_cap) return fail(RCX_ERR_ARG, "rcx_correct_batch_compact: null edits buffer");
+    c->cur_edits = edits; c->cur_edits_cap = edits_cap; c->cur_edits_n = 0; c->cur_edits_overflow = false;
+    if (n_edits) *n_edits = 0;
+    const int rc = correct_host(c, "rcx_correct_batch_compact", mode, n, seq, nullptr, qual_bits, has_qual ? 1 : 0, true, off, nullptr,
+                                correction, l, m, h);
+    c->cur_edits = nullptr;
+    if (rc) return rc;
+    if (n_edits) *n_edits = c->cur_edits_n;
+    if (c->cur_edits_overflow)
+        return fail(RCX_ERR_ARG, "rcx_correct_batch_compact: the edits buffer is too small (" + std::to_string(c->cur_edits_n) + " entries needed)");
     return RCX_OK;
 }
 

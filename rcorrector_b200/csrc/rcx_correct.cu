@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
 __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrectArgs a) {
     extern __shared__ unsigned int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = a.t.k, K = a.max_fix_per_k, Q = a.bad_qual;
+    const int k = a.t.k, K = a.max_fix_per_k;
     const CorLayout L = cor_layout(a.max_len, k);
     const int mw = L.mw;
     WarpMem M;
@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
         {
             if (result == -2) {
                 // ---------------- A.7 post-filters (:1296-1466)
-                const char* q = a.qual + o;
-                const int q0 = q[0];
+                const bool q0 = rcx_has_qual(a, o);
+                auto qhi = [&](int i) { return rcx_qual_high(a, o, i); };  // qual[i] > badQualityThreshold
                 int* P = M.sbuf;  // ascending positions with a fix on a non-N base
                 int np = 0;
                 #pragma unroll 1
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
                 #pragma unroll 1
                 for (int i = 1; i < np; ++i) {  // pair filter (:1314-1398)
                     const int pa = P[i - 1], pb = P[i];
-                    if (q0 != 0 && q[pb] <= Q && q[pa] <= Q) continue;
+                    if (q0 && !qhi(pb) && !qhi(pa)) continue;
                     if (pb - pa + 1 > k) continue;
                     const int lim = (i < np - 1) ? P[i + 1] - k + 1 : 0x7fffffff;  // j + k - 1 >= P[i+1]  <=>  j >= lim
                     int j0 = pa - k + 1;
@@ -515,14 +515,14 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
                     {
                         const int i = lane;
                         const bool nn = i < 10 && !getbit(M.P.mN, i);
-                        const bool f = nn && M.fix[i] != -1 && q[i] > Q;
+                        const bool f = nn && M.fix[i] != -1 && qhi(i);
                         if (__popc(__ballot_sync(RCX_FULL, f)) >= 2 && nn) M.fix[i] = -1;
                     }
                     __syncwarp();
                     {
                         const int i = len - 10 + lane;
                         const bool nn = lane < 10 && !getbit(M.P.mN, i);
-                        const bool f = nn && M.fix[i] != -1 && q[i] > Q;
+                        const bool f = nn && M.fix[i] != -1 && qhi(i);
                         if (__popc(__ballot_sync(RCX_FULL, f)) >= 3 && nn) M.fix[i] = -1;
                     }
                     __syncwarp();
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
                     for (int c = 0; (c << 5) < len; ++c) {
                         const int i = (c << 5) + lane;
                         const bool f = i < len && M.fix[i] != -1 && !getbit(M.P.mN, i);
-                        const bool good = f && q[i] > Q;
+                        const bool good = f && qhi(i);
                         const unsigned int bg = __ballot_sync(RCX_FULL, good), bb = __ballot_sync(RCX_FULL, f && !good);
                         if (lane == 0) { M.fixm[c] = bg; M.fixm[mw + c] = bb; }
                     }
@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
                         const int i = (c << 5) + lane;
                         const bool f = i < len && M.fix[i] != -1;
                         if (f) a.seq[o + i] = "ACGT"[M.fix[i]];
+                        if (a.emit_edits && i < len) a.fixbuf[o + i] = M.fix[i];  // what survived the filters, for the gather kernel
                         ret += __popc(__ballot_sync(RCX_FULL, f));
                     }
                     if (ret == 0 && bad_segments > 0) result = -1;

@@ -60,7 +60,7 @@ struct TfPend {
 template <int NW, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCorrectArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int k = a.t.k, K = a.max_fix_per_k, Q = a.bad_qual;
+    const int k = a.t.k, K = a.max_fix_per_k;
     const TfLayout LY = tf_layout(a.max_len, k, NT);
     unsigned int* cnt_all = reinterpret_cast<unsigned int*>(smem_raw);
     unsigned char* seq_all = reinterpret_cast<unsigned char*>(cnt_all + (size_t)NT * LY.cw);
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
             if (result == RCX_ST_POSTFILTER) {
                 // ---------------- A.7 post-filters (:1296-1466).  fix[] arrives as the search kernel's edit list
                 // (count, then pos / base pairs, in the read's fixbuf bytes): every filter works on the few edited positions.
-                const char* q = a.qual + o;
-                const int q0 = q[0];
+                const bool q0 = rcx_has_qual(a, o);
+                auto qhi = [&](int i) { return rcx_qual_high(a, o, i); };  // qual[i] > badQualityThreshold
                 unsigned char P[128], V[128];    // ascending positions with a fix on a non-N base, their bases (0xff = fix removed)
                 unsigned char NP[128], NV[128];  // fixes on literal-N positions (no filter touches them)
                 int np = 0, nn = 0;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                 }
                 for (int i = 1; i < np; ++i) {  // pair filter (:1314-1398)
                     const int pa = P[i - 1], pb = P[i];
-                    if (q0 != 0 && q[pb] <= Q && q[pa] <= Q) continue;
+                    if (q0 && !qhi(pb) && !qhi(pa)) continue;
                     if (pb - pa + 1 > k) continue;
                     const int lim = (i < np - 1) ? P[i + 1] - k + 1 : 0x7fffffff;  // j + k - 1 >= P[i+1]  <=>  j >= lim
                     int j0 = pa - k + 1;
@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                 }
                 if (total_fix > 3 && len > 10) {  // edge filter (:1407-1430)
                     int c = 0;
-                    for (int i = 0; i < np; ++i) c += P[i] < 10 && V[i] != 0xff && q[P[i]] > Q;
+                    for (int i = 0; i < np; ++i) c += P[i] < 10 && V[i] != 0xff && qhi(P[i]);
                     if (c >= 2)
                         for (int i = 0; i < np; ++i) if (P[i] < 10) V[i] = 0xff;
                     c = 0;
-                    for (int i = 0; i < np; ++i) c += P[i] >= len - 10 && V[i] != 0xff && q[P[i]] > Q;
+                    for (int i = 0; i < np; ++i) c += P[i] >= len - 10 && V[i] != 0xff && qhi(P[i]);
                     if (c >= 3)
                         for (int i = 0; i < np; ++i) if (P[i] >= len - 10) V[i] = 0xff;
                 }
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                     bool dense = false;
                     for (int i = 0; i < np; ++i) {
                         if (V[i] == 0xff) continue;
-                        sum += q[P[i]] > Q ? 2 : 1;
-                        while (P[i] - P[lo] >= k || V[lo] == 0xff) { if (V[lo] != 0xff) sum -= q[P[lo]] > Q ? 2 : 1; ++lo; }
+                        sum += qhi(P[i]) ? 2 : 1;
+                        while (P[i] - P[lo] >= k || V[lo] == 0xff) { if (V[lo] != 0xff) sum -= qhi(P[lo]) ? 2 : 1; ++lo; }
                         if (sum > 2 * K) dense = true;
                     }
                     if (dense) result = -1;
@@ -215,6 +215,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                     for (int i = 0; i < nn; ++i) put(NP[i], NV[i]);
                     if (ret == 0 && bad_segments > 0) result = -1;
                     else { result = ret; changed = ret > 0; }
+                    if (a.emit_edits && changed) {  // the applied edits (a subset of the list that came in) for the gather kernel
+                        signed char* fx = a.fixbuf + o;
+                        int e = 0;
+                        for (int i = 0; i < np; ++i) if (V[i] != 0xff) { fx[1 + 2 * e] = (signed char)P[i]; fx[2 + 2 * e] = (signed char)V[i]; ++e; }
+                        for (int i = 0; i < nn; ++i) { fx[1 + 2 * e] = (signed char)NP[i]; fx[2 + 2 * e] = (signed char)NV[i]; ++e; }
+                        fx[0] = (signed char)e;
+                    }
                 }
             }
             // ---------------- GetKmerInformation on the final sequence (:1567-1602).  Unchanged windows keep the count and the

@@ -14,6 +14,7 @@
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
        RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
+       RCX_C_NEDITS,                             // edits written by the gather kernel of the compact host interface
        RCX_C_SINK,                               // scratch word of the random-read micro-benchmark
        RCX_C_COUNT = RCX_C_SINK + 4 };
 
@@ -76,7 +77,21 @@ struct RcxCorrectArgs {
     signed char* dfs_path;   // search scratch: path[] per thread, interleaved by lane
     int dfs_depth, dfs_lpad;
     int compact_fix;         // fixbuf holds the search kernel's edit list per read (thread-per-item finalize) instead of a dense fix[]
+    // compact host interface (rcx_correct_batch_compact): quality as one bit per base (bit (i & 7) of byte i >> 3 for the
+    // batch's base i: qual[i] > badQualityThreshold) instead of `qual`; has_qual = "qual[0] != 0" of every read (0 for FASTA)
+    const unsigned char* qbits;
+    int has_qual;
+    int emit_edits;          // the finalize kernels leave the applied edits in fixbuf for the gather kernel
 };
+// qual[i] > badQualityThreshold for base i of the read at offset o (ErrorCorrection.cpp:1314-1316,1407-1455 read quality only so)
+__device__ __forceinline__ bool rcx_qual_high(const RcxCorrectArgs& a, uint32_t o, int i) {
+    if (a.qbits) { const unsigned long long x = (unsigned long long)o + (unsigned int)i; return (a.qbits[x >> 3] >> (x & 7)) & 1; }
+    if (!a.qual) return false;  // compact interface without quality (FASTA): every qual[i] is 0 and so is the threshold
+    return (int)a.qual[o + i] > a.bad_qual;
+}
+__device__ __forceinline__ bool rcx_has_qual(const RcxCorrectArgs& a, uint32_t o) {
+    return a.qbits ? a.has_qual != 0 : (a.qual ? a.qual[o] != 0 : false);
+}
 
 // per-work-item state in HBM (int32 words): 8-word header, then ST_SEGW words per segment
 #define ST_STATUS 0
@@ -122,6 +137,10 @@ cudaError_t rcx_launch_correct(const RcxCorrectArgs& a, int sm_count, int dfs_gr
 // thread-per-item post-filters + apply + l/m/h (rcx_finalize_thread.cu)
 bool rcx_finalize_thread_supported(int max_len, int k);
 cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);
+// compact host interface: applied edits of the changed reads gathered in record order (rcx_edits.cu)
+size_t rcx_edits_temp_bytes(long long n);
+cudaError_t rcx_launch_edits_gather(const int32_t* corr, const uint32_t* off, long long n, const signed char* fixbuf, int compact_fix,
+                                    uint32_t* scan, void* temp, size_t temp_bytes, uint16_t* edits, unsigned long long* counters, cudaStream_t s);
 // search (rcx_dfs.cu)
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int max_fix_per_k, int* grid, int* depth, int* lpad);
 size_t rcx_dfs_stack_words(int grid, int depth);

@@ -51,6 +51,14 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     return RCX_OK;
 }
 
+extern "C" int rcx_table_build_multi(rcx_ctx** ctxs, int nctx, int k, const uint64_t* fwd_codes, const int32_t* counts, uint64_t n) {
+    for (int g = 0; g < nctx; ++g) {
+        const int rc = rcx_table_build(ctxs[g], k, fwd_codes, counts, n, 0);
+        if (rc) return rc;
+    }
+    return RCX_OK;
+}
+
 extern "C" int rcx_set_params(rcx_ctx* c, const rcx_params* p) {
     if (!c || !p || !c->table || p->k != c->k) { g_err = "rcx_set_params (double): bad argument or no table"; return RCX_ERR_STATE; }
     c->params.k = p->k;

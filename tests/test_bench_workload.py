@@ -64,3 +64,47 @@ def test_stdout_carries_only_the_json_line(workdir):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
     assert r.stdout == '{"ok": 1}\n'
     assert "from-a-child" in r.stderr and "from-python" in r.stderr
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_bench_prepass_scalars_and_sample_match_the_reference(workdir, paired):
+    """bench.py derives ERROR_RATE's input order and badQualityThreshold itself (no hard-coded parameters): the records it
+    hands to rcx_estimate_error_rate are the text dump's leading records, its quality threshold is the one the reference
+    binary prints for the sample file, and the FASTQ sample is the prefix of read seed 1's shard."""
+    if not os.path.exists(T.REF_BIN):
+        pytest.skip("oracle/_ref/rcorrector not built")
+    sys.path.insert(0, ROOT)
+    import bench
+
+    argv = ["--reads", "6000", "--tx-bases", "60000", "--cpu-sample", "1000", "--workdir", os.path.join(workdir, "bw2")]
+    if paired:
+        argv += ["--paired", "--len", "150"]
+    a = bench.parse_args(argv)
+    os.makedirs(a.workdir, exist_ok=True)
+    td = bench.gen_table(a, want_dump=True, fq_limit=a.cpu_sample)
+    codes = np.fromfile(os.path.join(td, "table.codes"), dtype=np.uint64)
+    counts = np.fromfile(os.path.join(td, "table.counts"), dtype=np.int32)
+    dcodes, dcounts = T.dump_to_arrays(os.path.join(td, "table.dump"), a.k)
+    pre = bench.dump_order_prefix(codes, counts)
+    assert np.array_equal(pre, dcodes[: len(pre)]) and len(pre) == len(dcodes)  # (few records >= 1000 here: the whole order)
+    (rs, nr), = bench.shard_plan(a, 1, 0)
+    sd = bench.gen_shard(a, rs, nr)
+    qual = np.fromfile(os.path.join(sd, "reads.qual"), dtype=np.uint8)
+    seq = np.fromfile(os.path.join(sd, "reads.seq"), dtype=np.uint8)
+    off = np.fromfile(os.path.join(sd, "reads.off"), dtype=np.uint32)
+    bs = [T.read_fastq(os.path.join(td, f)) for f in (("sample.fq", "sample2.fq") if paired else ("sample.fq",))]
+    b = T.interleave(*bs) if paired else bs[0]
+    assert b.n == a.cpu_sample and np.array_equal(b.seq, seq[: off[b.n]]) and np.array_equal(b.off, off[: b.n + 1])
+    r = bench.run_reference_binary(a, td, bench.reference_sample_files(a, td, 1), 2, keep_first=True)
+    assert bench.bad_quality_threshold(qual, off, paired, a.cpu_sample) == r["bad_qual"]
+    meta = json.load(open(os.path.join(bench.keep_dir(td), "meta.json")))
+    assert meta["reads"] == a.cpu_sample and meta["bad_qual"] == r["bad_qual"]
+    # the kept *.cor.fq is what the oracle gives for the sample with the printed parameters
+    table = T.OracleTable(a.k)
+    table.put(codes, counts)
+    er = table.error_rate(os.path.join(td, "table.dump"))
+    assert "%.6f" % er == r["rate6"]
+    so, corr, l, m, h = T.oracle_correct(table, b, a.k, T.INTERLEAVED if paired else T.SINGLE, er, r["bad_qual"], a.maxcork)
+    for i in range(2 if paired else 1):
+        want = open(os.path.join(bench.keep_dir(td), "sample%s.cor.fq" % ("" if i == 0 else "2")), "rb").read()
+        assert T.format_fastq(b, so, corr, l, m, h, rows=range(i, b.n, 2) if paired else None) == want

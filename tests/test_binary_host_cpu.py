@@ -288,7 +288,8 @@ def test_binary_stops_on_reads_the_gpu_path_does_not_reproduce(double_exe, workd
     r = subprocess.run([double_exe, "-r", fq[0], "-c", dump, "-k", str(meta["k"]), "-od", od] + meta["extra"], capture_output=True,
                        env=dict(os.environ, RCX_DOUBLE_UNSUPPORTED="3"))
     assert r.returncode == 1 and b"3 reads of this batch need a case the GPU path does not reproduce" in r.stderr
-    assert os.path.getsize(os.path.join(od, meta["outputs"][0][:-3])) == 0
+    assert not os.path.exists(os.path.join(od, meta["outputs"][0][:-3]))  # no truncated *.cor.fq is left behind
+    assert not os.path.exists(od)                                          # nor the directory this run created for it
 
 
 @pytest.mark.parametrize("batch", [2, 4, 8, 16])

@@ -15,15 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "rcorrector_b200", "bin", "rcorrector")
 
 
-@pytest.fixture(scope="module")
-def gpu():
-    from rcorrector_b200 import Corrector
-
-    c = Corrector(0)
-    yield c
-    c.close()
-
-
 @pytest.mark.parametrize("name", T.golden_cases())
 def test_c_abi_reproduces_reference_bytes(gpu, name, workdir):
     meta, fq, dump, expected = T.load_golden(name, workdir)
@@ -211,3 +202,113 @@ def test_dump_parsers_agree(workdir):
                     [open(os.path.join(od, f), "rb").read() for f in sorted(os.listdir(od))]))
     assert res[0] == res[1] == res[2]
     assert res[0][2] == expected
+
+
+def _fasta_of(fq_path, out_path):
+    lines = open(fq_path, "rb").read().split(b"\n")
+    fa = []
+    for i in range(0, len(lines) - 1, 4):
+        fa += [b">" + lines[i][1:], lines[i + 1]]
+    open(out_path, "wb").write(b"\n".join(fa) + b"\n")
+
+
+@pytest.mark.parametrize("name", ["single_repeat_n", "paired_k23"])
+def test_fasta_input_through_the_product_binary(name, workdir):
+    """SURVEY §8f N4 on hardware: FASTA in -> <name>.cor.fa out.  Quality is absent (qual[0] == 0), so the finalize kernels
+    take the `no quality` side of the three post-filters.  Compared with the unmodified reference (-t 2: its -t 1 FASTA path
+    dereferences a NULL pointer) when it travelled to this box, and always with the CPU oracle fed zero qualities."""
+    meta, fq, dump, expected = T.load_golden(name, workdir)
+    w = os.path.join(workdir, "fasta_" + name)
+    os.makedirs(w, exist_ok=True)
+    fa = []
+    for i, f in enumerate(fq):
+        fa.append(os.path.join(w, "x_%d.fa" % (i + 1)))
+        _fasta_of(f, fa[-1])
+    k = meta["k"]
+    files = ["-p"] + fa if meta["paired"] else ["-r", fa[0]]
+    od = os.path.join(w, "ours")
+    r = _run(files + ["-c", dump, "-k", str(k), "-od", od, "-t", "2"] + meta["extra"])
+    assert r.returncode == 0, r.stderr.decode()
+    got = [open(os.path.join(od, "x_%d.cor.fa" % (i + 1)), "rb").read() for i in range(len(fa))]
+    # oracle: same reads with zero qualities and badQualityThreshold 0 (GetBadQuality returns 0 without quality)
+    bs = [T.read_fastq(f) for f in fq]
+    b = T.interleave(*bs) if meta["paired"] else bs[0]
+    b.qual[:] = 0
+    table = T.OracleTable(k)
+    table.load_dump(dump)
+    er = table.error_rate(dump, meta["wk"])
+    so, corr, l, m, h = T.oracle_correct(table, b, k, T.INTERLEAVED if meta["paired"] else T.SINGLE, er, 0, meta["maxcorK"])
+    for i in range(len(fa)):
+        rows = range(i, b.n, 2) if meta["paired"] else range(b.n)
+        exp = b"".join(b">" + b.ids[x][1:] + b" l:%d m:%d h:%d" % (l[x], m[x], h[x]) +
+                       (b"" if corr[x] == 0 else (b" unfixable_error" if corr[x] == -1 else b" cor")) + b"\n" +
+                       so[b.off[x]:b.off[x + 1]].tobytes() + b"\n" for x in rows)
+        assert got[i] == exp
+    ref = os.path.join(ROOT, "oracle", "_ref", "rcorrector")
+    if os.path.exists(ref):
+        odr = os.path.join(w, "ref")
+        rr = subprocess.run([ref] + files + ["-c", dump, "-k", str(k), "-od", odr, "-t", "2"] + meta["extra"], capture_output=True)
+        assert rr.returncode == 0
+        assert [open(os.path.join(odr, "x_%d.cor.fa" % (i + 1)), "rb").read() for i in range(len(fa))] == got
+        assert T.parse_ref_stderr(rr.stderr.decode()) == T.parse_ref_stderr(r.stderr.decode())
+
+
+def test_fastq_then_fasta_on_one_command_line(workdir):
+    """DESIGN §9 deviation, pinned: `-r a.fq -r b.fa` — the reference's post-filters read the stale quality bytes the FASTQ
+    records left in its batch slots for the FASTA records; here a FASTA record has no quality (zeros), whatever came
+    before it.  So each file's output equals what the file gives when it is corrected alone with the same parameters."""
+    meta, fq, dump, expected = T.load_golden("single_repeat_n", workdir)
+    w = os.path.join(workdir, "mixed")
+    os.makedirs(w, exist_ok=True)
+    fa = os.path.join(w, "b.fa")
+    _fasta_of(fq[0], fa)
+    k = str(meta["k"])
+    r = _run(["-r", fq[0], "-r", fa, "-c", dump, "-k", k, "-od", os.path.join(w, "both"), "-t", "2"])
+    assert r.returncode == 0, r.stderr.decode()
+    r1 = _run(["-r", fq[0], "-c", dump, "-k", k, "-od", os.path.join(w, "fq"), "-t", "2"])
+    bq = T.parse_ref_stderr(r1.stderr.decode())["bad_qual"]
+    assert open(os.path.join(w, "both", "reads_1.cor.fq"), "rb").read() == open(os.path.join(w, "fq", "reads_1.cor.fq"), "rb").read() == expected[0]
+    # the FASTA file alone would run with badQualityThreshold 0; after a FASTQ file it keeps the FASTQ file's threshold --
+    # without quality no post-filter compares against it, so the bytes are the same
+    r2 = _run(["-r", fa, "-c", dump, "-k", k, "-od", os.path.join(w, "fa"), "-t", "2"])
+    assert r2.returncode == 0 and bq != 0
+    assert open(os.path.join(w, "both", "b.cor.fa"), "rb").read() == open(os.path.join(w, "fa", "b.cor.fa"), "rb").read()
+
+
+def test_gpus_2_shards_a_batch_over_two_devices(workdir):
+    """-gpus 2: one host thread and one context per GPU, the table uploaded once and copied device to device, contiguous
+    record shards (mates together), output in input order — the reference's bytes."""
+    import ctypes
+
+    try:
+        n = ctypes.c_int(0)
+        cudart = ctypes.CDLL("libcudart.so")
+        cudart.cudaGetDeviceCount(ctypes.byref(n))
+        ndev = n.value
+    except OSError:
+        import torch
+        ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    for name in ("paired_k23", "paired_rate_default", "single_wk01_rate"):
+        meta, fq, dump, expected = T.load_golden(name, workdir)
+        od = os.path.join(workdir, "g2_" + name)
+        args = (["-p"] + fq if meta["paired"] else ["-r", fq[0]]) + ["-c", dump, "-k", str(meta["k"]), "-od", od, "-t", "4", "-gpus", "2"] + meta["extra"]
+        r = _run(args)
+        assert r.returncode == 0, r.stderr.decode()
+        assert T.parse_ref_stderr(r.stderr.decode()) == meta["stderr"]
+        for f, exp in zip(meta["outputs"], expected):
+            assert open(os.path.join(od, f[:-3]), "rb").read() == exp, f
+
+
+def test_unsupported_stop_leaves_no_partial_output(workdir):
+    """rcx_stats.unsupported != 0 (a read the CUDA path cannot reproduce bit for bit; forced here through the library's test
+    hook): the binary stops with an error, exit code 1, and removes the outputs it had started instead of leaving
+    truncated *.cor.fq files behind."""
+    meta, fq, dump, expected = T.load_golden("paired_k23", workdir)
+    od = os.path.join(workdir, "unsup")
+    r = subprocess.run([EXE, "-p"] + fq + ["-c", dump, "-k", str(meta["k"]), "-od", od, "-batch", "64"], capture_output=True,
+                       env=dict(os.environ, RCX_TEST_FORCE_UNSUPPORTED="3"))
+    assert r.returncode == 1
+    assert b"does not reproduce" in r.stderr
+    assert not os.path.exists(od) or os.listdir(od) == []

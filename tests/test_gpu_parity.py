@@ -22,13 +22,16 @@ CASES = [
 ]
 
 
-@pytest.fixture(scope="module")
-def gpu():
-    from rcorrector_b200 import Corrector
+def _check_compact(gpu, mode, b, bq, exp, has_qual=True):
+    """The compact host interface (one quality bit per base in, applied edits out) gives the same reads and tags."""
+    from rcorrector_b200.api import apply_edits, quality_bits
 
-    c = Corrector(0)
-    yield c
-    c.close()
+    corr, l, m, h, edits = gpu.correct_compact(mode, b.seq, quality_bits(b.qual, bq) if has_qual else None, b.off, has_qual=has_qual)
+    assert len(edits) == int(np.maximum(corr, 0).sum())
+    got = (apply_edits(b.seq, b.off, corr, edits), corr, l, m, h)
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "compact %s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
 
 
 def _load(workdir, name, k, paired, kw):
@@ -61,6 +64,7 @@ def test_correct_batch_matches_oracle(gpu, workdir, name, k, paired, maxcor, kw)
         bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
         assert len(bad) == 0, "%s: %d mismatches, first at %d (exp %r got %r)" % (nm, len(bad), bad[0], e[bad[0]], g[bad[0]])
     assert int((exp[1] > 0).sum()) > 0  # the case really exercises corrections
+    _check_compact(gpu, mode, b, bq, exp)
 
 
 @pytest.mark.parametrize("name,k,paired,maxcor,kw", CASES[:4], ids=[c[0] for c in CASES[:4]])
@@ -202,6 +206,7 @@ def test_chunked_host_batch_matches_oracle(gpu, workdir, chunk, monkeypatch):
     assert st["kernel_launches"] >= 5 * ((b.n + chunk - 1) // chunk)
     for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
         assert np.array_equal(np.asarray(e), np.asarray(g)), nm
+    _check_compact(gpu, T.INTERLEAVED, b, bq, exp)  # the chunks' edits land in chunk order
 
 
 def test_million_reads_full_pipeline(gpu, workdir):
@@ -220,6 +225,7 @@ def test_million_reads_full_pipeline(gpu, workdir):
     _os.environ["RCX_CHUNK_READS"] = "262144"
     try:
         got = gpu.correct(T.SINGLE, b.seq, b.qual, b.off)
+        _check_compact(gpu, T.SINGLE, b, bq, exp)
     finally:
         del _os.environ["RCX_CHUNK_READS"]
     st = gpu.stats()
@@ -291,6 +297,7 @@ def test_long_reads_use_the_warp_kernels(gpu, workdir):
         bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
         assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
     assert int((exp[1] > 0).sum()) > 0
+    _check_compact(gpu, T.INTERLEAVED, b, bq, exp)  # dense fix[] of the warp-per-read path
 
 
 @pytest.mark.parametrize("name,k,paired,maxcor,kw", [CASES[0], CASES[3]], ids=[CASES[0][0], CASES[3][0]])
@@ -310,3 +317,4 @@ def test_warp_kernels_on_short_reads(gpu, workdir, name, k, paired, maxcor, kw, 
     assert gpu.stats()["kernel_launches"] == 6
     for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
         assert np.array_equal(np.asarray(e), np.asarray(g)), nm
+    _check_compact(gpu, mode, b, bq, exp)

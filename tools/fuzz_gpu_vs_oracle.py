@@ -77,6 +77,14 @@ def main():
             got = gpu.correct(mode, b.seq, b.qual, b.off)
             st = gpu.stats()
             problems = []
+            # the compact host interface (quality bits in, edits out) on the same case
+            from rcorrector_b200.api import apply_edits, quality_bits
+            c_corr, c_l, c_m, c_h, c_edits = gpu.correct_compact(mode, b.seq, quality_bits(b.qual, bq), b.off)
+            st["unsupported"] += gpu.stats()["unsupported"]
+            got_c = (apply_edits(b.seq, b.off, c_corr, c_edits), c_corr, c_l, c_m, c_h)
+            for name, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got_c):
+                if not np.array_equal(np.asarray(e), np.asarray(g)):
+                    problems.append("compact " + name)
             if repr(er_gpu) != repr(er):
                 problems.append("error rate %r vs %r" % (er_gpu, er))
             for name, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):

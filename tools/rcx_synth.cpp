@@ -12,6 +12,8 @@
 // prefix of the binary buffers.
 //
 // Outputs (all optional):
+//   -cover N    reads / pairs of the whole job (default: -reads): the table's expected counts follow it, so that the
+//               shards of one job (-reads n_i -rseed s_i) share one table
 //   -rseed S    seed of the reads only (default: -seed): another shard of reads from the same transcriptome
 //   -fq1 F [-fq2 F] [-fqlimit M]  FASTQ text (first M reads/pairs only)
 //   -bin P      P.seq P.qual (concatenated, no separators) P.off (uint32[n+1]);
@@ -60,6 +62,7 @@ struct Opts {
     int txmin = 300, txmax = 2500;
     double polya = 0.3, paralog = 0.0, repeat = 0.0, chimera = 0.2, sigma = 2.0;
     long reads = 20000;  // reads (single) or pairs (paired)
+    long cover = 0;      // reads / pairs of the WHOLE job the table's expected counts follow (0: -reads); shards of one job share a table
     int len = 100;
     bool paired = false;
     double err = 0.01, nrate = 0.002, shortfrac = 0.02;
@@ -87,6 +90,7 @@ int main(int argc, char** argv) {
         else if (is("-chimera")) o.chimera = atof(argv[++i]);
         else if (is("-sigma")) o.sigma = atof(argv[++i]);
         else if (is("-reads")) o.reads = atol(argv[++i]);
+        else if (is("-cover")) o.cover = atol(argv[++i]);
         else if (is("-len")) o.len = atoi(argv[++i]);
         else if (is("-paired")) o.paired = true;
         else if (is("-err")) o.err = atof(argv[++i]);
@@ -157,7 +161,7 @@ int main(int argc, char** argv) {
     }
 
     // ---------------------------------------------------------------- reads
-    const long nrec_all = o.paired ? 2 * o.reads : o.reads;  // the table's expected coverage always uses the full workload
+    const long nrec_all = (o.paired ? 2 : 1) * (o.cover > 0 ? o.cover : o.reads);  // the table's expected coverage always uses the full workload
     if (!o.bin && o.fq1 && o.fqlimit >= 0 && o.fqlimit < o.reads) o.reads = o.fqlimit;  // FASTQ sample only: generate just that prefix
     const long nrec = o.paired ? 2 * o.reads : o.reads;
     const bool want_reads = o.bin || o.fq1;
