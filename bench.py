@@ -741,7 +741,7 @@ def measure(a, steps, warmup, world, rank, local, dist, guard_cpu_leg=True):
         "rcx_prep_kernel": {"ms": st["ms_prep"], "requests": 0, "bytes": 0, "does": "second-pass re-threshold + preparation (few reads)"},
         "rcx_dfs_kernel": {"ms": st["ms_dfs"], "requests": st["search_probes"], "nodes": st["search_nodes"],
                            "bytes": 32 * 4 * st["search_probes"] + 2 * bases, "does": "ordered correction search"},
-        "rcx_finalize_thread_kernel": {"ms": st["ms_finalize"], "requests": st["rescan_probes"], "bytes": 32 * st["rescan_probes"] + 6 * bases,
+        "rcx_finalize_thread_kernel": {"ms": st["ms_finalize"], "requests": st["rescan_probes"], "bytes": 32 * st["rescan_windows"] + 6 * bases,
                                        "does": "post-filters + apply + l/m/h"},
     }
     req_peak = rr32 / 32.0  # G requests/s

@@ -53,13 +53,15 @@ typedef struct {
     uint64_t bases;
     uint64_t scan_probes;    /* 32-byte table sector requests of the scan kernel (one answers two adjacent k-windows) */
     uint64_t search_probes;  /* requests of the correction search (one answers the four extensions of a node / jump step) */
-    uint64_t rescan_probes;  /* requests of the l/m/h re-scan (one per window that covers a changed base) */
+    uint64_t rescan_probes;  /* requests of the l/m/h re-scan (one answers two adjacent windows that cover a changed base) */
     uint64_t search_nodes;   /* SearchPaths_* node visits */
     uint64_t kernel_launches;/* CUDA kernels launched by the call (5 per chunk of a host batch) */
     float ms_scan, ms_correct, ms_total, ms_h2d, ms_d2h; /* CUDA-event times on the context's stream; ms_correct = triage..finalize */
     float ms_triage, ms_prep, ms_dfs, ms_finalize;       /* per-kernel split of ms_correct (both passes summed) */
     uint64_t work_items;     /* reads that needed the search (not all-trusted, not rejected) */
     uint64_t second_pass;    /* of those, reads that took the second pass of the A.4 loop */
+    uint64_t heavy_items;    /* of the work items, those filed as likely long searches (searched first) */
+    uint64_t rescan_windows; /* k-windows of the l/m/h re-scan (GetKmerInformation looks every one of them up) */
     uint64_t unsupported;    /* must be 0: a read that would need a third A.4 pass, a count >= 2^29, an edit-row overflow */
 } rcx_stats;
 

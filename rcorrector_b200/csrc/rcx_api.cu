@@ -98,6 +98,7 @@ struct rcx_ctx {
     unsigned long long* big_keys = nullptr;
     unsigned int* big_counts = nullptr;
     int nbig = 0;
+    bool wide_counts = false;  // some count >= 2^29: the thread-per-read kernels keep 29 bits next to their flags, so the warp-per-read ones run
     int k = 0;
     // params
     rcx_params params{};
@@ -192,6 +193,7 @@ static void free_table(rcx_ctx* c) {
     if (c->big_keys) { cudaFree(c->big_keys); c->big_keys = nullptr; }
     if (c->big_counts) { cudaFree(c->big_counts); c->big_counts = nullptr; }
     c->nbig = 0;
+    c->wide_counts = false;
     c->nlines = 0;
     c->entries = 0;
 }
@@ -354,6 +356,7 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
         std::vector<unsigned long long> sk(c->nbig);
         std::vector<unsigned int> sc(c->nbig);
         for (int i = 0; i < c->nbig; ++i) { sk[i] = bk[order[i]]; sc[i] = bc[order[i]]; }
+        for (int i = 0; i < c->nbig; ++i) if (sc[i] >= (1u << 29)) c->wide_counts = true;
         CUDA_TRY(cudaMemcpy(d_big_keys, sk.data(), c->nbig * sizeof(unsigned long long), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d_big_counts, sc.data(), c->nbig * sizeof(unsigned int), cudaMemcpyHostToDevice));
     }
@@ -537,7 +540,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         CUDA_TRY(sl.d_worklist.ensure((size_t)n + 2));
         CUDA_TRY(sl.d_worklist2.ensure((size_t)n + 2));
         CUDA_TRY(sl.d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
-        CUDA_TRY(sl.d_fixbuf.ensure(span + 96));
+        CUDA_TRY(sl.d_fixbuf.ensure(2 * (span + 96)));  // dense fix[] (1 byte per base) or 16-bit edit lists (a count + up to len - 1 edits per read)
         CUDA_TRY(sl.d_posbuf.ensure(span + 96));
     }
     CUDA_TRY(cudaMemsetAsync(sl.d_counters, 0, sizeof(unsigned long long) * RCX_C_COUNT, sl.stream));
@@ -549,11 +552,19 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     sa.correction = d_corr; sa.l = d_l; sa.m = d_m; sa.h = d_h; sa.worklist = correct ? sl.d_worklist.p : nullptr;
     sa.total_bases = end_base; sa.max_fix_per_k = c->params.max_fix_per_k;
     sa.state = correct ? sl.d_state.p : nullptr;
+    // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
+    // long reads, RCX_SCAN_WARP=1, or a table with counts of 2^29 and more: the warp-per-read kernels
+    const bool thread_scan = rcx_scan_thread_supported(max_len, c->k, d_seq) && !getenv("RCX_SCAN_WARP") && !c->wide_counts;
+    // heavy = at least 2k untrusted k-windows (one isolated error explains k of them); RCX_HEAVY_WINDOWS overrides, 0 = off
+    sa.heavy_windows = 2 * c->k;
+    if (const char* e = getenv("RCX_HEAVY_WINDOWS")) sa.heavy_windows = atoi(e);
+    if (!(thread_scan && rcx_finalize_thread_supported(max_len, c->k)))
+        sa.heavy_windows = 0;  // (the warp-per-read kernels keep one list)
     sa.posbuf = correct ? sl.d_posbuf.p + lead - first_base : nullptr;
     sa.fixbuf = correct ? sl.d_fixbuf.p + lead - first_base : nullptr;
+    sa.fixlist = correct ? reinterpret_cast<unsigned short*>(sl.d_fixbuf.p) + lead - first_base : nullptr;
     // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
     // long reads (or RCX_SCAN_WARP=1): the warp-per-read kernels
-    const bool thread_scan = rcx_scan_thread_supported(max_len, c->k, d_seq) && !getenv("RCX_SCAN_WARP");
     sa.compact_fix = (thread_scan && rcx_finalize_thread_supported(max_len, c->k)) ? 1 : 0;
     CUDA_TRY(cudaEventRecord(sl.ev[1], sl.stream));
     if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, sl.stream));
@@ -574,7 +585,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         rcx_dfs_geometry(c->sm_count, max_len, c->k, c->params.max_fix_per_k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
         CUDA_TRY(sl.d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
         CUDA_TRY(sl.d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
-        ca.posbuf = sa.posbuf; ca.dfs_stack = sl.d_dfs_stack.p; ca.dfs_path = sl.d_dfs_path.p;
+        ca.posbuf = sa.posbuf; ca.dfs_stack = sl.d_dfs_stack.p; ca.dfs_path = sl.d_dfs_path.p; ca.fixlist = sa.fixlist;
         ca.compact_fix = (thread_scan && rcx_finalize_thread_supported(max_len, c->k)) ? 1 : 0;
         CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, sl.stream, sl.kev, thread_scan));
         sl.kev_valid = true;
@@ -584,7 +595,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
             CUDA_TRY(sl.d_temp.ensure(tb));
             CUDA_TRY(sl.d_scan.ensure((size_t)n + 1));
             CUDA_TRY(sl.d_edits.ensure(span + 64));  // a read cannot have more edits than bases
-            CUDA_TRY(rcx_launch_edits_gather(d_corr, d_off, n, ca.fixbuf, ca.compact_fix, sl.d_scan.p, sl.d_temp.p, tb, sl.d_edits.p, sl.d_counters, sl.stream));
+            CUDA_TRY(rcx_launch_edits_gather(d_corr, d_off, n, ca.fixbuf, ca.compact_fix ? ca.fixlist : nullptr, sl.d_scan.p, sl.d_temp.p, tb, sl.d_edits.p, sl.d_counters, sl.stream));
             sl.launches += 1;
         }
     }
@@ -610,8 +621,10 @@ static int harvest(rcx_ctx* c, RcxSlot& sl) {
     c->stats.scan_probes += h[RCX_C_SCAN_PROBES];
     c->stats.search_probes += h[RCX_C_SEARCH_PROBES];
     c->stats.rescan_probes += h[RCX_C_RESCAN_PROBES];
+    c->stats.rescan_windows += h[RCX_C_RESCAN_WINDOWS];
     c->stats.search_nodes += h[RCX_C_SEARCH_NODES];
-    c->stats.work_items += h[RCX_C_NWORK];
+    c->stats.work_items += h[RCX_C_NWORK] + h[RCX_C_NWORKH];
+    c->stats.heavy_items += h[RCX_C_NWORKH];
     c->stats.second_pass += h[RCX_C_NWORK2];
     c->stats.unsupported += h[RCX_C_UNSUPPORTED];
     {   // test hook (tests/test_gpu_golden.py): RCX_TEST_FORCE_UNSUPPORTED=n flags the n-th harvested batch of the process

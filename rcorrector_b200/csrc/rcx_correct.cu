@@ -407,8 +407,9 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
                 const bool pr = i - k + 1 >= 0 && getbit(M.pstrict, i - k + 1), pl = getbit(M.pstrict, i);  // :343 / :577
                 a.posbuf[o + i] = (unsigned char)(rcx_base(M.P.pk, i) | (getbit(M.P.inv, i) << 2) | ((free_pos && !pr) ? 8 : 0) |
                                                   ((free_pos && !pl) ? 16 : 0));
-                a.fixbuf[o + i] = -1;
+                if (!a.compact_fix) a.fixbuf[o + i] = -1;
             }
+            if (a.compact_fix && lane == 0) a.fixlist[o] = 0;  // edit-list hand-over: an empty list
         }
         if (lane == 0) {
             st[ST_STATUS] = status; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
@@ -609,6 +610,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_finalize_kernel(RcxCorrect
     }
     n_rprobes = warp_sum_u64(n_rprobes);
     if (lane == 0 && n_rprobes) atomicAdd(&a.counters[RCX_C_RESCAN_PROBES], n_rprobes);
+    if (lane == 0 && n_rprobes) atomicAdd(&a.counters[RCX_C_RESCAN_WINDOWS], n_rprobes);  // (one window per request here)
 }
 
 static cudaError_t launch_one(void (*kern)(RcxCorrectArgs), const RcxCorrectArgs& a, int sm_count, long long items, size_t smem,

@@ -82,9 +82,12 @@ __host__ __device__ inline int dfs_cap_path(int max_len, int k, int K) {
     return c < max_len ? c : max_len;
 }
 // Shared memory holds only the edits of the CURRENT path (touched at every substitution and every pop); the accepted edits
-// of the read (2 x cap entries, written at the few terminals that improve on the best path, read once at the end) live in
-// the lane-interleaved global scratch, so the rows no longer limit the blocks per SM for long reads or a large -maxcorK
-// (150 bp: 4 -> 6 blocks; k = 31 with -maxcorK 8: 3 -> 6).
+// of the read (written at the few terminals that improve on the best path, read once at the end) live in the
+// lane-interleaved global scratch, so the rows no longer limit the blocks per SM for long reads or a large -maxcorK
+// (150 bp: 4 -> 6 blocks; k = 31 with -maxcorK 8: 3 -> 6).  Neither list can overflow: the row holds what maxFixCnt allows
+// on one path, and a path with more substitutions than that -- they are free on non-ACGT letters other than N, which the
+// read filter does not count -- continues in a spill area of the same global scratch; both global lists have max_len
+// entries (a position is edited at most once: the segments are disjoint and substitutions happen on untrusted positions).
 __host__ __device__ inline int dfs_row_entries(int max_len, int k, int K) { return dfs_cap_path(max_len, k, K) | 1; }  // odd: rows spread over the banks
 template <bool SMEM>
 __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(RcxCorrectArgs a) {
@@ -100,16 +103,19 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     }
     __syncthreads();
     const int stride = rcx_state_stride(a.max_len, k);
-    const long long nitems = (long long)a.counters[a.pass == 0 ? RCX_C_NWORK : RCX_C_NWORK2];
+    const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
+    const long long nitems = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] + nheavy : (long long)a.counters[RCX_C_NWORK2];
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
     // per-thread scratch, interleaved by lane
     const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
     unsigned int* stack = a.dfs_stack + gwarp * (long long)a.dfs_depth * DFS_FRAME * 32 + lane;
     signed char* path = a.dfs_path + gwarp * (long long)a.dfs_lpad * 32 + lane;  // dense path[] (long reads only)
-    const int cap_path = dfs_cap_path(a.max_len, k, a.max_fix_per_k);
+    const int cap_path = dfs_cap_path(a.max_len, k, a.max_fix_per_k);  // row entries; edits beyond them go to the spill area
     unsigned short* E = dfs_rows + (size_t)threadIdx.x * dfs_row_entries(a.max_len, k, a.max_fix_per_k);  // edits on the current path
     // accepted edits of the read (SMEM mode): address rebuilt at the few uses instead of a pointer kept live across the walk
 #define A(e) (reinterpret_cast<unsigned short*>(a.dfs_path + ((((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5) * (long long)a.dfs_lpad << 5)) + (threadIdx.x & 31))[(e) * 32]
+#define ESPILL(e) A(a.max_len + (e))  // entries cap_path, cap_path + 1, ... of the current path's list
+#define EGET(e) ((e) < cap_path ? (unsigned int)E[e] : (unsigned int)ESPILL((e) - cap_path))
     int ne = 0, na = 0, na_base = 0;
     bool edit_overflow = false;
 #define STK(f, w) stack[((f) * DFS_FRAME + (w)) * 32]
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             const long long w = nx_w;  // reserved while the previous item was searched
             if (w >= nitems) break;
             nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
-            item = a.pass == 0 ? w : (long long)a.worklist2[w];
+            item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy items first
             st = a.state + item * stride;
             // header (8 words) + first segment in one round trip: four independent 16-byte loads
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
@@ -198,12 +204,13 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 // the post-filters read fix[] from HBM; a read that asked for a second pass may still keep this pass' edits
                 // (no lower plateau found, :1288-1289).  fixbuf is -1 everywhere, so only the edits are written.
                 if (SMEM && (rethreshold || result == RCX_ST_POSTFILTER)) {
-                    if (a.compact_fix) {  // thread-per-item finalize: the edit list itself (count, then pos / base pairs) in the read's bytes
-                        if (1 + 2 * na_base <= len && na_base < 128) {
-                            fix[0] = (signed char)na_base;
-                            for (int e = 0; e < na_base; ++e) { const unsigned int x = A(e); fix[1 + 2 * e] = (signed char)(x & 255u); fix[2 + 2 * e] = (signed char)(x >> 8); }
+                    if (a.compact_fix) {  // thread-per-item finalize: the edit list itself (count, then pos | base << 8) in the read's words
+                        unsigned short* fl = a.fixlist + (fix - a.fixbuf);
+                        if (na_base < len) {
+                            fl[0] = (unsigned short)na_base;
+                            for (int e = 0; e < na_base; ++e) fl[1 + e] = A(e);
                         } else {
-                            edit_overflow = true;
+                            edit_overflow = true;  // cannot happen: at least one position of a work item is trusted
                         }
                     } else {
                         for (int e = 0; e < na_base; ++e) { const unsigned int x = A(e); fix[x & 255u] = (signed char)(x >> 8); }
@@ -250,8 +257,8 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     if (fc < max_fix) trial = -(max_fix - fc + 1) * RCX_MAX_TRIAL;
                     const int lo = right ? start : pos + 1, hi = right ? pos - 1 : start;
                     if (SMEM) {  // the edits of this path replace the segment's previously accepted ones
-                        if (na_base + ne <= 2 * cap_path) { for (int e = 0; e < ne; ++e) A(na_base + e) = E[e]; na = ne; }
-                        else edit_overflow = true;
+                        if (na_base + ne <= a.max_len) { for (int e = 0; e < ne; ++e) A(na_base + e) = (unsigned short)EGET(e); na = ne; }
+                        else edit_overflow = true;  // cannot happen: every position is edited at most once
                     } else {
                         for (int i = lo; i <= hi; ++i) fix[i] = PATH(i);
                     }
@@ -331,8 +338,11 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     if (here_ok && b == hb) continue;
                     const int c = dfs_sel4(b, c0, c1, c2, c3);
                     if (c >= thr) {
-                        if (SMEM) { if (ne < cap_path) E[ne] = (unsigned short)(pos | (b << 8)); else edit_overflow = true; }
-                        else PATH(pos) = (signed char)b;
+                        if (SMEM) {
+                            if (ne < cap_path) E[ne] = (unsigned short)(pos | (b << 8));
+                            else if (ne - cap_path < a.max_len) ESPILL(ne - cap_path) = (unsigned short)(pos | (b << 8));
+                            else edit_overflow = true;  // cannot happen: one substitution per position on a path
+                        } else PATH(pos) = (signed char)b;
                         ++trial;
                         ext = 1;
                         // a frame is only needed if another alternative can still pass after this one: otherwise the parent
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                             STK(sp, 7) = (unsigned int)c0; STK(sp, 8) = (unsigned int)c1; STK(sp, 9) = (unsigned int)c2; STK(sp, 10) = (unsigned int)c3;
                             ++sp;
                         }
-                        if (SMEM && ne < cap_path) ++ne;  // the substitution joins the current path (the frame keeps the count before it)
+                        if (SMEM) ++ne;  // the substitution joins the current path (the frame keeps the count before it)
                         if (right) rcx_k_append(kc, b, false, k, mask); else rcx_k_prepend(kc, b, false, k, mask);
                         if (!right) t = thr;
                         pos = right ? pos + 1 : pos - 1;
@@ -436,6 +446,8 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     }
 #undef STK
 #undef PATH
+#undef EGET
+#undef ESPILL
 #undef A
     // counters: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
@@ -469,8 +481,9 @@ void rcx_dfs_geometry(int sm_count, int max_len, int k, int K, int* grid, int* d
     int kc = max_len - k + 1;
     if (kc < 1) kc = 1;
     *depth = kc + 3;
-    // bytes per thread of the lane-interleaved scratch: the dense path[] of long reads, or the accepted edit list (2 x cap 16-bit entries)
-    *lpad = dfs_smem_rows(max_len) ? 4 * dfs_cap_path(max_len, k, K) + 4 : max_len + 2;
+    // bytes per thread of the lane-interleaved scratch: the dense path[] of long reads, or the accepted edit list + the spill area of
+    // the current path's list (max_len 16-bit entries each)
+    *lpad = dfs_smem_rows(max_len) ? 4 * max_len + 8 : max_len + 2;
 }
 size_t rcx_dfs_stack_words(int grid, int depth) { return (size_t)grid * (DFS_THREADS / 32) * depth * DFS_FRAME * 32; }
 size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREADS / 32) * lpad * 32; }

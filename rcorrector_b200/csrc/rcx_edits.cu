@@ -23,7 +23,8 @@ size_t rcx_edits_temp_bytes(long long n) {
 
 __global__ void __launch_bounds__(256) rcx_edits_gather_kernel(const int32_t* __restrict__ corr, const uint32_t* __restrict__ off, long long n,
                                                                const uint32_t* __restrict__ scan, const signed char* __restrict__ fixbuf,
-                                                               int compact_fix, uint16_t* __restrict__ edits, unsigned long long* counters) {
+                                                               const unsigned short* __restrict__ fixlist, uint16_t* __restrict__ edits,
+                                                               unsigned long long* counters) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int c = corr[r];
@@ -31,10 +32,11 @@ __global__ void __launch_bounds__(256) rcx_edits_gather_kernel(const int32_t* __
     if (c <= 0) return;
     uint16_t* out = edits + scan[r];
     const uint32_t o = off[r];
-    const signed char* fx = fixbuf + o;
-    if (compact_fix) {  // count, then position / base byte pairs
-        for (int e = 0; e < c; ++e) out[e] = (uint16_t)((unsigned char)fx[1 + 2 * e] | ((unsigned int)(unsigned char)fx[2 + 2 * e] << 10));
-    } else {            // dense fix[]: -1 = unchanged
+    if (fixlist) {  // count, then pos | base << 8
+        const unsigned short* fl = fixlist + o;
+        for (int e = 0; e < c; ++e) { const unsigned int x = fl[1 + e]; out[e] = (uint16_t)((x & 255u) | ((x >> 8) << 10)); }
+    } else {        // dense fix[]: -1 = unchanged
+        const signed char* fx = fixbuf + o;
         const int len = (int)(off[r + 1] - o);
         int e = 0;
         for (int i = 0; i < len && e < c; ++i)
@@ -42,12 +44,12 @@ __global__ void __launch_bounds__(256) rcx_edits_gather_kernel(const int32_t* __
     }
 }
 
-cudaError_t rcx_launch_edits_gather(const int32_t* corr, const uint32_t* off, long long n, const signed char* fixbuf, int compact_fix,
+cudaError_t rcx_launch_edits_gather(const int32_t* corr, const uint32_t* off, long long n, const signed char* fixbuf, const unsigned short* fixlist,
                                     uint32_t* scan, void* temp, size_t temp_bytes, uint16_t* edits, unsigned long long* counters, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     RcxPositiveIt it(corr, RcxPositive());
     cudaError_t e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, scan, (int)n, s);
     if (e != cudaSuccess) return e;
-    rcx_edits_gather_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(corr, off, n, scan, fixbuf, compact_fix, edits, counters);
+    rcx_edits_gather_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(corr, off, n, scan, fixbuf, fixlist, edits, counters);
     return cudaGetLastError();
 }

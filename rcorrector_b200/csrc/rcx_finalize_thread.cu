@@ -67,10 +67,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
     TfMeta* meta = reinterpret_cast<TfMeta*>(seq_all + (size_t)NT * LY.bw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
-    const long long nwork = (long long)a.counters[RCX_C_NWORK];
+    const long long nheavy = (long long)a.counters[RCX_C_NWORKH];
+    const long long nwork = (long long)a.counters[RCX_C_NWORK] + nheavy;
     const long long ntiles = (nwork + NT - 1) / NT;
     const int stride = rcx_state_stride(a.max_len, k);
-    unsigned int n_rprobes = 0;
+    unsigned int n_rprobes = 0, n_rwindows = 0;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long w0 = tile * NT;
@@ -79,12 +80,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
         // ---- stage: every thread fetches the metadata of its own item, then a warp copies one item at a time with
         // cp.async (global -> shared without a register round trip, so the copies of all items overlap)
         if (tid < nw) {
-            const long long rr = a.worklist[w0 + tid];
+            const long long slot = rcx_work_slot(w0 + tid, nheavy, a.n);
+            const long long rr = a.worklist[slot];
             const uint32_t oo = a.off[rr];
             meta[tid].r = (uint32_t)rr;
             meta[tid].o = oo;
             meta[tid].len = (int)(a.off[rr + 1] - oo);
-            meta[tid].status = a.state[(w0 + tid) * stride + ST_STATUS];
+            meta[tid].status = a.state[slot * stride + ST_STATUS];
         }
         __syncthreads();
         for (int t = warp; t < nw; t += NT / 32) {
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
             len = meta[tid].len;
             kcnt = len - k + 1;
             S += o & 3;
-            const int* st = a.state + (w0 + tid) * stride;
+            const int* st = a.state + rcx_work_slot(w0 + tid, nheavy, a.n) * stride;
             result = meta[tid].status;
             const int total_fix = st[ST_TOTALFIX], bad_segments = st[ST_BADSEG];
             bool changed = false;
@@ -126,15 +128,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                 // (count, then pos / base pairs, in the read's fixbuf bytes): every filter works on the few edited positions.
                 const bool q0 = rcx_has_qual(a, o);
                 auto qhi = [&](int i) { return rcx_qual_high(a, o, i); };  // qual[i] > badQualityThreshold
-                unsigned char P[128], V[128];    // ascending positions with a fix on a non-N base, their bases (0xff = fix removed)
-                unsigned char NP[128], NV[128];  // fixes on literal-N positions (no filter touches them)
+                unsigned char P[256], V[256];    // ascending positions with a fix on a non-N base, their bases (0xff = fix removed)
+                unsigned char NP[8], NV[8];      // fixes on literal-N positions (no filter touches them; a read with more than 5 N is rejected)
                 int np = 0, nn = 0;
                 {
-                    const signed char* fx = a.fixbuf + o;
-                    int cnt = (unsigned char)fx[0];
-                    if (cnt == 0xff) cnt = 0;  // fixbuf is initialised to -1: no edits
+                    const unsigned short* fl = a.fixlist + o;
+                    const int cnt = fl[0];  // at most len - 1 <= 254
                     for (int e = 0; e < cnt; ++e) {  // insertion by position (segments come in order, a Left search lists its edits downwards)
-                        const unsigned char pe = (unsigned char)fx[1 + 2 * e], be = (unsigned char)fx[2 + 2 * e];
+                        const unsigned int xe = fl[1 + e];
+                        const unsigned char pe = (unsigned char)(xe & 255u), be = (unsigned char)(xe >> 8);
                         if (S[pe] == 'N') {
                             int j = nn++;
                             while (j > 0 && NP[j - 1] > pe) { NP[j] = NP[j - 1]; NV[j] = NV[j - 1]; --j; }
@@ -216,11 +218,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                     if (ret == 0 && bad_segments > 0) result = -1;
                     else { result = ret; changed = ret > 0; }
                     if (a.emit_edits && changed) {  // the applied edits (a subset of the list that came in) for the gather kernel
-                        signed char* fx = a.fixbuf + o;
+                        unsigned short* fl = a.fixlist + o;
                         int e = 0;
-                        for (int i = 0; i < np; ++i) if (V[i] != 0xff) { fx[1 + 2 * e] = (signed char)P[i]; fx[2 + 2 * e] = (signed char)V[i]; ++e; }
-                        for (int i = 0; i < nn; ++i) { fx[1 + 2 * e] = (signed char)NP[i]; fx[2 + 2 * e] = (signed char)NV[i]; ++e; }
-                        fx[0] = (signed char)e;
+                        for (int i = 0; i < np; ++i) if (V[i] != 0xff) fl[1 + e++] = (unsigned short)(P[i] | ((unsigned int)V[i] << 8));
+                        for (int i = 0; i < nn; ++i) fl[1 + e++] = (unsigned short)(NP[i] | ((unsigned int)NV[i] << 8));
+                        fl[0] = (unsigned short)e;
                     }
                 }
             }
@@ -234,14 +236,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                     if (s0 >= kcnt) break;
                     const int e0 = need.next(s0, kcnt, false);
                     jpos = e0;
+                    n_rwindows += (unsigned int)(e0 - s0);
                     unsigned long long F = 0;
-                    int run = 0, i = s0;
+                    int run = 0, run_prev = 0, left = 0, i = s0;
                     auto append = [&]() {
                         const unsigned char ch = S[i];  // (the staged copy already holds the corrected bases)
                         const unsigned int idx = (unsigned int)ch - 'A';
                         const bool ok = idx < 26u && ((0x00080045u >> idx) & 1u);
                         const int code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3) : 3;
+                        left = (int)((F >> (2 * (k - 1))) & 3);
                         F = ((F << 2) | (unsigned long long)code) & kmask;
+                        run_prev = run;
                         run = ok ? run + 1 : 0;
                         ++i;
                     };
@@ -253,40 +258,56 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                         for (int u = 0; u < TF_DEPTH; ++u) {
                             p[u].info = -1;
                             if (j < e0) {
-                                append();  // window j = the k bases that end here
-                                if (run >= k) {  // right extension of its prefix context
+                                // like the scan: the context seq[j+1 .. j+k) answers window j (its left extension by seq[j]) and
+                                // window j+1 (its right extension by seq[j+k]) -- one sector for two windows of the run
+                                append();  // completes window j
+                                const bool pair = j + 1 < e0;
+                                bool wantL, wantR;
+                                int bl, br;
+                                if (pair) {
+                                    append();  // completes window j+1
+                                    wantL = run_prev >= k; wantR = run >= k;
+                                    bl = left; br = (int)(F & 3);
+                                    if (!wantL) row[j] = TF_INVALID;
+                                    if (!wantR) row[j + 1] = TF_INVALID;
+                                } else {  // last window of an odd run: right extension of its prefix context
+                                    wantL = false; wantR = run >= k;
+                                    bl = 0; br = (int)(F & 3);
+                                    if (!wantR) row[j] = TF_INVALID;
+                                }
+                                if (wantL || wantR) {
                                     const unsigned long long ctx = F >> 2;
                                     const unsigned long long rc = rcx_revcomp(ctx, k - 1);
                                     const bool flip = rc < ctx;
                                     p[u].key = flip ? rc : ctx;
-                                    p[u].info = j | ((int)(F & 3) << 10) | (flip ? 1 << 12 : 0);
+                                    p[u].info = (pair ? j + 1 : j) | (bl << 10) | (br << 12) | (wantL ? 1 << 14 : 0) | (wantR ? 1 << 15 : 0) | (flip ? 1 << 16 : 0);
                                     rcx_issue(a.t, __umul64hi(rcx_hash(p[u].key), a.t.nlines << 2), p[u].d);
                                     ++n_rprobes;
-                                } else {
-                                    row[j] = TF_INVALID;
                                 }
-                                ++j;
+                                j += pair ? 2 : 1;
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < TF_DEPTH; ++u) {
                             const int info = p[u].info;
                             if (info >= 0) {
-                                int c = 0;
-                                if (tf_find(a.t, p[u].key, p[u].d)) {
-                                    const bool flip = (info >> 12) & 1;
-                                    const int b = (info >> 10) & 3;
+                                const bool found = tf_find(a.t, p[u].key, p[u].d);
+                                const bool flip = (info >> 16) & 1;
+                                const int jr = info & 1023;  // window answered by the right extension
+                                auto field = [&](bool left_ext, int b) -> int {
+                                    if (!found) return 0;
                                     unsigned int f0, f1, f2, f3;
-                                    rcx_group(p[u].d, flip, f0, f1, f2, f3);  // right extension: RIGHT group, LEFT when flipped
+                                    rcx_group(p[u].d, left_ext != flip, f0, f1, f2, f3);
                                     const int bb = flip ? 3 - b : b;
                                     const unsigned int f = bb == 0 ? f0 : bb == 1 ? f1 : bb == 2 ? f2 : f3;
-                                    c = (int)f;
                                     if (f == RCX_BIG) {
                                         const unsigned long long ctx = flip ? rcx_revcomp(p[u].key, k - 1) : p[u].key;
-                                        c = rcx_big_count(a.t, rcx_canonical(rcx_ext_kmer(ctx, false, b, k), k));
+                                        return rcx_big_count(a.t, rcx_canonical(rcx_ext_kmer(ctx, left_ext, b, k), k));
                                     }
-                                }
-                                row[info & 1023] = (unsigned int)c;
+                                    return (int)f;
+                                };
+                                if (info & (1 << 14)) row[jr - 1] = (unsigned int)field(true, (info >> 10) & 3);
+                                if (info & (1 << 15)) row[jr] = (unsigned int)field(false, (info >> 12) & 3);
                             }
                         }
                     }
@@ -333,7 +354,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
         }
     }
     n_rprobes = __reduce_add_sync(RCX_FULL, n_rprobes);
+    n_rwindows = __reduce_add_sync(RCX_FULL, n_rwindows);
     if (lane == 0 && n_rprobes) atomicAdd(&a.counters[RCX_C_RESCAN_PROBES], (unsigned long long)n_rprobes);
+    if (lane == 0 && n_rwindows) atomicAdd(&a.counters[RCX_C_RESCAN_WINDOWS], (unsigned long long)n_rwindows);
 }
 
 bool rcx_finalize_thread_supported(int max_len, int k) {

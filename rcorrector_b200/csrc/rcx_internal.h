@@ -14,6 +14,8 @@
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
        RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
+       RCX_C_NWORKH,                             // HEAVY work items (long untrusted spans): slots n-1, n-2, ... of the work list, searched first
+       RCX_C_RESCAN_WINDOWS,                     // k-windows the finalize kernels looked up again (two per request on the thread path)
        RCX_C_NEDITS,                             // edits written by the gather kernel of the compact host interface
        RCX_C_SINK,                               // scratch word of the random-read micro-benchmark
        RCX_C_COUNT = RCX_C_SINK + 4 };
@@ -43,7 +45,9 @@ struct RcxScanArgs {
     int32_t* state;
     unsigned char* posbuf;
     signed char* fixbuf;
-    int compact_fix;   // only the first fixbuf byte of a read is cleared (edit-list hand-over to the thread-per-item finalize)
+    int compact_fix;   // edit-list hand-over to the thread-per-item finalize: only the count word of a read's list is cleared
+    unsigned short* fixlist;  // [off[n]] 16-bit view of the fix buffer in that mode: fixlist[off[r]] = number of edits of read r, then pos | base << 8
+    int heavy_windows; // work items with at least this many untrusted k-windows go to the heavy end of the work list (0: none)
 };
 #define RCX_TS_MAX_KCNT 232  // reads with more k-windows use the warp-per-read kernels
 
@@ -76,7 +80,8 @@ struct RcxCorrectArgs {
     unsigned int* dfs_stack; // search scratch: explicit recursion stacks, interleaved by lane
     signed char* dfs_path;   // search scratch: path[] per thread, interleaved by lane
     int dfs_depth, dfs_lpad;
-    int compact_fix;         // fixbuf holds the search kernel's edit list per read (thread-per-item finalize) instead of a dense fix[]
+    int compact_fix;         // the fix buffer holds the search kernel's edit list per read (thread-per-item finalize) instead of a dense fix[]
+    unsigned short* fixlist; // [off[n]] that list: fixlist[off[r]] = count, then pos | base << 8 (at most len - 1 edits: one position is always trusted)
     // compact host interface (rcx_correct_batch_compact): quality as one bit per base (bit (i & 7) of byte i >> 3 for the
     // batch's base i: qual[i] > badQualityThreshold) instead of `qual`; has_qual = "qual[0] != 0" of every read (0 for FASTA)
     const unsigned char* qbits;
@@ -107,6 +112,11 @@ __device__ __forceinline__ bool rcx_has_qual(const RcxCorrectArgs& a, uint32_t o
 #define RCX_ST_POSTFILTER (-2)   // searches done: post-filters decide
 #define ST_OFF 6    // off[r] and length of the read: the search kernel gets them with the header instead of chasing worklist -> off[]
 #define ST_LEN 7
+// Work-list slots.  The thread-per-read scan kernel files the items whose search is likely to be long (many untrusted
+// k-windows) from the END of the work list (slots n-1, n-2, ...; RCX_C_NWORKH of them) and the others from the front
+// (RCX_C_NWORK); the search kernel takes the heavy ones first, so that the long walks do not start when the launch is
+// nearly over.  Item number w of the RCX_C_NWORK + RCX_C_NWORKH items -> slot (= index into worklist[] and state[]).
+__host__ __device__ inline long long rcx_work_slot(long long w, long long nheavy, long long n) { return w < nheavy ? n - 1 - w : w - nheavy; }
 // multiple of 8 words: every item header is 32-byte aligned
 __host__ __device__ inline int rcx_state_stride(int max_len, int k) { return (ST_HDR + ST_SEGW * (max_len / k + 4) + 7) & ~7; }
 
@@ -139,7 +149,7 @@ bool rcx_finalize_thread_supported(int max_len, int k);
 cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cudaStream_t s);
 // compact host interface: applied edits of the changed reads gathered in record order (rcx_edits.cu)
 size_t rcx_edits_temp_bytes(long long n);
-cudaError_t rcx_launch_edits_gather(const int32_t* corr, const uint32_t* off, long long n, const signed char* fixbuf, int compact_fix,
+cudaError_t rcx_launch_edits_gather(const int32_t* corr, const uint32_t* off, long long n, const signed char* fixbuf, const unsigned short* fixlist,
                                     uint32_t* scan, void* temp, size_t temp_bytes, uint16_t* edits, unsigned long long* counters, cudaStream_t s);
 // search (rcx_dfs.cu)
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int max_fix_per_k, int* grid, int* depth, int* lpad);

@@ -349,15 +349,26 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                 a.correction[r] = result; a.l[r] = l; a.m[r] = m; a.h[r] = h;
             }
         }
-        // work-list slots: one atomic per block
+        // work-list slots: one atomic per block and class.  Items with many untrusted k-windows (more than one isolated
+        // error explains) are the candidates for long searches: they are filed from the far end of the list and searched first.
         const bool is_work = result == -2;
-        const unsigned int wb = __ballot_sync(RCX_FULL, is_work);
-        if (lane == 0) blk[warp] = __popc(wb);
+        bool heavy = false;
+        if (is_work && a.heavy_windows > 0) {
+            int nun = 0;
+            for (int j = 0; j < kcnt; ++j) {
+                const unsigned int x = row[j];
+                nun += (int)(x & TS_CMASK) < strong || (x & TS_STRICT) != 0;
+            }
+            heavy = nun >= a.heavy_windows;
+        }
+        const unsigned int wb = __ballot_sync(RCX_FULL, is_work && !heavy), wbh = __ballot_sync(RCX_FULL, is_work && heavy);
+        if (lane == 0) { blk[warp] = __popc(wb); blk[4 + warp] = __popc(wbh); }
         __syncthreads();
         if (tid == 0) {
-            int tot = 0;
-            for (int w = 0; w < NT / 32; ++w) { const int c = blk[w]; blk[w] = tot; tot += c; }
+            int tot = 0, toth = 0;
+            for (int w = 0; w < NT / 32; ++w) { const int c = blk[w]; blk[w] = tot; tot += c; const int ch = blk[4 + w]; blk[4 + w] = toth; toth += ch; }
             blk[8] = tot ? (int)atomicAdd(&a.counters[RCX_C_NWORK], (unsigned long long)tot) : 0;
+            blk[9] = toth ? (int)atomicAdd(&a.counters[RCX_C_NWORKH], (unsigned long long)toth) : 0;
         }
         __syncthreads();
 
@@ -365,7 +376,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         // Bit masks in registers (NW 64-bit words cover the read) keep the lanes of a warp in step: one uniform pass over
         // the k-mers builds them, runs and islands are then found with ffs/clz instead of per-element loops.
         if (is_work) {
-            const long long item = (long long)(unsigned int)blk[8] + blk[warp] + __popc(wb & ((1u << lane) - 1));
+            const long long item = heavy ? a.n - 1 - ((long long)(unsigned int)blk[9] + blk[4 + warp] + __popc(wbh & ((1u << lane) - 1)))
+                                         : (long long)(unsigned int)blk[8] + blk[warp] + __popc(wb & ((1u << lane) - 1));
             a.worklist[item] = (uint32_t)r;
             int* st = a.state + item * stride;
             RcxMask<NW> T, S, LOWM, M;  // trusted k-mers (:875), strict poly-A k-mers, counts <= 2 && < trust, trusted positions
@@ -499,7 +511,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         if (a.triage) {
             for (unsigned long long p = g0 + tid; p < g1; p += NT) a.posbuf[p] = bytes[p - a0] & 31;
             if (a.compact_fix) {
-                if (tid < nr) a.fixbuf[offs[tid]] = -1;  // no edits yet: the search kernel leaves its edit list here (first byte = count)
+                if (tid < nr) a.fixlist[offs[tid]] = 0;  // no edits yet: the search kernel leaves its edit list here (first word = count)
             } else {
                 for (unsigned long long p = g0 + tid; p < g1; p += NT) a.fixbuf[p] = -1;
             }

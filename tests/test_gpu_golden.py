@@ -233,7 +233,7 @@ def test_fasta_input_through_the_product_binary(name, workdir):
     # oracle: same reads with zero qualities and badQualityThreshold 0 (GetBadQuality returns 0 without quality)
     bs = [T.read_fastq(f) for f in fq]
     b = T.interleave(*bs) if meta["paired"] else bs[0]
-    b.qual[:] = 0
+    b.qual = np.zeros_like(b.qual)
     table = T.OracleTable(k)
     table.load_dump(dump)
     er = table.error_rate(dump, meta["wk"])

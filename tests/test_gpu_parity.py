@@ -318,3 +318,87 @@ def test_warp_kernels_on_short_reads(gpu, workdir, name, k, paired, maxcor, kw, 
     for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
         assert np.array_equal(np.asarray(e), np.asarray(g)), nm
     _check_compact(gpu, mode, b, bq, exp)
+
+
+# Cases the GPU-vs-oracle campaign (tools/fuzz_gpu_vs_oracle.py, first run on hardware in round 2) found: small k with
+# -maxcorK 8 puts more accepted edits on a read than the old byte-pair edit list of the search -> finalize hand-over held
+# (rcx_stats.unsupported != 0 and differing reads).  The lists are 16-bit now and cannot overflow.
+FUZZ_REGRESSIONS = [
+    (23, False, 8, 0.5, dict(seed=934166292, ntx=20, reads=800, len=150, err=0.04, nrate=0.03, paralog=0.6, repeat=0.3, polya=0.3, short=0.0, sigma=2.0, txmin=300, txmax=1200)),
+    (15, False, 8, 0.95, dict(seed=61331796, ntx=40, reads=2000, len=200, err=0.08, nrate=0.01, paralog=0.3, repeat=0.3, polya=0.3, short=0.02, sigma=2.0, txmin=300, txmax=1200)),
+    (21, False, 8, 0.95, dict(seed=6873285, ntx=8, reads=2000, len=150, err=0.08, nrate=0.0, paralog=0.0, repeat=0.3, polya=0.9, short=0.02, sigma=2.0, txmin=300, txmax=1200)),
+    (11, True, 8, 0.5, dict(seed=1014507394, ntx=20, reads=6000, len=100, err=0.003, nrate=0.03, paralog=0.0, repeat=0.3, polya=0.0, short=0.2, sigma=3.0, txmin=300, txmax=1200)),
+    (17, True, 8, 0.95, dict(seed=696262160, ntx=40, reads=6000, len=125, err=0.01, nrate=0.03, paralog=0.0, repeat=0.6, polya=0.0, short=0.2, sigma=0.5, txmin=300, txmax=2500)),
+]
+
+
+@pytest.mark.parametrize("k,paired,maxcor,wk,kw", FUZZ_REGRESSIONS, ids=["k%d_%d" % (c[0], c[4]["len"]) for c in FUZZ_REGRESSIONS])
+def test_many_accepted_edits_per_read(gpu, workdir, k, paired, maxcor, wk, kw):
+    d, bs, b, codes, counts = _load(workdir, "fz%d_%d" % (k, kw["seed"] % 1000), k, paired, kw)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"], wk)
+    bq = T.oracle_bad_quality(bs[0])
+    mode = T.INTERLEAVED if paired else T.SINGLE
+    exp = T.oracle_correct(table, b, k, mode, er, bq, maxcor)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, maxcor)
+    got = gpu.correct(mode, b.seq, b.qual, b.off)
+    assert gpu.stats()["unsupported"] == 0
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
+    _check_compact(gpu, mode, b, bq, exp)
+
+
+def test_free_substitutions_spill_the_edit_row(gpu, workdir):
+    """Substitutions on non-ACGT letters other than N are free (they do not count towards maxFixCnt) and the read filter
+    only counts N, so one search path can carry far more edits than maxFixCnt: with -maxcorK 1 and k = 31 the shared-memory
+    row of the search holds (250 / 31) * 2 + 9 = 25 of them and the rest goes to the spill area.  Reads peppered with 'R'."""
+    k, maxcor = 31, 1
+    d, bs, b, codes, counts = _load(workdir, "spill", k, False, dict(seed=77, ntx=12, reads=1500, len=250, err=0.0, nrate=0.0, txmin=600, txmax=2500, short=0.0))
+    rng = np.random.default_rng(5)
+    seq = b.seq.copy()
+    for r in range(0, b.n, 3):  # every third read: an 'R' every ~6 bases beyond the first k
+        o, e = int(b.off[r]), int(b.off[r + 1])
+        pos = o + k + np.flatnonzero(rng.random(e - o - k) < 0.16)
+        seq[pos] = ord("R")
+    b = T.Batch(b.ids, seq, b.qual, b.off)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    exp = T.oracle_correct(table, b, k, T.SINGLE, er, bq, maxcor)
+    assert int(exp[1].max()) > 30  # some read really gets more edits than the row holds
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, maxcor)
+    got = gpu.correct(T.SINGLE, b.seq, b.qual, b.off)
+    assert gpu.stats()["unsupported"] == 0
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
+    _check_compact(gpu, T.SINGLE, b, bq, exp)
+
+
+def test_counts_of_2_to_the_29_take_the_warp_kernels(gpu, workdir):
+    """A table with a count of 2^29 or more (poly-A in a very deep data set): the thread-per-read kernels keep 29 bits next to
+    their flags, so the library routes such a table to the warp-per-read kernels (full 32-bit counts) at build time
+    instead of flagging reads as unsupported."""
+    name, k, paired, maxcor, kw = CASES[1]
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    counts = counts.copy()
+    hot = np.argsort(-counts.astype(np.int64))[:50]
+    counts[hot[:10]] = 600_000_000   # >= 2^29
+    counts[hot[10:50]] = 30_000_000  # >= 2^24 - 1: the side list of saturated 24-bit fields
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    bq = T.oracle_bad_quality(bs[0])
+    exp = T.oracle_correct(table, b, k, T.SINGLE, 0.01, bq, maxcor)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, 0.01, bq, maxcor)
+    got = gpu.correct(T.SINGLE, b.seq, b.qual, b.off)
+    st = gpu.stats()
+    assert st["unsupported"] == 0 and st["kernel_launches"] == 6  # the warp-per-read kernels ran
+    assert int(np.asarray(exp[4]).max()) >= 600_000_000           # the wide count reaches an h: tag
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        assert np.array_equal(np.asarray(e), np.asarray(g)), nm
