@@ -699,6 +699,7 @@ int main(int argc, char* argv[]) {
         memset(first, 0, sizeof first);
         memset(last, 0, sizeof last);
         long total = 0;
+        std::string lastq;  // quality line of the last FASTQ record of this pass
         for (size_t fi = 0; fi < files.size() && total < 1000000; ++fi) {
             LineReader r;
             if (!r.open(files[fi].path)) continue;
@@ -706,7 +707,6 @@ int main(int argc, char* argv[]) {
             size_t n;
             bool nl;
             const int per = files[fi].type == 1 ? 4 : 2;
-            std::string seq;
             while (total < 1000000 && r.getline(p, n, nl)) {
                 size_t L = 0;
                 if (r.getline(p, n, nl)) L = n;
@@ -715,7 +715,13 @@ int main(int argc, char* argv[]) {
                     if (r.getline(p, n, nl) && L > 0 && n > 0) {
                         ++last[(unsigned char)(L - 1 < n ? p[L - 1] : 0)];
                         ++first[(unsigned char)p[0]];
+                        lastq.assign(p, n);
                     }
+                } else if (L > 0) {
+                    // a FASTA file after FASTQ ones: Reads::Next (Reads.h:186-222) leaves its quality buffer alone for a FASTA
+                    // record, so GetBadQuality counts the LAST FASTQ record's quality line again, indexed by this record's length
+                    ++last[(unsigned char)(L - 1 < lastq.size() ? lastq[L - 1] : 0)];
+                    ++first[(unsigned char)(lastq.empty() ? 0 : lastq[0])];
                 }
                 ++total;
             }

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) rcx_prep_kernel(RcxCorrectArgs
             if (a.compact_fix && lane == 0) a.fixlist[o] = 0;  // edit-list hand-over: an empty list
         }
         if (lane == 0) {
-            st[ST_STATUS] = status; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
+            st[ST_STATUS] = status; st[ST_TOTALFIX] = rcx_force_bound(strong, a.error_rate); st[ST_BADSEG] = 0;
             st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < L.nseg ? nseg : L.nseg;
             st[ST_OFF] = (int)o; st[ST_LEN] = len;
         }

@@ -120,6 +120,22 @@ __device__ __forceinline__ bool rcx_lookup_end(const RcxTable& t, RcxLookup& L) 
         if (i >= 4 * t.nlines) return false;
     }
 }
+// finish a lookup whose home sector was loaded into d: true if `key` is stored (d then holds its entry)
+static __device__ __noinline__ bool rcx_find_slow(const RcxTable& t, unsigned long long key, RcxEntryRegs& d) {
+    const unsigned long long home = __umul64hi(rcx_hash(key), t.nlines << 2);
+    for (unsigned int i = 1;; ++i) {  // rare: a key homed there lives further along the probe sequence
+        rcx_issue(t, rcx_probe_sector(t, home, i), d);
+        if (d.q0 == ~0ull) return false;
+        if ((d.q0 & RCX_KEY_MASK) == key) return true;
+        if (i >= 4 * t.nlines) return false;
+    }
+}
+__device__ __forceinline__ bool rcx_find(const RcxTable& t, unsigned long long key, RcxEntryRegs& d) {
+    if ((d.q0 & RCX_KEY_MASK) == key) return true;
+    if (d.q0 == ~0ull || !(d.q0 & RCX_OVERFLOW_BIT)) return false;
+    return rcx_find_slow(t, key, d);
+}
+__device__ __forceinline__ unsigned long long rcx_home(const RcxTable& t, unsigned long long key) { return __umul64hi(rcx_hash(key), t.nlines << 2); }
 // the four 24-bit fields of the stored RIGHT (left = false) or LEFT group
 __device__ __forceinline__ void rcx_group(const RcxEntryRegs& d, bool left, unsigned int& f0, unsigned int& f1, unsigned int& f2, unsigned int& f3) {
     const unsigned int x0 = left ? (unsigned int)(d.q2 >> 32) : (unsigned int)d.q1;
@@ -212,6 +228,18 @@ __device__ __forceinline__ double rcx_bound_d(int c, double er) {
 __device__ __forceinline__ int rcx_bound_i(int c, double er) {
     if (c < 0) return (int)0x80000000;
     return __double2int_rz(rcx_bound_d(c, er));
+}
+
+// The search kernel's "force the next round" test (ErrorCorrection.cpp:1195) compares an int with GetBound(strong) in FP64:
+// (double)x < B  <=>  x < ceil(B) for an integer x, so the preparation computes ceil(B) once per read (INT_MIN when B is
+// NaN, i.e. never) and the search compares integers.
+__device__ __forceinline__ int rcx_force_bound(int strong, double er) {
+    const double B = rcx_bound_d(strong, er);
+    if (!(B == B)) return (int)0x80000000;
+    if (B >= 2147483647.0) return 0x7fffffff;
+    int b = __double2int_rz(B);
+    if ((double)b < B) ++b;
+    return b;
 }
 
 // out-of-line copies for the (large) correction kernel: its hot loops must stay inside the instruction cache

@@ -44,6 +44,22 @@ __device__ __noinline__ void dfs_probe4(const RcxTable& t, const RcxKmer& kc, bo
     rcx_counts4(t, ctx, !right, L, found, c0, c1, c2, c3);
 }
 
+// the same from an entry already in registers: counts of the four extensions ctx+b (left = false) or b+ctx (left = true)
+__device__ __forceinline__ void dfs_counts4(const RcxTable& t, unsigned long long ctx, bool left, const RcxEntryRegs& d, bool flip, bool found,
+                                            int& c0, int& c1, int& c2, int& c3) {
+    c0 = c1 = c2 = c3 = 0;
+    if (!found) return;
+    unsigned int f0, f1, f2, f3;
+    rcx_group(d, left != flip, f0, f1, f2, f3);
+    c0 = (int)(flip ? f3 : f0); c1 = (int)(flip ? f2 : f1); c2 = (int)(flip ? f1 : f2); c3 = (int)(flip ? f0 : f3);
+    if (((f0 + 1) | (f1 + 1) | (f2 + 1) | (f3 + 1)) & 0x1000000u) {  // some field == RCX_BIG
+        if (c0 == (int)RCX_BIG) c0 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 0, t.k), t.k));
+        if (c1 == (int)RCX_BIG) c1 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 1, t.k), t.k));
+        if (c2 == (int)RCX_BIG) c2 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 2, t.k), t.k));
+        if (c3 == (int)RCX_BIG) c3 = rcx_big_count(t, rcx_canonical(rcx_ext_kmer(ctx, left, 3, t.k), t.k));
+    }
+}
+
 // InferPosThreshold (:144-173) given the four extension counts; lut[c] = max(1, (int)GetBound(c)) for small c
 __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upper, double er, const int* lut) {
     int mx = c0 > c1 ? c0 : c1;
@@ -67,6 +83,9 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #endif
 #ifndef DFS_MINBLOCKS
 #define DFS_MINBLOCKS 6
+#endif
+#ifndef DFS_AHEAD
+#define DFS_AHEAD 1  // keep-base chains: the child's sector is requested before the node's own counts are consumed
 #endif
 // SMEM (reads up to 255 bases): path[] / fix[] are kept as EDIT LISTS in shared memory.  Every accepted path of a segment
 // copies the same range path[start .. to) into fix[], and everything in that range was assigned by the nodes of the
@@ -126,7 +145,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     int* st = nullptr;
     const unsigned char* pinfo = nullptr;
     signed char* fix = nullptr;
-    int len = 0, nseg = 0, g = 0, trust = 0, strong = 0, total_fix = 0, bad_segments = 0, best_bn_all = RCX_INF;
+    int len = 0, nseg = 0, g = 0, trust = 0, fbound = 0, max_top2 = -1, total_fix = 0, bad_segments = 0, best_bn_all = RCX_INF;
     bool abort_read = false;
     long long item = 0;
     // ---- per-segment state (the by-reference parameters of SearchPaths_*)
@@ -138,6 +157,11 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     RcxKmer kc;
     kc.code = 0; kc.inv = -1;
+    // the lookup issued one node ahead (DFS_AHEAD): canonical context and its home sector, possibly still in flight
+    unsigned long long pf_key = 0;
+    RcxEntryRegs pf_d;
+    pf_d.q0 = pf_d.q1 = pf_d.q2 = pf_d.q3 = 0;
+    bool pf_on = false;
     int stage = T_FETCH;
     int4 seg0a = make_int4(0, 0, 0, 0), seg0b = make_int4(0, 0, 0, 0);
     long long nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
@@ -158,7 +182,8 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             len = h1.w;
             pinfo = a.posbuf + o;
             fix = a.fixbuf + o;
-            nseg = h1.y; trust = h1.x; strong = h0.w;
+            nseg = h1.y; trust = h1.x; fbound = h0.y;  // (ST_TOTALFIX carries rcx_force_bound(strong) in)
+            max_top2 = -1;
             na_base = 0;  // fix[] = -1 (:1113-1114): no accepted edits yet
             g = 0; total_fix = 0; bad_segments = 0; best_bn_all = RCX_INF; abort_read = false;
             stage = T_SEG;
@@ -173,11 +198,10 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 } else {
                     bool force_next = false;
                     if (nseg > 0) {
-                        int best_fix_cnt = 1;
-                        for (int s = 0; s < nseg; ++s)
-                            if (st[ST_HDR + ST_SEGW * s + 5] >= best_bn_all) best_fix_cnt *= 2;
-                        if (a.pass == 0 && (double)best_bn_all < rcx_bound_d(strong, er)) force_next = true;  // :1195 FP64 compare
-                        if (best_fix_cnt >= 2) result = -1;
+                        // :1186-1199: bestFixCnt doubles for every segment whose top2FixBottleNeck[1] reaches the read's best
+                        // bottleneck (any one of them rejects the read); the FP64 compare with GetBound(strong) as integers
+                        if (a.pass == 0 && best_bn_all < fbound) force_next = true;
+                        if (max_top2 >= best_bn_all) result = -1;
                     }
                     if (result == RCX_ST_POSTFILTER) {
                         const bool unfixable = total_fix > len;  // :1234 (never true in practice)
@@ -271,18 +295,45 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             if (leave) {
                 stage = T_POP;
             } else {
-                dfs_probe4(a.t, kc, right, mask, c0, c1, c2, c3);
-                n_probes += 1;
+                // ---- the node's sector (the four one-base extensions of kc): taken from the lookup issued ahead by the parent
+                // when it is the one (same canonical context), else issued now
+                const bool cvalid = kc.inv == -1 || (right ? kc.inv + 1 >= k : kc.inv <= 0);
+                const unsigned long long ctx = right ? (kc.code & (mask >> 2)) : (kc.code >> 2);
+                unsigned long long key = 0;
+                bool flip = false;
+                RcxEntryRegs d;
+                if (cvalid) {
+                    const unsigned long long rc = rcx_revcomp(ctx, k - 1);
+                    flip = rc < ctx;
+                    key = flip ? rc : ctx;
+                    if (DFS_AHEAD && pf_on && pf_key == key) d = pf_d;
+                    else { rcx_issue(a.t, rcx_home(a.t, key), d); n_probes += 1; }
+                }
+                const int pi = pinfo[pos];
+                // ---- one node ahead: if the read's base is kept here, the child's context is known before this node's counts
+                // arrive -- its sector travels while this node is decided (a substitution or a pop just drops it)
+                RcxKmer x = kc;
+                const int hb = pi & 3;
+                if (!(pi & 4)) { if (right) rcx_k_append(x, hb, false, k, mask); else rcx_k_prepend(x, hb, false, k, mask); }
+                if (DFS_AHEAD) {
+                    pf_on = false;
+                    const int np1 = right ? pos + 1 : pos - 1;
+                    if (!(pi & 4) && (right ? np1 < to : np1 >= to) && (x.inv == -1 || (right ? x.inv + 1 >= k : x.inv <= 0))) {
+                        const unsigned long long nctx = right ? (x.code & (mask >> 2)) : (x.code >> 2);
+                        const unsigned long long nrc = rcx_revcomp(nctx, k - 1);
+                        pf_key = nrc < nctx ? nrc : nctx;
+                        rcx_issue(a.t, rcx_home(a.t, pf_key), pf_d);
+                        n_probes += 1;  // (counted when issued: a substitution or a pop may leave it unused)
+                        pf_on = true;
+                    }
+                }
+                dfs_counts4(a.t, ctx, !right, d, flip, cvalid && rcx_find(a.t, key, d), c0, c1, c2, c3);
                 thr = dfs_infer(c0, c1, c2, c3, t, er, lut);
                 ext = 0;
                 stage = T_ALT0;
                 // ---- keep the read's base (:294-339 / :532-574)
-                const int pi = pinfo[pos];
                 if (!(pi & 4)) {
-                    const int hb = pi & 3;
                     int c = dfs_sel4(hb, c0, c1, c2, c3);
-                    RcxKmer x = kc;
-                    if (right) rcx_k_append(x, hb, false, k, mask); else rcx_k_prepend(x, hb, false, k, mask);
                     bool go = false;
                     int npos = 0, nfix = fix_cnt, nbn = bn;
                     if (c >= thr) {
@@ -419,7 +470,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
         if (stage == T_POP) {
             if (sp == 0) {
                 // ---------------- segment finished (:1162-1174)
-                st[ST_HDR + ST_SEGW * g + 5] = top2b;
+                if (top2b > max_top2) max_top2 = top2b;
                 na_base += na;  // fix[] keeps the segment's last accepted edits whether or not the segment ends "bad"
                 if (best_bn == -1) {
                     ++bad_segments;

@@ -313,15 +313,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                     }
                 }
             }
+            // GetKmerInformation takes min / median / max of the valid windows' counts with 0 -> 1: one pass normalises the
+            // row in place (an invalid window becomes INT_MAX, beyond every pivot), so the selection passes below are a load,
+            // a compare and three selects per window
             for (int j = 0; j < kcnt; ++j) {
                 const unsigned int x = row[j];
-                if (!(x & TF_INVALID)) {
-                    int v = (int)x;
-                    v = v == 0 ? 1 : v;
-                    ++nvalid;
-                    vmin = v < vmin ? v : vmin;
-                    vmax = v > vmax ? v : vmax;
-                }
+                int v = (int)x;
+                v = v == 0 ? 1 : v;
+                const bool ok = !(x & TF_INVALID);
+                nvalid += ok;
+                vmin = (ok && v < vmin) ? v : vmin;
+                vmax = (ok && v > vmax) ? v : vmax;
+                row[j] = ok ? (unsigned int)v : 0x7fffffffu;
             }
             // element [nvalid / 2] of the ascending valid counts: bisection on the value, the bounds snap to values that
             // occur (every lane of the warp needs one, so each walks its own row)
@@ -331,16 +334,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_finalize_thread_kernel(RcxCo
                 while (lo < hi) {
                     const int mid = lo + (int)(((unsigned int)hi - (unsigned int)lo) >> 1);
                     int c = 0, maxle = lo, mingt = hi;
+#pragma unroll 4
                     for (int j = 0; j < kcnt; ++j) {
-                        const unsigned int x = row[j];
-                        if (!(x & TF_INVALID)) {
-                            int v = (int)x;
-                            v = v == 0 ? 1 : v;
-                            const bool le = v <= mid;
-                            c += le;
-                            maxle = (le && v > maxle) ? v : maxle;
-                            mingt = (!le && v < mingt) ? v : mingt;
-                        }
+                        const int v = (int)row[j];
+                        const bool le = v <= mid;
+                        c += le;
+                        maxle = le ? max(maxle, v) : maxle;
+                        mingt = le ? mingt : min(mingt, v);
                     }
                     if (c > rank) hi = maxle; else lo = mingt;
                 }

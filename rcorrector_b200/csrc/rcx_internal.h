@@ -100,7 +100,7 @@ __device__ __forceinline__ bool rcx_has_qual(const RcxCorrectArgs& a, uint32_t o
 
 // per-work-item state in HBM (int32 words): 8-word header, then ST_SEGW words per segment
 #define ST_STATUS 0
-#define ST_TOTALFIX 1
+#define ST_TOTALFIX 1  // in (first pass): rcx_force_bound(strong) for the search kernel; out: totalFix
 #define ST_BADSEG 2
 #define ST_STRONG 3
 #define ST_TRUST 4

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                     B[i] = (unsigned char)((B[i] & 7) | (((ar >> b) & 1) << 3) | (((al >> b) & 1) << 4));
                 }
             }
-            st[ST_STATUS] = RCX_ST_SEARCH; st[ST_TOTALFIX] = 0; st[ST_BADSEG] = 0;
+            st[ST_STATUS] = RCX_ST_SEARCH; st[ST_TOTALFIX] = rcx_force_bound(strong, er); st[ST_BADSEG] = 0;
             st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < nseg_cap ? nseg : nseg_cap;
             st[ST_OFF] = (int)o; st[ST_LEN] = len;
         }

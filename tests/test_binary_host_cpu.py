@@ -38,6 +38,15 @@ def test_host_side_reproduces_reference_bytes(name, workdir):
     G.test_binary_is_a_drop_in(name, workdir + "_cpu")
 
 
+@pytest.mark.parametrize("name", ["single_repeat_n", "paired_k23"])
+def test_fasta_through_the_binary(name, workdir):
+    G.test_fasta_input_through_the_product_binary(name, workdir + "_cpu")
+
+
+def test_fastq_then_fasta(workdir):
+    G.test_fastq_then_fasta_on_one_command_line(workdir + "_cpu")
+
+
 def test_modes(workdir):
     G.test_binary_modes_match(workdir + "_cpu")
 
