@@ -25,7 +25,7 @@
 #define DFS_FRAME 11
 #define DFS_LUT 1024
 
-enum { T_FETCH = 0, T_SEG = 1, T_ENTER = 2, T_ALT0 = 3 /* ..T_ALT0+3 */, T_JUMP = 7, T_POP = 8 };
+enum { T_FETCH = 0, T_SEG = 1, T_ENTER = 2, T_ALT0 = 3 /* ..T_ALT0+3 */, T_JUMP = 7, T_POP = 8, T_IDLE = 9 };
 
 __device__ __forceinline__ int dfs_sel4(int b, int c0, int c1, int c2, int c3) { return b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3; }
 
@@ -85,7 +85,18 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #define DFS_MINBLOCKS 6
 #endif
 #ifndef DFS_AHEAD
-#define DFS_AHEAD 1  // keep-base chains: the child's sector is requested before the node's own counts are consumed
+// 1: keep-base chains request the child's sector before the node's own counts are consumed.  Measured slower (10 M x 100 bp:
+// search 21.6 -> 25.5 ms at 6 blocks / SM, 24.8 at 5; 150-bp pairs 121 -> 143 ms; k = 31 / -maxcorK 8 56 -> 66 ms,
+// profiles/r02_c): 11 more live registers and 5 % more requests cost more than the latency they hide -- six warps per
+// scheduler already cover it; the kernel is bound by instruction issue under divergence, not by memory latency.
+#define DFS_AHEAD 0
+#endif
+#ifndef DFS_BATCH
+// 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
+// taken by a whole warp at a time, 32 consecutive slots, and a lane that finishes waits for the others: items of one
+// batch take nearly the same walk, so the lanes go through fetch / segment / alternative / pop together instead of one or
+// two at a time.  The heavy items (first) and the second pass keep the per-lane dynamic fetch.
+#define DFS_BATCH 1
 #endif
 // SMEM (reads up to 255 bases): path[] / fix[] are kept as EDIT LISTS in shared memory.  Every accepted path of a segment
 // copies the same range path[start .. to) into fix[], and everything in that range was assigned by the nodes of the
@@ -122,8 +133,12 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     }
     __syncthreads();
     const int stride = rcx_state_stride(a.max_len, k);
+    // items taken one by one by the lanes (heavy ones of the first pass, everything of the second) and items taken by
+    // whole warps (light ones of the first pass)
     const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
-    const long long nitems = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] + nheavy : (long long)a.counters[RCX_C_NWORK2];
+    const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
+    const long long ndyn = a.pass == 0 ? (DFS_BATCH ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
+    const long long nbatch = (a.pass == 0 && DFS_BATCH) ? nlight : 0;
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
     // per-thread scratch, interleaved by lane
     const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
@@ -167,17 +182,34 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     long long nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
 
     for (;;) {
+        bool have_item = false;
         if (stage == T_FETCH) {
-            const long long w = nx_w;  // reserved while the previous item was searched
-            if (w >= nitems) break;
-            nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
-            item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy items first
+            if (nx_w < ndyn) {  // reserved while the previous item was searched
+                const long long w = nx_w;
+                nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
+                item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy items first
+                have_item = true;
+            } else {
+                stage = T_IDLE;
+            }
+        }
+        {   // every lane comes by here once per trip: when the whole warp is out of work it takes the next 32 light items
+            const unsigned int idle = __ballot_sync(RCX_FULL, stage == T_IDLE);
+            if (idle == RCX_FULL) {
+                long long base = 0;
+                if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKX0], 32ull);
+                base = __shfl_sync(RCX_FULL, base, 0);
+                if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
+                if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
+            }
+        }
+        if (have_item) {
             st = a.state + item * stride;
             // header (8 words) + first segment in one round trip: four independent 16-byte loads
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
             seg0a = *reinterpret_cast<const int4*>(st + 8);
             seg0b = *reinterpret_cast<const int4*>(st + 12);
-            if (h0.x != RCX_ST_SEARCH) continue;  // decided by the prep kernel
+            if (h0.x != RCX_ST_SEARCH) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass): next one
             const uint32_t o = (uint32_t)h1.z;    // ST_OFF / ST_LEN: written with the header, no worklist -> off[] chase
             len = h1.w;
             pinfo = a.posbuf + o;

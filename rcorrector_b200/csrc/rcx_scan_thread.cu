@@ -34,6 +34,7 @@
 #define TB_N 32
 #define TB_STRONG 64
 
+#define TS_BINS 256  // per-tile counting sort of the work items by their number of untrusted k-windows (<= RCX_TS_MAX_KCNT)
 struct TsLayout {
     int cw;         // words per count row (odd)
     int bytes_cap;  // staged bases
@@ -45,7 +46,7 @@ __host__ __device__ inline TsLayout ts_layout(int max_len, int k, int nt) {
     if (kc < 1) kc = 1;
     L.cw = kc | 1;
     L.bytes_cap = ((nt * max_len + 15) & ~15) + 32;
-    L.smem = sizeof(uint32_t) * (nt + 4) + sizeof(int) * 16 + sizeof(int) * (size_t)nt * L.cw + (size_t)L.bytes_cap;
+    L.smem = sizeof(uint32_t) * (nt + 4) + sizeof(int) * (16 + TS_BINS) + sizeof(int) * (size_t)nt * L.cw + (size_t)L.bytes_cap;
     return L;
 }
 bool rcx_scan_thread_supported(int max_len, int k, const void* seq) {
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
     const TsLayout LY = ts_layout(a.max_len, k, NT);
     uint32_t* offs = reinterpret_cast<uint32_t*>(smem_raw);                       // [T + 1] (+3 pad)
     int* blk = reinterpret_cast<int*>(offs + NT + 4);                     // [16] block scratch
-    unsigned int* cnt_all = reinterpret_cast<unsigned int*>(blk + 16);            // [T][cw]
+    int* bins = blk + 16;                                                 // [TS_BINS] work items of the tile per untrusted-window count
+    unsigned int* cnt_all = reinterpret_cast<unsigned int*>(bins + TS_BINS);      // [T][cw]
     unsigned char* bytes = reinterpret_cast<unsigned char*>(cnt_all + (size_t)NT * LY.cw);  // 16-byte aligned (all sizes above are multiples of 16)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         const int nr = (int)((a.n - r0) < NT ? (a.n - r0) : NT);
         __syncthreads();  // previous tile fully written out
         for (int t = tid; t <= nr; t += NT) offs[t] = a.off[r0 + t];
+        for (int t = tid; t < TS_BINS; t += NT) bins[t] = 0;
         __syncthreads();
         const unsigned long long g0 = offs[0], g1 = offs[nr];
         const unsigned long long a0 = g0 & ~15ull;
@@ -351,24 +354,39 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         }
         // work-list slots: one atomic per block and class.  Items with many untrusted k-windows (more than one isolated
         // error explains) are the candidates for long searches: they are filed from the far end of the list and searched first.
+        // The others are filed sorted by that number within the tile (counting sort in shared memory): the search kernel takes
+        // them 32 consecutive slots per warp, and items with the same number of untrusted windows take nearly the same walk.
         const bool is_work = result == -2;
         bool heavy = false;
-        if (is_work && a.heavy_windows > 0) {
-            int nun = 0;
+        int nun = 0, pos_in_bin = 0;
+        if (is_work) {
             for (int j = 0; j < kcnt; ++j) {
                 const unsigned int x = row[j];
                 nun += (int)(x & TS_CMASK) < strong || (x & TS_STRICT) != 0;
             }
-            heavy = nun >= a.heavy_windows;
+            heavy = a.heavy_windows > 0 && nun >= a.heavy_windows;
+            if (nun >= TS_BINS) nun = TS_BINS - 1;
+            if (!heavy) pos_in_bin = atomicAdd(&bins[nun], 1);
         }
-        const unsigned int wb = __ballot_sync(RCX_FULL, is_work && !heavy), wbh = __ballot_sync(RCX_FULL, is_work && heavy);
-        if (lane == 0) { blk[warp] = __popc(wb); blk[4 + warp] = __popc(wbh); }
+        const unsigned int wbh = __ballot_sync(RCX_FULL, is_work && heavy);
+        if (lane == 0) blk[4 + warp] = __popc(wbh);
         __syncthreads();
-        if (tid == 0) {
-            int tot = 0, toth = 0;
-            for (int w = 0; w < NT / 32; ++w) { const int c = blk[w]; blk[w] = tot; tot += c; const int ch = blk[4 + w]; blk[4 + w] = toth; toth += ch; }
-            blk[8] = tot ? (int)atomicAdd(&a.counters[RCX_C_NWORK], (unsigned long long)tot) : 0;
-            blk[9] = toth ? (int)atomicAdd(&a.counters[RCX_C_NWORKH], (unsigned long long)toth) : 0;
+        if (warp == 0) {  // exclusive prefix over the bins (TS_BINS / 32 per lane), total = light items of the tile
+            int v[TS_BINS / 32], sum = 0;
+#pragma unroll
+            for (int q = 0; q < TS_BINS / 32; ++q) { v[q] = bins[lane * (TS_BINS / 32) + q]; sum += v[q]; }
+            int incl = sum;
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y = __shfl_up_sync(RCX_FULL, incl, o2); if (lane >= o2) incl += y; }
+            int run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < TS_BINS / 32; ++q) { bins[lane * (TS_BINS / 32) + q] = run; run += v[q]; }
+            const int tot = __shfl_sync(RCX_FULL, incl, 31);
+            if (lane == 0) {
+                int toth = 0;
+                for (int w = 0; w < NT / 32; ++w) { const int ch = blk[4 + w]; blk[4 + w] = toth; toth += ch; }
+                blk[8] = tot ? (int)atomicAdd(&a.counters[RCX_C_NWORK], (unsigned long long)tot) : 0;
+                blk[9] = toth ? (int)atomicAdd(&a.counters[RCX_C_NWORKH], (unsigned long long)toth) : 0;
+            }
         }
         __syncthreads();
 
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         // the k-mers builds them, runs and islands are then found with ffs/clz instead of per-element loops.
         if (is_work) {
             const long long item = heavy ? a.n - 1 - ((long long)(unsigned int)blk[9] + blk[4 + warp] + __popc(wbh & ((1u << lane) - 1)))
-                                         : (long long)(unsigned int)blk[8] + blk[warp] + __popc(wb & ((1u << lane) - 1));
+                                         : (long long)(unsigned int)blk[8] + bins[nun] + pos_in_bin;
             a.worklist[item] = (uint32_t)r;
             int* st = a.state + item * stride;
             RcxMask<NW> T, S, LOWM, M;  // trusted k-mers (:875), strict poly-A k-mers, counts <= 2 && < trust, trusted positions

@@ -2,7 +2,8 @@
 """End-to-end timing of the drop-in `rcorrector` binary against the reference binary on the same generated files
 (GPU box).  Prints one JSON object: per-phase wall times from the timestamps of the stderr lines both binaries print
 (`Stored`, `Weak kmer`, `Bad quality`, `Processed`), output md5s (must be equal).
-usage: python tools/binary_round.py [reads] [ntx] [len] [paired 0/1] [extra args for ours...]"""
+usage: python tools/binary_round.py [reads] [ntx] [len] [paired 0/1] [extra args for ours...]
+       several variants of ours in one run (the reference runs once): ... [paired 0/1] -- -gpus 1 -- -gpus 8"""
 import hashlib
 import json
 import os
@@ -53,6 +54,17 @@ def main():
     rlen = int(sys.argv[3]) if len(sys.argv) > 3 else 100
     paired = len(sys.argv) > 4 and sys.argv[4] == "1"
     extra = sys.argv[5:]
+    variants = []
+    if "--" in extra:  # several argument sets for ours
+        cur = None
+        for x in extra:
+            if x == "--":
+                cur = []
+                variants.append(cur)
+            elif cur is not None:
+                cur.append(x)
+    else:
+        variants = [extra]
     d = "/dev/shm/rcx_binary_round"
     os.makedirs(d, exist_ok=True)
     k = 23
@@ -69,7 +81,8 @@ def main():
     res = {"reads": reads * (2 if paired else 1), "len": rlen, "k": k, "cores": cores, "generate_s": gen_s,
            "dump_bytes": os.path.getsize(os.path.join(d, "t.dump")), "fastq_bytes": os.path.getsize(os.path.join(d, "r_1.fq")) * (2 if paired else 1)}
     outs = {}
-    for name, binary, more in (("reference", REF, []), ("ours", OURS, extra)):
+    runs = [("reference", REF, [])] + [("ours" if i == 0 else "ours_%d" % i, OURS, v) for i, v in enumerate(variants)]
+    for name, binary, more in runs:
         od = os.path.join(d, "out_" + name)
         os.makedirs(od, exist_ok=True)
         m = run_timed([binary] + files + ["-c", os.path.join(d, "t.dump"), "-k", str(k), "-od", od, "-t", str(cores)] + more)
@@ -81,8 +94,9 @@ def main():
         m["reads_per_s_whole_run"] = res["reads"] / max(m["exit"], 1e-9)
         outs[name] = sorted(os.path.join(od, f) for f in os.listdir(od))
         m["md5"] = [md5(f) for f in outs[name]]
+        m["args"] = more
         res[name] = m
-    res["identical_output"] = res["reference"]["md5"] == res["ours"]["md5"]
+    res["identical_output"] = all(res["reference"]["md5"] == res[n]["md5"] for n, _, _ in runs[1:])
     res["speedup_correct_phase"] = res["reference"]["correct_s"] / max(res["ours"]["correct_s"], 1e-9)
     res["speedup_whole_run"] = res["reference"]["exit"] / max(res["ours"]["exit"], 1e-9)
     print(json.dumps(res))

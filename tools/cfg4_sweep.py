@@ -3,8 +3,8 @@
 k-mers, k = 23, 150-bp reads.   usage (GPU box): python tools/cfg4_sweep.py [--kmers 64,256,1000] [--reads 20000000]
 
 Everything is generated ON THE GPU (no 27 GB text dump, no host arrays): a random "transcriptome" of G bases whose G-k+1
-windows are the table's k-mers (distinct for k = 23 up to a handful of collisions: 4^23 = 7e13), counts uniform in
-[2, 200); reads are 150-bp windows of the same sequence with 1 % substitutions, so the scan meets stored contexts on the
+windows are the table's k-mers (distinct for k = 23 up to a handful of collisions: 4^23 = 7e13), counts following a
+log-normal expression level per ~1 500-base stretch; reads are 150-bp windows of the same sequence with 1 % substitutions, so the scan meets stored contexts on the
 clean windows and absent ones around every error, like the bench workload does.  The reads go through the WHOLE device
 path (rcx_correct_batch_device), so K1 runs in the mode it runs in production (thresholds, triage, preparation fused);
 its CUDA-event time, its sector requests and the random-request rate of the same table (rcx_measure_random_read) are
@@ -54,7 +54,13 @@ def main():
         codes = torch.zeros(nk, dtype=torch.int64, device=dev)
         for j in range(k):  # forward code of window i: first base in the highest bits (KmerCode::Append)
             codes.mul_(4).add_(genome[j:j + nk])
-        counts = torch.randint(2, 200, (nk,), dtype=torch.int32, device=dev, generator=g)
+        # counts like a transcriptome's: one expression level per ~1 500-base "transcript" (log-normal), +-15 % noise per k-mer,
+        # never below 2 -- neighbouring windows of a clean read agree, so clean reads leave at the triage like real ones do
+        nblk = (nk + 1499) // 1500
+        level = torch.exp(3.3 + 1.3 * torch.randn(nblk, device=dev, generator=g))
+        counts = level.repeat_interleave(1500)[:nk] * (0.85 + 0.3 * torch.rand(nk, device=dev, generator=g))
+        counts = counts.clamp_(2, 2e9).round_().to(torch.int32)
+        del level
         # reads: windows of the sequence, substitutions at rate err, constant quality
         starts = torch.randint(0, G - L, (n,), dtype=torch.int64, device=dev, generator=g)
         seq = torch.empty((n, L), dtype=torch.uint8, device=dev)
