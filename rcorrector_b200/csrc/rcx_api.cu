@@ -587,6 +587,8 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         CUDA_TRY(sl.d_dfs_path.ensure(rcx_dfs_path_bytes(dfs_grid, ca.dfs_lpad)));
         ca.posbuf = sa.posbuf; ca.dfs_stack = sl.d_dfs_stack.p; ca.dfs_path = sl.d_dfs_path.p; ca.fixlist = sa.fixlist;
         ca.compact_fix = (thread_scan && rcx_finalize_thread_supported(max_len, c->k)) ? 1 : 0;
+        ca.dfs_batch = (thread_scan && max_len <= 128) ? 1 : 0;  // the scan sorted the light items within 128-read tiles
+        if (const char* e = getenv("RCX_DFS_BATCH")) ca.dfs_batch = atoi(e);
         CUDA_TRY(rcx_launch_correct(ca, c->sm_count, dfs_grid, sl.stream, sl.kev, thread_scan));
         sl.kev_valid = true;
         sl.launches = thread_scan ? 5 : 6;  // scan (+ thresholds + triage [+ first preparation]), search, preparation + search of the second pass, finalize
@@ -733,9 +735,9 @@ static int correct_host(rcx_ctx* c, const char* who, int mode, int64_t n, const 
     }
     int si = 0;
     RcxSlot* prev = nullptr;
-    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci, si = (si + 1) % c->nslots) {
+    for (size_t ci = 0; ci + 1 < cuts.size(); ++ci) {
         const int64_t lo = cuts[ci], hi = cuts[ci + 1], cn = hi - lo;
-        if (cn <= 0) continue;
+        if (cn <= 0) continue;  // (an empty chunk must not advance the slot: the harvests below rely on the slot order)
         int32_t max_len = 0;
         rc = scan_lengths(off + lo, cn, &max_len);
         if (rc) return rc;
@@ -774,6 +776,7 @@ static int correct_host(rcx_ctx* c, const char* who, int mode, int64_t n, const 
         CUDA_TRY(cudaMemcpyAsync(h + lo, sl.d_h.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, sl.stream));
         rc = finish_enqueue(sl);
         if (rc) return rc;
+        si = (si + 1) % c->nslots;
     }
     for (int j = 0; j < c->nslots; ++j) {  // oldest chunk first: `si` is the slot the next chunk would have taken
         rc = harvest(c, c->slot[(si + j) % c->nslots]);

@@ -95,7 +95,10 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 // 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
 // taken by a whole warp at a time, 32 consecutive slots, and a lane that finishes waits for the others: items of one
 // batch take nearly the same walk, so the lanes go through fetch / segment / alternative / pop together instead of one or
-// two at a time.  The heavy items (first) and the second pass keep the per-lane dynamic fetch.
+// two at a time.  The heavy items (first) and the second pass keep the per-lane dynamic fetch.  Measured (profiles/r02_d):
+// with the scan's 128-read tiles (reads up to 128 bases) search 18.7 -> 16.8 ms per 10 M reads; with its 64-read tiles the
+// sorted runs are too short for homogeneous batches and batches lose (150-bp pairs 104 -> 115 ms, k = 31 / -maxcorK 8
+// 51 -> 56 ms): the launcher asks for batches only in the first case (RcxCorrectArgs::dfs_batch).
 #define DFS_BATCH 1
 #endif
 // SMEM (reads up to 255 bases): path[] / fix[] are kept as EDIT LISTS in shared memory.  Every accepted path of a segment
@@ -137,8 +140,9 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     // whole warps (light ones of the first pass)
     const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
     const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
-    const long long ndyn = a.pass == 0 ? (DFS_BATCH ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
-    const long long nbatch = (a.pass == 0 && DFS_BATCH) ? nlight : 0;
+    const bool batch = DFS_BATCH && a.dfs_batch && a.pass == 0;
+    const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
+    const long long nbatch = batch ? nlight : 0;
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
     // per-thread scratch, interleaved by lane
     const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             const unsigned int idle = __ballot_sync(RCX_FULL, stage == T_IDLE);
             if (idle == RCX_FULL) {
                 long long base = 0;
-                if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKX0], 32ull);
+                if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
                 base = __shfl_sync(RCX_FULL, base, 0);
                 if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
                 if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }

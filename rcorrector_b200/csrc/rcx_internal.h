@@ -14,6 +14,7 @@
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
        RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
+       RCX_C_WORKB,                              // search kernel: next batch of 32 light items
        RCX_C_NWORKH,                             // HEAVY work items (long untrusted spans): slots n-1, n-2, ... of the work list, searched first
        RCX_C_RESCAN_WINDOWS,                     // k-windows the finalize kernels looked up again (two per request on the thread path)
        RCX_C_NEDITS,                             // edits written by the gather kernel of the compact host interface
@@ -80,6 +81,7 @@ struct RcxCorrectArgs {
     unsigned int* dfs_stack; // search scratch: explicit recursion stacks, interleaved by lane
     signed char* dfs_path;   // search scratch: path[] per thread, interleaved by lane
     int dfs_depth, dfs_lpad;
+    int dfs_batch;           // search kernel: light items of the first pass are taken 32 consecutive slots per warp
     int compact_fix;         // the fix buffer holds the search kernel's edit list per read (thread-per-item finalize) instead of a dense fix[]
     unsigned short* fixlist; // [off[n]] that list: fixlist[off[r]] = count, then pos | base << 8 (at most len - 1 edits: one position is always trusted)
     // compact host interface (rcx_correct_batch_compact): quality as one bit per base (bit (i & 7) of byte i >> 3 for the
