@@ -122,7 +122,7 @@ __host__ __device__ inline int dfs_cap_path(int max_len, int k, int K) {
 // read filter does not count -- continues in a spill area of the same global scratch; both global lists have max_len
 // entries (a position is edited at most once: the segments are disjoint and substitutions happen on untrusted positions).
 __host__ __device__ inline int dfs_row_entries(int max_len, int k, int K) { return dfs_cap_path(max_len, k, K) | 1; }  // odd: rows spread over the banks
-template <bool SMEM>
+template <bool SMEM, bool BATCH>
 __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(RcxCorrectArgs a) {
     __shared__ int lut[DFS_LUT];
     extern __shared__ __align__(16) unsigned short dfs_rows[];
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     // whole warps (light ones of the first pass)
     const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
     const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
-    const bool batch = DFS_BATCH && a.dfs_batch && a.pass == 0;
+    const bool batch = BATCH && a.pass == 0;
     const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
     const long long nbatch = batch ? nlight : 0;
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
@@ -558,10 +558,14 @@ void rcx_dfs_geometry(int sm_count, int max_len, int k, int K, int* grid, int* d
     const size_t smem = dfs_smem_bytes(max_len, k, K);
     cudaError_t e;
     if (dfs_smem_rows(max_len)) {
-        cudaFuncSetAttribute(rcx_dfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<true>, DFS_THREADS, smem);
+        cudaFuncSetAttribute(rcx_dfs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(rcx_dfs_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<true, false>, DFS_THREADS, smem);
+        int per_sm_b = 0;
+        if (e == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, rcx_dfs_kernel<true, true>, DFS_THREADS, smem) == cudaSuccess &&
+            per_sm_b < per_sm) per_sm = per_sm_b;  // one grid (and scratch) size for both
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<false>, DFS_THREADS, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<false, false>, DFS_THREADS, 0);
     }
     if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     *grid = sm_count * per_sm;
@@ -576,7 +580,12 @@ size_t rcx_dfs_stack_words(int grid, int depth) { return (size_t)grid * (DFS_THR
 size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREADS / 32) * lpad * 32; }
 
 cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s) {
-    if (dfs_smem_rows(a.max_len)) rcx_dfs_kernel<true><<<grid, DFS_THREADS, dfs_smem_bytes(a.max_len, a.t.k, a.max_fix_per_k), s>>>(a);
-    else rcx_dfs_kernel<false><<<grid, DFS_THREADS, 0, s>>>(a);
+    const size_t smem = dfs_smem_bytes(a.max_len, a.t.k, a.max_fix_per_k);
+    if (dfs_smem_rows(a.max_len)) {
+        if (DFS_BATCH && a.dfs_batch && a.pass == 0) rcx_dfs_kernel<true, true><<<grid, DFS_THREADS, smem, s>>>(a);
+        else rcx_dfs_kernel<true, false><<<grid, DFS_THREADS, smem, s>>>(a);
+    } else {
+        rcx_dfs_kernel<false, false><<<grid, DFS_THREADS, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
