@@ -20,7 +20,7 @@ except Exception as e:
 P
 tail -3 $OUT/bench_n$N.err
 timeout 300 python -m pytest tests/test_gpu_golden.py -q -k "gpus_2" > $OUT/pytest_gpus2.log 2>&1; echo "pytest -gpus 2 rc=$?"; tail -2 $OUT/pytest_gpus2.log
-RCX_TIMING=1 timeout 600 python tools/binary_round.py 3000000 20000 150 1 -- -gpus 1 -- -gpus $N > $OUT/binary_gpus$N.json 2> $OUT/binary_gpus$N.err; echo "binary rc=$?"
+RCX_TIMING=1 timeout 600 python tools/binary_round.py ${BR_PAIRS:-3000000} ${BR_NTX:-20000} 150 1 -- -gpus 1 -- -gpus $N > $OUT/binary_gpus$N.json 2> $OUT/binary_gpus$N.err; echo "binary rc=$?"
 python - $OUT/binary_gpus$N.json <<'P'
 import json,sys
 try:
@@ -33,7 +33,7 @@ except Exception as e:
 P
 if [ "$N" == "8" ]; then
   for g in 0 1 2 3 4 5 6 7; do
-    CUDA_VISIBLE_DEVICES=$g timeout 500 python tools/cfg4_sweep.py --kmers 256,1000 --steps 2 --out $OUT/cfg4_gpu$g.json > /dev/null 2> $OUT/cfg4_gpu$g.err &
+    CUDA_VISIBLE_DEVICES=$g timeout 500 python tools/cfg4_sweep.py --kmers 1000 --steps 2 --out $OUT/cfg4_gpu$g.json > /dev/null 2> $OUT/cfg4_gpu$g.err &
   done
   wait
   echo "cfg4 x8 done"; grep -h "reads_per_s" $OUT/cfg4_gpu0.json | head -3
