@@ -93,6 +93,18 @@ int rcx_table_lookup(rcx_ctx* ctx, const uint64_t* fwd_codes, int32_t* counts_ou
 /* number of distinct canonical k-mers stored, 32-byte sectors allocated (one (k-1)-mer context each), bytes of HBM */
 int rcx_table_info(rcx_ctx* ctx, uint64_t* entries, uint64_t* slots, uint64_t* bytes);
 
+/* ---- the k-mer counting stages of run_rcorrector.pl (:262-281: `jellyfish bc`, `jellyfish count -C --bc`,
+ * `jellyfish dump -L 2`) on the GPU.  begin() opens an empty counting table; add() counts the canonical k-mers of a batch of
+ * reads (same layout as rcx_correct_batch: host pointers, every record of every input file, mates included; windows that
+ * hold a non-ACGT letter are skipped); finish() keeps the k-mers seen at least min_count times (2 = `dump -L 2`) and
+ * builds the count table from them on the device -- no text dump in between.  The kept (canonical code, count) records can
+ * be read back with export() (the order is the counting table's slot order: deterministic, but not Jellyfish's), e.g. for
+ * rcx_estimate_error_rate.  capacity_hint = expected distinct k-mers (0: start small; the table grows as needed). */
+int rcx_count_kmers_begin(rcx_ctx* ctx, int k, uint64_t capacity_hint);
+int rcx_count_kmers_add(rcx_ctx* ctx, int64_t n, const char* seq, const uint32_t* off);
+int rcx_count_kmers_finish(rcx_ctx* ctx, int32_t min_count, uint64_t* kept, uint64_t* distinct, uint64_t* instances);
+int rcx_count_kmers_export(rcx_ctx* ctx, uint64_t* codes_out, int32_t* counts_out, uint64_t n);
+
 int rcx_set_params(rcx_ctx* ctx, const rcx_params* p);
 
 /* ---- the hot path: ErrorCorrection_Thread run to completion over one batch

@@ -18,7 +18,7 @@ SINGLE, INTERLEAVED = 0, 1
 # every symbol include/rcx.h declares
 SYMBOLS = [
     "rcx_abi_version", "rcx_last_error", "rcx_create", "rcx_destroy", "rcx_table_build", "rcx_table_build_multi", "rcx_table_lookup",
-    "rcx_table_info", "rcx_set_params", "rcx_correct_batch", "rcx_correct_batch_compact", "rcx_correct_batch_device", "rcx_sync",
+    "rcx_table_info", "rcx_count_kmers_begin", "rcx_count_kmers_add", "rcx_count_kmers_finish", "rcx_count_kmers_export", "rcx_set_params", "rcx_correct_batch", "rcx_correct_batch_compact", "rcx_correct_batch_device", "rcx_sync",
     "rcx_scan_batch", "rcx_get_stats", "rcx_debug_counters", "rcx_measure_random_read", "rcx_stream", "rcx_host_alloc", "rcx_host_free", "rcx_estimate_error_rate",
 ]
 
@@ -64,6 +64,10 @@ def load_library():
     lib.rcx_table_build_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, vp, u64]
     lib.rcx_table_lookup.argtypes = [vp, vp, vp, u64]
     lib.rcx_table_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    lib.rcx_count_kmers_begin.argtypes = [vp, C.c_int, u64]
+    lib.rcx_count_kmers_add.argtypes = [vp, i64, vp, vp]
+    lib.rcx_count_kmers_finish.argtypes = [vp, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    lib.rcx_count_kmers_export.argtypes = [vp, vp, vp, u64]
     lib.rcx_set_params.argtypes = [vp, C.POINTER(RcxParams)]
     lib.rcx_correct_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rcx_correct_batch_compact.argtypes = [vp, C.c_int, i64, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
@@ -131,6 +135,22 @@ class Corrector:
             n = len(codes)
         self._check(self.lib.rcx_table_build(self.h, k, _ptr(codes), _ptr(counts), n, 1 if on_device else 0))
         self.k = k
+
+    def count_kmers(self, k, batches, min_count=2, capacity_hint=0):
+        """count the canonical k-mers of `batches` (iterable of (seq, off) host arrays) on the GPU, keep those seen
+        at least min_count times and build the count table from them.  Returns (codes, counts, distinct, instances)."""
+        self._check(self.lib.rcx_count_kmers_begin(self.h, k, capacity_hint))
+        for seq, off in batches:
+            seq = np.ascontiguousarray(seq, dtype=np.uint8)
+            off = np.ascontiguousarray(off, dtype=np.uint32)
+            self._check(self.lib.rcx_count_kmers_add(self.h, len(off) - 1, _ptr(seq), _ptr(off)))
+        kept, distinct, inst = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.rcx_count_kmers_finish(self.h, min_count, C.byref(kept), C.byref(distinct), C.byref(inst)))
+        codes = np.zeros(kept.value, dtype=np.uint64)
+        counts = np.zeros(kept.value, dtype=np.int32)
+        self._check(self.lib.rcx_count_kmers_export(self.h, _ptr(codes), _ptr(counts), kept.value))
+        self.k = k
+        return codes, counts, distinct.value, inst.value
 
     def table_info(self):
         e, s, b = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -12,7 +12,9 @@
 // order.  There is no CPU correction path: without a GPU it exits 1.
 //
 // Extra options (not in the reference): -gpus N (default 1; env RCX_GPUS),
-// -batch N (records per pipeline batch, default 1M).
+// -batch N (records per pipeline batch, default 1M), -countkmers (instead of
+// -c: count the k-mers of the input files on the GPU, SURVEY 8f N3 -- what
+// run_rcorrector.pl's stages 0-2 ask Jellyfish for).
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -600,7 +602,7 @@ static void correct_on_gpus(std::vector<Gpu>& gpus, int mode, HostBatch& b) {
 int main(int argc, char* argv[]) {
     int k = 23, threads = 1, max_fix_per_k = 4, ngpu = 1;
     double wk = 0.95;
-    bool to_stdout = false;
+    bool to_stdout = false, count_kmers = false;
     const char* dump_path = nullptr;
     std::string od = "./";
     size_t batch_reads = 1u << 20;  // records per pipeline batch (3 pinned buffers cycle through read -> correct -> write)
@@ -623,15 +625,16 @@ int main(int argc, char* argv[]) {
         else if (!strcmp("-stdout", argv[i])) { to_stdout = true; }
         else if (!strcmp("-verbose", argv[i])) { /* per-read trace to stdout: not produced */ }
         else if (!strcmp("-gpus", argv[i])) { ngpu = atoi(argv[i + 1]); ++i; }
+        else if (!strcmp("-countkmers", argv[i])) { count_kmers = true; }
         else if (!strcmp("-batch", argv[i])) { batch_reads = (size_t)atol(argv[i + 1]); ++i; }
         else if (!strcmp("-h", argv[i])) { print_help(); exit(0); }
         else { fprintf(stderr, "Unknown argument: %s\n", argv[i]); exit(0); }
     }
-    if (!dump_path) {
+    if (!dump_path && !count_kmers) {
         fprintf(stderr, "Could not open file (no -c jf_dump given)\n");
         exit(1);
     }
-    {
+    if (dump_path) {
         FILE* t = fopen(dump_path, "r");
         if (!t) {
             fprintf(stderr, "Could not open file %s\n", dump_path);
@@ -763,10 +766,53 @@ int main(int argc, char* argv[]) {
         for (auto& st : sets) st.b.alloc(batch_reads, cap_bases);
     });
     Dump dump;
-    load_dump(dump_path, k, dump, threads);
-    tmark("dump parsed");
+    if (dump_path) {
+        load_dump(dump_path, k, dump, threads);
+        tmark("dump parsed");
+    }
     gpus_ready.wait();
     tmark("CUDA contexts ready");
+    if (!dump_path) {
+        // -countkmers: what `jellyfish count -C` + `dump -L 2` would have handed over -- the canonical k-mers
+        // of every input file (mates included) seen at least twice -- counted on the first GPU.  Sequence lines only.
+        rcx_ctx* c0 = gpus[0].ctx;
+        if (rcx_count_kmers_begin(c0, k, 0)) die_rcx("rcx_count_kmers_begin");
+        std::vector<char> cs;
+        std::vector<uint32_t> co(1, 0);
+        auto flush = [&]() {
+            if (co.size() > 1 && rcx_count_kmers_add(c0, (int64_t)co.size() - 1, cs.data(), co.data())) die_rcx("rcx_count_kmers_add");
+            cs.clear();
+            co.assign(1, 0);
+        };
+        auto count_file = [&](const std::string& path, int type) {
+            LineReader r;
+            if (!r.open(path)) { fprintf(stderr, "ERROR: Could not access file %s\n", path.c_str()); exit(1); }
+            const char* p;
+            size_t n;
+            bool nl;
+            while (r.getline(p, n, nl)) {      // id line
+                if (!r.getline(p, n, nl)) break;  // sequence line
+                cs.insert(cs.end(), p, p + n);
+                co.push_back((uint32_t)cs.size());
+                if (type == 1) { r.getline(p, n, nl); r.getline(p, n, nl); }  // '+' and quality lines
+                if (cs.size() > (256u << 20)) flush();
+            }
+        };
+        for (auto& f : files) {
+            count_file(f.path, f.type);
+            if (f.paired) count_file(f.mate_path, sniff_type(f.mate_path));
+        }
+        flush();
+        uint64_t kept = 0, distinct = 0, instances = 0;
+        if (rcx_count_kmers_finish(c0, 2, &kept, &distinct, &instances)) die_rcx("rcx_count_kmers_finish");
+        dump.codes.resize(kept);
+        dump.counts.resize(kept);
+        if (rcx_count_kmers_export(c0, dump.codes.data(), dump.counts.data(), kept)) die_rcx("rcx_count_kmers_export");
+        dump.stored = (int64_t)kept;
+        dump.rate_records = kept;
+        tmark("k-mers counted");
+    }
+    if (dump_path || ngpu > 1)
     {   // one upload over PCIe, device-to-device copies to the other GPUs (NVLink), local inserts in parallel
         std::vector<rcx_ctx*> ctxs;
         for (auto& g : gpus) ctxs.push_back(g.ctx);

@@ -107,6 +107,15 @@ struct rcx_ctx {
     int nslots = 3;  // slots a host batch cycles through (RCX_SLOTS)
     int chain = 0;   // RCX_CHAIN: 1 = a chunk's kernels start when the previous chunk has reached its finalize kernel, 2 = when it is done
     rcx_stats stats{};
+    // k-mer counting (rcx_count_kmers_*): the counting table, and after finish() the kept records
+    unsigned long long* cnt_keys = nullptr;
+    unsigned int* cnt_counts = nullptr;
+    unsigned long long cnt_cap = 0, cnt_occupied = 0, cnt_instances = 0;
+    unsigned long long* cnt_stat = nullptr;  // device: [0] occupied slots, [1] k-mer instances
+    int cnt_k = 0;
+    unsigned long long* kept_codes = nullptr;
+    int32_t* kept_counts = nullptr;
+    unsigned long long kept_n = 0;
     // the compact call in progress: where the chunks' edits go (harvest appends them in chunk order)
     uint16_t* cur_edits = nullptr;
     uint64_t cur_edits_cap = 0, cur_edits_n = 0;
@@ -148,12 +157,14 @@ extern "C" int rcx_create(int device, rcx_ctx** out) {
 }
 
 static void free_table(rcx_ctx* c);
+static void count_release(rcx_ctx* c, bool kept_too);
 
 extern "C" void rcx_destroy(rcx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& sl : c->slot) if (sl.stream) cudaStreamSynchronize(sl.stream);
     free_table(c);
+    count_release(c, true);
     for (auto& sl : c->slot) {
         sl.release();
         if (sl.d_counters) cudaFree(sl.d_counters);
@@ -450,6 +461,146 @@ extern "C" int rcx_table_build_multi(rcx_ctx** ctxs, int nctx, int k, const uint
     for (auto& t : th) t.join();
     release();
     for (int g = 0; g < nctx; ++g) if (rcs[g]) return fail(rcs[g], errs[g]);
+    return RCX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ k-mer counting (N3)
+static void count_release(rcx_ctx* c, bool kept_too) {
+    if (c->cnt_keys) { cudaFree(c->cnt_keys); c->cnt_keys = nullptr; }
+    if (c->cnt_counts) { cudaFree(c->cnt_counts); c->cnt_counts = nullptr; }
+    if (c->cnt_stat) { cudaFree(c->cnt_stat); c->cnt_stat = nullptr; }
+    c->cnt_cap = c->cnt_occupied = c->cnt_instances = 0;
+    if (kept_too) {
+        if (c->kept_codes) { cudaFree(c->kept_codes); c->kept_codes = nullptr; }
+        if (c->kept_counts) { cudaFree(c->kept_counts); c->kept_counts = nullptr; }
+        c->kept_n = 0;
+    }
+}
+static int count_alloc(rcx_ctx* c, unsigned long long cap, unsigned long long** keys, unsigned int** counts) {
+    *keys = nullptr; *counts = nullptr;
+    CUDA_TRY(cudaMalloc(keys, cap * sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc(counts, cap * sizeof(unsigned int));
+    if (e != cudaSuccess) { cudaFree(*keys); *keys = nullptr; return fail(RCX_ERR_NOMEM, "rcx_count_kmers: the counting table does not fit the device memory"); }
+    CUDA_TRY(rcx_launch_count_init(*keys, *counts, cap, c->stream));
+    return RCX_OK;
+}
+extern "C" int rcx_count_kmers_begin(rcx_ctx* c, int k, uint64_t capacity_hint) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_count_kmers_begin: null context");
+    if (k < 2 || k > RCX_MAX_K) return fail(RCX_ERR_ARG, "rcx_count_kmers_begin: k must be in [2, 32]");
+    CUDA_TRY(cudaSetDevice(c->device));
+    count_release(c, true);
+    c->cnt_k = k;
+    c->cnt_cap = std::max<unsigned long long>(1ull << 20, 2 * (unsigned long long)capacity_hint + 1024);
+    int rc = count_alloc(c, c->cnt_cap, &c->cnt_keys, &c->cnt_counts);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(&c->cnt_stat, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(c->cnt_stat, 0, 2 * sizeof(unsigned long long), c->stream));
+    return RCX_OK;
+}
+extern "C" int rcx_count_kmers_add(rcx_ctx* c, int64_t n, const char* seq, const uint32_t* off) {
+    if (!c || !c->cnt_keys) return fail(RCX_ERR_STATE, "rcx_count_kmers_add: rcx_count_kmers_begin first");
+    if (n < 0 || (n && (!seq || !off))) return fail(RCX_ERR_ARG, "rcx_count_kmers_add: bad arguments");
+    if (n == 0) return RCX_OK;
+    if (off[0] != 0) return fail(RCX_ERR_ARG, "rcx_count_kmers_add: off[0] must be 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+    RcxSlot& sl = c->slot[0];
+    int rc = harvest(c, sl);
+    if (rc) return rc;
+    // chunks of at most 2^28 bases: the table is kept at most half full BEFORE a chunk that could add one k-mer per base
+    const int k = c->cnt_k;
+    int64_t lo = 0;
+    while (lo < n) {
+        int64_t hi = lo;
+        while (hi < n && (uint64_t)(off[hi + 1] - off[lo]) <= (1ull << 28)) ++hi;
+        if (hi == lo) hi = lo + 1;
+        const uint64_t b0 = off[lo], span = off[hi] - b0;
+        const unsigned long long worst = c->cnt_occupied + span;  // every window a new k-mer
+        if (2 * worst > c->cnt_cap) {  // grow by re-insertion
+            unsigned long long ncap = c->cnt_cap;
+            while (2 * worst > ncap) ncap *= 2;
+            unsigned long long* nk = nullptr;
+            unsigned int* nc = nullptr;
+            rc = count_alloc(c, ncap, &nk, &nc);
+            if (rc) return rc;
+            CUDA_TRY(rcx_launch_count_rehash(c->cnt_keys, c->cnt_counts, c->cnt_cap, nk, nc, ncap, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(c->cnt_keys); cudaFree(c->cnt_counts);
+            c->cnt_keys = nk; c->cnt_counts = nc; c->cnt_cap = ncap;
+        }
+        CUDA_TRY(sl.d_seq.ensure(span + 96));
+        CUDA_TRY(sl.d_off.ensure((size_t)(hi - lo) + 1));
+        CUDA_TRY(cudaMemcpyAsync(sl.d_seq.p, seq + b0, span, cudaMemcpyHostToDevice, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.d_off.p, off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.stream));
+        CUDA_TRY(rcx_launch_count_reads(sl.d_seq.p - b0, sl.d_off.p, hi - lo, k, c->cnt_keys, c->cnt_counts, c->cnt_cap, c->cnt_stat, c->sm_count, sl.stream));
+        unsigned long long h_stat[2];
+        CUDA_TRY(cudaMemcpyAsync(h_stat, c->cnt_stat, sizeof h_stat, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        c->cnt_occupied = h_stat[0];
+        c->cnt_instances = h_stat[1];
+        lo = hi;
+    }
+    return RCX_OK;
+}
+extern "C" int rcx_count_kmers_finish(rcx_ctx* c, int32_t min_count, uint64_t* kept, uint64_t* distinct, uint64_t* instances) {
+    if (!c || !c->cnt_keys) return fail(RCX_ERR_STATE, "rcx_count_kmers_finish: rcx_count_kmers_begin first");
+    if (min_count < 1) min_count = 1;
+    CUDA_TRY(cudaSetDevice(c->device));
+    // stable selection in slot order, a window of slots at a time: count, then allocate, then scatter
+    const unsigned long long win = 1ull << 27;
+    unsigned int *flags = nullptr, *pos = nullptr;
+    void* temp = nullptr;
+    const size_t tb = rcx_count_select_temp_bytes(win);
+    CUDA_TRY(cudaMalloc(&flags, win * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&pos, win * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&temp, tb));
+    auto cleanup = [&]() { cudaFree(flags); cudaFree(pos); cudaFree(temp); };
+    unsigned long long total = 0;
+    std::vector<unsigned long long> base;
+    for (int pass = 0; pass < 2; ++pass) {
+        unsigned long long run = 0;
+        size_t wi = 0;
+        for (unsigned long long lo = 0; lo < c->cnt_cap; lo += win, ++wi) {
+            const unsigned long long n = std::min(win, c->cnt_cap - lo);
+            cudaError_t e = rcx_launch_count_select(c->cnt_keys, c->cnt_counts, lo, n, (unsigned int)min_count, flags, pos, temp, tb,
+                                                    pass ? base[wi] : 0, pass ? c->kept_codes : nullptr, pass ? c->kept_counts : nullptr, c->stream);
+            if (e != cudaSuccess) { cleanup(); return fail(RCX_ERR_CUDA, std::string("rcx_count_kmers_finish: ") + cudaGetErrorString(e)); }
+            if (!pass) {
+                unsigned int last_pos = 0, last_flag = 0;
+                cudaMemcpyAsync(&last_pos, pos + (n - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream);
+                cudaMemcpyAsync(&last_flag, flags + (n - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream);
+                if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cleanup(); return fail(RCX_ERR_CUDA, "rcx_count_kmers_finish: selection failed"); }
+                base.push_back(run);
+                run += (unsigned long long)last_pos + last_flag;
+            }
+        }
+        if (!pass) {
+            total = run;
+            if (c->kept_codes) { cudaFree(c->kept_codes); c->kept_codes = nullptr; }
+            if (c->kept_counts) { cudaFree(c->kept_counts); c->kept_counts = nullptr; }
+            if (cudaMalloc(&c->kept_codes, std::max<unsigned long long>(total, 1) * sizeof(unsigned long long)) != cudaSuccess ||
+                cudaMalloc(&c->kept_counts, std::max<unsigned long long>(total, 1) * sizeof(int32_t)) != cudaSuccess) {
+                cleanup();
+                return fail(RCX_ERR_NOMEM, "rcx_count_kmers_finish: the kept k-mers do not fit the device memory");
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cleanup();
+    c->kept_n = total;
+    if (kept) *kept = total;
+    if (distinct) *distinct = c->cnt_occupied;
+    if (instances) *instances = c->cnt_instances;
+    const int k = c->cnt_k;
+    count_release(c, false);  // the counting table makes room for the count table
+    return rcx_table_build(c, k, (const uint64_t*)c->kept_codes, c->kept_counts, total, 1);
+}
+extern "C" int rcx_count_kmers_export(rcx_ctx* c, uint64_t* codes_out, int32_t* counts_out, uint64_t n) {
+    if (!c) return fail(RCX_ERR_ARG, "rcx_count_kmers_export: null context");
+    if (n > c->kept_n) return fail(RCX_ERR_ARG, "rcx_count_kmers_export: more records asked for than kept");
+    if (n == 0) return RCX_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (codes_out) CUDA_TRY(cudaMemcpy(codes_out, c->kept_codes, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (counts_out) CUDA_TRY(cudaMemcpy(counts_out, c->kept_counts, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return RCX_OK;
 }
 

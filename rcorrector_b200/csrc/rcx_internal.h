@@ -153,6 +153,16 @@ cudaError_t rcx_launch_finalize_thread(const RcxCorrectArgs& a, int sm_count, cu
 size_t rcx_edits_temp_bytes(long long n);
 cudaError_t rcx_launch_edits_gather(const int32_t* corr, const uint32_t* off, long long n, const signed char* fixbuf, const unsigned short* fixlist,
                                     uint32_t* scan, void* temp, size_t temp_bytes, uint16_t* edits, unsigned long long* counters, cudaStream_t s);
+// k-mer counting, SURVEY 8f N3 (rcx_count.cu)
+cudaError_t rcx_launch_count_init(unsigned long long* keys, unsigned int* counts, unsigned long long cap, cudaStream_t s);
+cudaError_t rcx_launch_count_reads(const char* seq, const uint32_t* off, long long n, int k, unsigned long long* keys, unsigned int* counts,
+                                   unsigned long long cap, unsigned long long* stat, int sm_count, cudaStream_t s);
+cudaError_t rcx_launch_count_rehash(const unsigned long long* okeys, const unsigned int* ocounts, unsigned long long ocap, unsigned long long* keys,
+                                    unsigned int* counts, unsigned long long cap, cudaStream_t s);
+size_t rcx_count_select_temp_bytes(unsigned long long n);
+cudaError_t rcx_launch_count_select(const unsigned long long* keys, const unsigned int* counts, unsigned long long lo, unsigned long long n,
+                                    unsigned int min_count, unsigned int* flags, unsigned int* pos, void* temp, size_t temp_bytes,
+                                    unsigned long long base, unsigned long long* out_codes, int32_t* out_counts, cudaStream_t s);
 // search (rcx_dfs.cu)
 void rcx_dfs_geometry(int sm_count, int max_len, int k, int max_fix_per_k, int* grid, int* depth, int* lpad);
 size_t rcx_dfs_stack_words(int grid, int depth);

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rcx.h"
@@ -56,6 +57,52 @@ extern "C" int rcx_table_build_multi(rcx_ctx** ctxs, int nctx, int k, const uint
         const int rc = rcx_table_build(ctxs[g], k, fwd_codes, counts, n, 0);
         if (rc) return rc;
     }
+    return RCX_OK;
+}
+
+// -countkmers on the CPU (exact canonical counts; the product counts on the GPU, rcx_count.cu)
+static std::unordered_map<uint64_t, uint32_t> g_cnt;
+static std::vector<uint64_t> g_kept_codes;
+static std::vector<int32_t> g_kept_counts;
+static int g_cnt_k = 0;
+extern "C" int rcx_count_kmers_begin(rcx_ctx* c, int k, uint64_t) {
+    if (!c || k < 2 || k > RCX_MAX_K) { g_err = "rcx_count_kmers_begin (double): bad argument"; return RCX_ERR_ARG; }
+    g_cnt.clear(); g_cnt_k = k;
+    return RCX_OK;
+}
+extern "C" int rcx_count_kmers_add(rcx_ctx*, int64_t n, const char* seq, const uint32_t* off) {
+    const int k = g_cnt_k;
+    const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    for (int64_t r = 0; r < n; ++r) {
+        uint64_t fw = 0, rv = 0;
+        int run = 0;
+        for (uint32_t i = off[r]; i < off[r + 1]; ++i) {
+            const char ch = seq[i];
+            const int v = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+            fw = ((fw << 2) | (uint64_t)(v & 3)) & mask;
+            rv = (rv >> 2) | ((uint64_t)(3 - (v & 3)) << (2 * (k - 1)));
+            run = v >= 0 ? run + 1 : 0;
+            if (run >= k) ++g_cnt[fw < rv ? fw : rv];
+        }
+    }
+    return RCX_OK;
+}
+extern "C" int rcx_count_kmers_finish(rcx_ctx* c, int32_t min_count, uint64_t* kept, uint64_t* distinct, uint64_t* instances) {
+    g_kept_codes.clear(); g_kept_counts.clear();
+    uint64_t inst = 0;
+    for (auto& kv : g_cnt) {
+        inst += kv.second;
+        if ((int64_t)kv.second >= min_count) { g_kept_codes.push_back(kv.first); g_kept_counts.push_back((int32_t)kv.second); }
+    }
+    if (kept) *kept = g_kept_codes.size();
+    if (distinct) *distinct = g_cnt.size();
+    if (instances) *instances = inst;
+    return rcx_table_build(c, g_cnt_k, g_kept_codes.data(), g_kept_counts.data(), g_kept_codes.size(), 0);
+}
+extern "C" int rcx_count_kmers_export(rcx_ctx*, uint64_t* codes_out, int32_t* counts_out, uint64_t n) {
+    if (n > g_kept_codes.size()) return RCX_ERR_ARG;
+    if (codes_out) memcpy(codes_out, g_kept_codes.data(), n * sizeof(uint64_t));
+    if (counts_out) memcpy(counts_out, g_kept_counts.data(), n * sizeof(int32_t));
     return RCX_OK;
 }
 

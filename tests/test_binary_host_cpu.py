@@ -47,6 +47,15 @@ def test_fastq_then_fasta(workdir):
     G.test_fastq_then_fasta_on_one_command_line(workdir + "_cpu")
 
 
+def test_countkmers_through_the_binary(workdir):
+    """-countkmers: the binary's own pass over the input files (sequence lines of every file, mates included) feeds the
+    counter; with the exact counts the rest of the run is the fixture's."""
+    import test_gpu_count as GC
+
+    GC.EXE = G.EXE
+    GC.test_binary_counts_its_own_kmers(workdir + "_cpu")
+
+
 def test_modes(workdir):
     G.test_binary_modes_match(workdir + "_cpu")
 
