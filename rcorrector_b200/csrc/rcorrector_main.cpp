@@ -741,6 +741,13 @@ int main(int argc, char* argv[]) {
     });
 
     // ---- GPUs and table
+    // On a multi-GPU host the CUDA runtime initialises every visible device at the first call (several seconds for eight):
+    // unless the user chose the devices, only the first -gpus N are made visible to this process.
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string vis;
+        for (int g = 0; g < ngpu; ++g) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
     // CUDA context creation and the pinned batch buffers overlap the parsing of the dump
     std::vector<Gpu> gpus(ngpu);
     std::future<void> gpus_ready = std::async(std::launch::async, [&]() {
