@@ -26,6 +26,7 @@
 #include <cstring>
 #include <ctime>
 #include <future>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -375,7 +376,51 @@ static bool read_record(LineReader& r, int type, HostBatch& b, Chunk& c, const s
     return true;
 }
 
-// Reads.h:360-421 OutputBatch for records [lo, hi) of the batch (stride/start select one mate of an interleaved batch)
+// Reads.h:360-421 OutputBatch for records [lo, hi) of the batch (stride/start select one mate of an interleaved batch),
+// written through a sink: a byte counter (the size of a piece is known before its place in the file is reserved), a raw
+// pointer into the mapped output file, or a string (gzip members, streams).
+struct CountSink {
+    size_t n = 0;
+    void put(const char*, size_t len) { n += len; }
+    void ch(char) { ++n; }
+};
+struct PtrSink {
+    char* p;
+    void put(const char* s, size_t len) { memcpy(p, s, len); p += len; }
+    void ch(char c) { *p++ = c; }
+};
+struct StringSink {
+    std::string& out;
+    void put(const char* s, size_t len) { out.append(s, len); }
+    void ch(char c) { out.push_back(c); }
+};
+template <class Sink>
+static void emit_records(Sink& out, const HostBatch& b, const Chunk& c, int type, size_t lo, size_t hi, size_t stride) {
+    char num[16];
+    for (size_t r = lo; r < hi; r += stride) {
+        if (c.ext_ids) out.put(c.id_ptr[r], c.id_len[r]);
+        else out.put(c.ids.data() + c.id_off[r], c.id_off[r + 1] - c.id_off[r]);
+        out.put(" l:", 3);
+        out.put(num, rcxio::format_int(num, b.l[r]));
+        out.put(" m:", 3);
+        out.put(num, rcxio::format_int(num, b.m[r]));
+        out.put(" h:", 3);
+        out.put(num, rcxio::format_int(num, b.h[r]));
+        if (b.corr[r] == -1) out.put(" unfixable_error", 16);
+        else if (b.corr[r] > 0) out.put(" cor", 4);
+        out.ch('\n');
+        out.put(b.seq + b.off[r], b.off[r + 1] - b.off[r]);
+        out.ch('\n');
+        if (type == 1) {
+            out.put("+\n", 2);
+            if (c.ragged_qual && r + 1 < c.qual_text_off.size() && c.qual_text_off[r + 1] > c.qual_text_off[r])
+                out.put(c.qual_text.data() + c.qual_text_off[r], c.qual_text_off[r + 1] - c.qual_text_off[r]);
+            else
+                out.put(b.qual + b.off[r], b.off[r + 1] - b.off[r]);
+            out.ch('\n');
+        }
+    }
+}
 static void format_records(const HostBatch& b, const Chunk& c, int type, size_t lo, size_t hi, size_t stride, std::string& out) {
     out.clear();
     if (lo < hi) {  // one allocation: ids + twice the bases + at most 64 bytes of tags and separators per record
@@ -385,30 +430,8 @@ static void format_records(const HostBatch& b, const Chunk& c, int type, size_t 
         const size_t want = idb + 2 * bases + 64 * nrec;
         if (out.capacity() < want) out.reserve(want + want / 8);
     }
-    char num[16];
-    for (size_t r = lo; r < hi; r += stride) {
-        if (c.ext_ids) out.append(c.id_ptr[r], c.id_len[r]);
-        else out.append(c.ids.data() + c.id_off[r], c.id_off[r + 1] - c.id_off[r]);
-        out.append(" l:");
-        out.append(num, rcxio::format_int(num, b.l[r]));
-        out.append(" m:");
-        out.append(num, rcxio::format_int(num, b.m[r]));
-        out.append(" h:");
-        out.append(num, rcxio::format_int(num, b.h[r]));
-        if (b.corr[r] == -1) out.append(" unfixable_error");
-        else if (b.corr[r] > 0) out.append(" cor");
-        out.push_back('\n');
-        out.append(b.seq + b.off[r], b.off[r + 1] - b.off[r]);
-        out.push_back('\n');
-        if (type == 1) {
-            out.append("+\n");
-            if (c.ragged_qual && r + 1 < c.qual_text_off.size() && c.qual_text_off[r + 1] > c.qual_text_off[r])
-                out.append(c.qual_text.data() + c.qual_text_off[r], c.qual_text_off[r + 1] - c.qual_text_off[r]);
-            else
-                out.append(b.qual + b.off[r], b.off[r + 1] - b.off[r]);
-            out.push_back('\n');
-        }
-    }
+    StringSink sink{out};
+    emit_records(sink, b, c, type, lo, hi, stride);
 }
 
 
@@ -856,7 +879,8 @@ int main(int argc, char* argv[]) {
     tmark("pinned batch buffers ready");
     const int nfmt = std::min(threads, 32);
     const bool fast_io = !getenv("RCX_SERIAL_IO");
-    std::shared_future<void> last_write;  // chain of writes: keeps the output in input order
+    std::shared_future<void> last_write;     // the latest batch's formatting + writing
+    std::shared_future<void> last_reserved;  // chain of reservations: keeps the output in input order
     std::vector<std::shared_future<void>> set_write(NSETS);
     for (size_t fi = 0; fi < files.size(); ++fi) {
         const ReadFile& f = files[fi];
@@ -931,7 +955,10 @@ int main(int argc, char* argv[]) {
         // batch to batch; plain files are then written by the same threads with positional writes at offsets reserved in
         // batch order (the batches' writes themselves may overlap); gzip files and stdout are sequential streams, written in
         // batch order.
-        auto consume = [&, fi](BatchSet& st, std::shared_future<void> prev) {
+        // `prev_reserved` becomes ready when the batch before this one has its place in the output (plain files: right after
+        // the reservation, so the batches' formatting and page faults overlap; streams: when it is written); `reserved` is
+        // this batch's turn of the same chain.
+        auto consume = [&, fi](BatchSet& st, std::shared_future<void> prev_reserved, std::shared_ptr<std::promise<void>> reserved) {
             HostBatch& b = st.b;
             Chunk& c = st.c;
             struct Part { Writer* w; size_t start, stride, recs; int parts; std::vector<std::string>* pieces; std::vector<std::string>* out; };
@@ -954,13 +981,77 @@ int main(int argc, char* argv[]) {
             } else {
                 plan(out1[fi], 0, 1, 0);  // single, interleaved, or paired to stdout (mate1, mate2, mate1, ...)
             }
+            auto range = [&](const Part& p, int t, size_t& lo, size_t& hi) {
+                lo = p.start + p.stride * (p.recs * t / p.parts);
+                hi = std::min(p.start + p.stride * (p.recs * (t + 1) / p.parts), b.n);
+            };
+            bool direct = !getenv("RCX_NO_DIRECT_OUT");
+            for (int q = 0; q < nparts; ++q) direct = direct && part[q].w->can_scatter() && !part[q].w->gz();
+            if (direct) {
+                // plain files: piece sizes first (no bytes move), then the place in the file, then every thread formats its
+                // piece straight into the mapping of that region -- no intermediate buffer, no second copy
+                std::vector<size_t> sizes[2];
+                {
+                    StageTimer timer(g_us_format);
+                    for (int q = 0; q < nparts; ++q) {
+                        Part& p = part[q];
+                        sizes[q].assign(p.parts, 0);
+                        rcxio::parallel_for(p.parts, [&](int t) {
+                            size_t lo, hi;
+                            range(p, t, lo, hi);
+                            CountSink cs;
+                            emit_records(cs, b, c, f.type, lo, hi, p.stride);
+                            sizes[q][t] = cs.n;
+                        });
+                    }
+                }
+                if (prev_reserved.valid()) prev_reserved.wait();
+                uint64_t at0[2] = {0, 0}, total[2] = {0, 0};
+                bool mapped_ok = true;
+                void* mbase[2] = {nullptr, nullptr};
+                size_t mlen[2] = {0, 0};
+                char* dst[2] = {nullptr, nullptr};
+                for (int q = 0; q < nparts; ++q) {
+                    for (int t = 0; t < part[q].parts; ++t) total[q] += sizes[q][t];
+                    at0[q] = part[q].w->reserve(total[q]);
+                    dst[q] = total[q] ? part[q].w->map(at0[q], total[q], mbase[q], mlen[q]) : nullptr;  // (grows the file: in order)
+                    if (total[q] && !dst[q]) mapped_ok = false;
+                }
+                reserved->set_value();
+                StageTimer timer(g_us_write);
+                for (int q = 0; q < nparts; ++q) {
+                    Part& p = part[q];
+                    if (!total[q]) continue;
+                    std::vector<size_t> offs(p.parts, 0);
+                    for (int t = 1; t < p.parts; ++t) offs[t] = offs[t - 1] + sizes[q][t - 1];
+                    std::atomic<int> failed{0};
+                    rcxio::parallel_for(p.parts, [&](int t) {
+                        size_t lo, hi;
+                        range(p, t, lo, hi);
+                        if (mapped_ok) {
+                            PtrSink ps{dst[q] + offs[t]};
+                            emit_records(ps, b, c, f.type, lo, hi, p.stride);
+                        } else {  // the file could not be mapped: format into a buffer, positional write
+                            format_records(b, c, f.type, lo, hi, p.stride, (*p.pieces)[t]);
+                            if (!p.w->write_at(at0[q] + offs[t], (*p.pieces)[t].data(), (*p.pieces)[t].size())) failed = 1;
+                        }
+                    });
+                    Writer::unmap(mbase[q], mlen[q]);
+                    if (failed) {
+                        fprintf(stderr, "ERROR: Could not write the output of %s\n", f.path.c_str());
+                        exit(1);
+                    }
+                }
+                return;
+            }
             {
                 StageTimer timer(g_us_format);
                 for (int q = 0; q < nparts; ++q) {
                     Part& p = part[q];
                     rcxio::parallel_for(p.parts, [&](int t) {
-                        const size_t lo = p.start + p.stride * (p.recs * t / p.parts), hi = p.start + p.stride * (p.recs * (t + 1) / p.parts);
-                        format_records(b, c, f.type, lo, std::min(hi, b.n), p.stride, (*p.pieces)[t]);
+                        size_t lo, hi;
+                        range(p, t, lo, hi);
+                        format_records(b, c, f.type, lo, hi, p.stride, (*p.pieces)[t]);
                         if (p.w->gz()) {  // one gzip member per piece, level 1 like the reference's gzopen(.., "w1")
                             if ((*p.pieces)[t].empty()) (*p.out)[t].clear();
                             else if (!rcxio::gzip_member((*p.pieces)[t].data(), (*p.pieces)[t].size(), 1, (*p.out)[t])) {
@@ -971,7 +1062,7 @@ int main(int argc, char* argv[]) {
                     });
                 }
             }
-            if (prev.valid()) prev.wait();  // the previous batch has reserved its place (plain files) / is written (streams)
+            if (prev_reserved.valid()) prev_reserved.wait();  // the previous batch has reserved its place (plain files) / is written (streams)
             StageTimer timer(g_us_write);
             for (int q = 0; q < nparts; ++q) {
                 Part& p = part[q];
@@ -996,6 +1087,7 @@ int main(int argc, char* argv[]) {
                     for (int t = 0; t < p.parts; ++t) p.w->write((*p.pieces)[t].data(), (*p.pieces)[t].size());
                 }
             }
+            reserved->set_value();
         };
         int cur = 0;
         bool have = produce(sets[cur]);
@@ -1030,13 +1122,15 @@ int main(int argc, char* argv[]) {
                 ++total_reads;
                 if (b.corr[r] > 0) total_corrections += (uint64_t)b.corr[r];
             }
-            std::shared_future<void> prev = last_write;
-            last_write = std::async(std::launch::async, [&, cur, prev]() { consume(sets[cur], prev); }).share();
+            std::shared_future<void> prev = last_reserved;
+            auto rp = std::make_shared<std::promise<void>>();
+            last_reserved = rp->get_future().share();
+            last_write = std::async(std::launch::async, [&, cur, prev, rp]() { consume(sets[cur], prev, rp); }).share();
             set_write[cur] = last_write;
             have = may_have_more ? fnext.get() : false;
             cur = nxt;
         }
-        if (last_write.valid()) last_write.wait();  // this file's sources go out of scope
+        for (auto& w : set_write) if (w.valid()) w.wait();  // every batch of this file is written: its sources go out of scope
         if (unpaired) {
             fprintf(stderr, "ERROR: The files are not paired!\n");  // main.cpp:463-466
             exit(1);
