@@ -192,6 +192,39 @@ __device__ __forceinline__ int rcx_probe_kmer(const RcxTable& t, unsigned long l
     return rcx_count1(t, code >> 2, false, (int)(code & 3), L, found);
 }
 
+// ----------------------------------------------------------------------------- bulk tile copy (TMA, 1-D) + mbarrier
+// One thread hands a contiguous, 16-byte aligned range of global memory to the copy engine; the bytes land in shared
+// memory without passing through registers and complete a transaction barrier the whole block waits on.
+__device__ __forceinline__ unsigned int rcx_smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rcx_mbar_init(void* bar, unsigned int arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcx_smem_addr(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// (shared memory the block wrote with ordinary stores is about to be written by the async proxy)
+__device__ __forceinline__ void rcx_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void rcx_bulk_load(void* smem_dst, const void* gsrc, unsigned int bytes, void* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcx_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rcx_smem_addr(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(rcx_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void rcx_mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcx_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void rcx_mbar_wait(void* bar, unsigned int phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RCX_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RCX_MBAR_DONE;\n"
+        "bra RCX_MBAR_WAIT;\n"
+        "RCX_MBAR_DONE:\n"
+        "}\n" ::"r"(rcx_smem_addr(bar)),
+        "r"(phase)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------- KmerCode state machine
 struct RcxKmer {
     unsigned long long code;

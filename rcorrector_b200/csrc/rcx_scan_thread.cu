@@ -140,6 +140,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
     const int nseg_cap = a.max_len / k + 4;
     unsigned int probes = 0, toobig = 0;
     const long long ntiles = (a.n + NT - 1) / NT;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(blk + 12);  // transaction barrier of the tile copy (8-byte aligned)
+    unsigned int tile_phase = 0;
+    if (tid == 0) rcx_mbar_init(mbar, 1);
+    __syncthreads();
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long r0 = tile * NT;
@@ -150,15 +154,21 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         __syncthreads();
         const unsigned long long g0 = offs[0], g1 = offs[nr];
         const unsigned long long a0 = g0 & ~15ull;
-        {   // stage the tile's bases: 16-byte vectors, byte tail (never reads past the batch)
+        {   // stage the tile's bases: ONE bulk copy (TMA, 1-D) of the 16-byte aligned body handed to the copy engine by thread 0
+            // -- no registers, no staging loop -- and a byte tail (never reads past the batch); the block waits on the
+            // transaction barrier
             unsigned long long e16 = (g1 + 15) & ~15ull;
             if (e16 > (a.total_bases & ~15ull)) e16 = a.total_bases & ~15ull;
             if (e16 < a0) e16 = a0;
-            const uint4* src = reinterpret_cast<const uint4*>(a.seq + a0);
-            uint4* dst = reinterpret_cast<uint4*>(bytes);
-            const int nv = (int)((e16 - a0) >> 4);
-            for (int v = tid; v < nv; v += NT) dst[v] = src[v];
+            if (tid == 0) {
+                const unsigned int nbytes = (unsigned int)(e16 - a0);
+                rcx_fence_proxy_async();  // the previous tile's bytes were rewritten in place by the threads
+                if (nbytes) rcx_bulk_load(bytes, a.seq + a0, nbytes, mbar);
+                else rcx_mbar_arrive(mbar);
+            }
             for (unsigned long long p = e16 + tid; p < g1; p += NT) bytes[p - a0] = (unsigned char)a.seq[p];
+            rcx_mbar_wait(mbar, tile_phase);
+            tile_phase ^= 1u;
         }
         __syncthreads();
 
