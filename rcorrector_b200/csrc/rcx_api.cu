@@ -833,9 +833,13 @@ extern "C" int rcx_correct_batch_device(rcx_ctx* c, int mode, int64_t n, char* s
     if (!seq || !qual || !off || !correction || !l || !m || !h) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: null pointer");
     if (max_len < 1 || max_len > RCX_MAX_READ_LENGTH) return fail(RCX_ERR_ARG, "rcx_correct_batch_device: bad max_len");
     CUDA_TRY(cudaSetDevice(c->device));
+    RcxSlot& sl = c->slot[0];
+    // Asynchronous on purpose: a device batch enqueued behind another one does not wait for it on the host (the kernels are
+    // stream-ordered; counters and event times then describe the LAST batch).  Waiting here put a host round trip between
+    // the steps of a loop of device batches -- 8 ms per step with eight processes on one host (profiles/r02_n8_bench.json).
+    sl.pending = false;
     rc = begin_call(c, (uint64_t)n, total);
     if (rc) return rc;
-    RcxSlot& sl = c->slot[0];
     CUDA_TRY(cudaEventRecord(sl.ev[0], sl.stream));
     rc = launch_pipeline(c, sl, mode, n, seq, qual, off, 0, total, max_len, correction, l, m, h, true);
     if (rc) return rc;
