@@ -664,6 +664,8 @@ def measure(a, steps, warmup, world, rank, local, dist, guard_cpu_leg=True):
                 collect.append(cor.stats())
         edits_seen[0] = tot
 
+    by_rank = []  # per timed region: ms per step of every rank (the line reports the maximum)
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -676,10 +678,13 @@ def measure(a, steps, warmup, world, rank, local, dist, guard_cpu_leg=True):
         e1.synchronize()
         barrier()
         ms = e0.elapsed_time(e1)
+        by_rank.append([ms / steps])
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            g = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            by_rank[-1] = [float(x.item()) / steps for x in g]
+            ms = max(float(x.item()) for x in g)
         return ms
 
     rr32 = cor.measure_random_read(32)
@@ -696,6 +701,12 @@ def measure(a, steps, warmup, world, rank, local, dist, guard_cpu_leg=True):
     cor.sync()
     acc = lambda lst: {k: sum(s[k] for s in lst) for k in lst[0]}
     st, st_e2e = acc(sd), acc(se)
+    kern_by_rank = [[st["ms_scan"], st["ms_dfs"], st["ms_finalize"]]]
+    if world > 1:
+        t = torch.tensor(kern_by_rank[0], dtype=torch.float64, device=dev)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        kern_by_rank = [[round(float(v), 2) for v in x.tolist()] for x in g]
 
     # size-independent parity property inside the bench: both arms agree on every read's correction count
     chk = [sum(int(b["d_res"][0].sum().item()) for b in batches), sum(int(b["corr_p"][0].sum().item()) for b in batches)]
@@ -789,6 +800,8 @@ def measure(a, steps, warmup, world, rank, local, dist, guard_cpu_leg=True):
         "kernels": kern, "work_items": st["work_items"], "second_pass": st["second_pass"],
         "table": table_t, "params": {"error_rate": er, "bad_qual": bq, "source": "rcx_estimate_error_rate + quality histogram (as the binaries)"},
         "reads_this_rank": n_rank, "clocks": clocks,
+        "by_rank": {"ms_per_step": [round(v, 2) for v in by_rank[0]], "e2e_ms_per_step": [round(v, 2) for v in by_rank[1]],
+                    "scan_dfs_finalize_ms": kern_by_rank},
     }
     if parity is not None:
         line["parity"] = parity

@@ -24,6 +24,12 @@
 // TS_DEPTH (template parameter DEPTH): sector requests in flight per thread.  Measured for 100-bp reads (128-read tiles,
 // 512 threads per SM) 2 / 4 / 8: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding) -> 2; for 150-bp
 // reads (64-read tiles, 320 threads per SM) 2 / 4: 28.2 / 29.0 ms per 6 M reads -> 2 (profiles/r01_u_e2e_chunks.md).
+#ifndef TS_ROTATE
+#define TS_ROTATE 1
+#endif
+#ifndef TS_DEPTH_DEFAULT
+#define TS_DEPTH_DEFAULT 2
+#endif
 #define TS_LOOSE 0x80000000u   // flag bits stored with a count in shared memory
 #define TS_STRICT 0x40000000u
 #define TS_INVALID 0x20000000u
@@ -110,7 +116,7 @@ __device__ __forceinline__ int ts_select_coop(const unsigned int* warp_rows, int
             int c = 0;
             for (int j = lane; j < n; j += 32) {
                 const unsigned int x = row[j];
-                if (KIND == 0) c += ts_masked(x) <= mid;
+                if (KIND == 0) c += (int)(x & ~(TS_STRICT | TS_INVALID)) <= mid;  // a loose entry (bit 31) reads as negative: like its -1, never above a pivot >= -1
                 else if (!(x & TS_INVALID)) { int v = (int)(x & TS_CMASK); v = v == 0 ? 1 : v; c += v <= mid; }
             }
             c = __reduce_add_sync(RCX_FULL, c);
@@ -210,56 +216,76 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                 ++i;
             };
             while (i < k - 1) append();
-            while (i < len) {
-                TsPend p[TS_DEPTH];
-#pragma unroll
-                for (int u = 0; u < TS_DEPTH; ++u) {
-                    p[u].info = -1;
-                    bool trig = false;
-                    int j = 0;
-                    while (i < len && !trig) {
-                        append();
-                        j = i - k;  // window that ends at the base just appended
-                        const bool lo_ = wA >= k - loose_thr || wT >= k - loose_thr;  // IsPolyA(seq + j, k, max(7, k/2))
-                        const bool st_ = wA >= k - 2 || wT >= k - 2;                  // IsPolyA(seq + j, k, 2)
-                        row[j] = (lo_ ? TS_LOOSE : 0u) | (st_ ? TS_STRICT : 0u) | (run >= k ? 0u : TS_INVALID);
-                        trig = (j & 1) || i == len;
-                    }
-                    if (trig) {
-                        // context = the k-1 bases before the newest one: window j-1 is its left extension (by the base that
-                        // just left F), window j its right extension (by the newest base)
-                        const bool wantL = (j & 1) && run_prev >= k;
-                        const bool wantR = run >= k;
-                        if (wantL || wantR) {
-                            const unsigned long long ctx = F >> 2;
-                            const unsigned long long rc = rcx_revcomp(ctx, k - 1);
-                            const bool flip = rc < ctx;
-                            p[u].key = flip ? rc : ctx;
-                            p[u].info = j | (left << 10) | ((int)(F & 3) << 12) | (wantL ? 1 << 14 : 0) | (wantR ? 1 << 15 : 0) | (flip ? 1 << 16 : 0);
-                            rcx_issue(a.t, __umul64hi(rcx_hash(p[u].key), a.t.nlines << 2), p[u].d);
-                            ++probes;
-                        }
+            // advance to the next request (one per two windows) and issue it; p.info = -1 when the read ends first
+            auto issue = [&](TsPend& p) {
+                p.info = -1;
+                bool trig = false;
+                int j = 0;
+                while (i < len && !trig) {
+                    append();
+                    j = i - k;  // window that ends at the base just appended
+                    const bool lo_ = wA >= k - loose_thr || wT >= k - loose_thr;  // IsPolyA(seq + j, k, max(7, k/2))
+                    const bool st_ = wA >= k - 2 || wT >= k - 2;                  // IsPolyA(seq + j, k, 2)
+                    row[j] = (lo_ ? TS_LOOSE : 0u) | (st_ ? TS_STRICT : 0u) | (run >= k ? 0u : TS_INVALID);
+                    trig = (j & 1) || i == len;
+                }
+                if (trig) {
+                    // context = the k-1 bases before the newest one: window j-1 is its left extension (by the base that
+                    // just left F), window j its right extension (by the newest base)
+                    const bool wantL = (j & 1) && run_prev >= k;
+                    const bool wantR = run >= k;
+                    if (wantL || wantR) {
+                        const unsigned long long ctx = F >> 2;
+                        const unsigned long long rc = rcx_revcomp(ctx, k - 1);
+                        const bool flip = rc < ctx;
+                        p.key = flip ? rc : ctx;
+                        p.info = j | (left << 10) | ((int)(F & 3) << 12) | (wantL ? 1 << 14 : 0) | (wantR ? 1 << 15 : 0) | (flip ? 1 << 16 : 0);
+                        rcx_issue(a.t, __umul64hi(rcx_hash(p.key), a.t.nlines << 2), p.d);
+                        ++probes;
                     }
                 }
+            };
+            auto consume = [&](TsPend& p) {
+                const int info = p.info;
+                p.info = -1;
+                if (info >= 0 && ts_find(a.t, p.key, p.d)) {
+                    const int j = info & 1023;
+                    const bool flip = (info >> 16) & 1;
+                    if (info & (1 << 14)) {
+                        const int c = ts_field(a.t, p.d, p.key, flip, true, (info >> 10) & 3);
+                        toobig |= (unsigned int)c > TS_CMASK;
+                        row[j - 1] |= (unsigned int)c & TS_CMASK;
+                    }
+                    if (info & (1 << 15)) {
+                        const int c = ts_field(a.t, p.d, p.key, flip, false, (info >> 12) & 3);
+                        toobig |= (unsigned int)c > TS_CMASK;
+                        row[j] |= (unsigned int)c & TS_CMASK;
+                    }
+                }
+            };
+            TsPend p[TS_DEPTH];
+#pragma unroll
+            for (int u = 0; u < TS_DEPTH; ++u) p[u].info = -1;
+#if TS_ROTATE
+            // rotating pipeline: a request is consumed one round AFTER it was issued -- every sector has the time of
+            // TS_DEPTH - 1 further requests (and of the other warps) to arrive, instead of being waited for right after the issue
+            while (i < len) {
 #pragma unroll
                 for (int u = 0; u < TS_DEPTH; ++u) {
-                    const int info = p[u].info;
-                    if (info >= 0 && ts_find(a.t, p[u].key, p[u].d)) {
-                        const int j = info & 1023;
-                        const bool flip = (info >> 16) & 1;
-                        if (info & (1 << 14)) {
-                            const int c = ts_field(a.t, p[u].d, p[u].key, flip, true, (info >> 10) & 3);
-                            toobig |= (unsigned int)c > TS_CMASK;
-                            row[j - 1] |= (unsigned int)c & TS_CMASK;
-                        }
-                        if (info & (1 << 15)) {
-                            const int c = ts_field(a.t, p[u].d, p[u].key, flip, false, (info >> 12) & 3);
-                            toobig |= (unsigned int)c > TS_CMASK;
-                            row[j] |= (unsigned int)c & TS_CMASK;
-                        }
-                    }
+                    consume(p[u]);
+                    issue(p[u]);
                 }
             }
+#else
+            while (i < len) {
+#pragma unroll
+                for (int u = 0; u < TS_DEPTH; ++u) issue(p[u]);
+#pragma unroll
+                for (int u = 0; u < TS_DEPTH; ++u) consume(p[u]);
+            }
+#endif
+#pragma unroll
+            for (int u = 0; u < TS_DEPTH; ++u) consume(p[u]);
         } else if (have) {
             for (int i = 0; i < len; ++i) {  // shorter than k: only the per-base conversion (the bytes go out as per-base info)
                 const unsigned char ch = B[i];
@@ -569,6 +595,6 @@ static cudaError_t launch_scan_thread_nw(const RcxScanArgs& a, int sm_count, cud
 
 cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS, 2>(a, sm_count, s);
-    return launch_scan_thread_nw<4, 64, 2>(a, sm_count, s);  // max_len <= 255 (4 in flight measured on 150-bp reads: 28.2 -> 29.0 ms)
+    if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS, TS_DEPTH_DEFAULT>(a, sm_count, s);
+    return launch_scan_thread_nw<4, 64, TS_DEPTH_DEFAULT>(a, sm_count, s);  // max_len <= 255 (4 in flight measured on 150-bp reads: 28.2 -> 29.0 ms)
 }
