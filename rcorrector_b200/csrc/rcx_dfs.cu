@@ -91,6 +91,9 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 // scheduler already cover it; the kernel is bound by instruction issue under divergence, not by memory latency.
 #define DFS_AHEAD 0
 #endif
+#ifndef DFS_TAIL_PREFETCH
+#define DFS_TAIL_PREFETCH 4  // lanes: at or below this many active lanes in the node loop, the keep-base child's sector is prefetched into L2 (0: off)
+#endif
 #ifndef DFS_BATCH
 // 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
 // taken by a whole warp at a time, 32 consecutive slots, and a lane that finishes waits for the others: items of one
@@ -351,6 +354,18 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 RcxKmer x = kc;
                 const int hb = pi & 3;
                 if (!(pi & 4)) { if (right) rcx_k_append(x, hb, false, k, mask); else rcx_k_prepend(x, hb, false, k, mask); }
+                if (DFS_TAIL_PREFETCH > 0 && !(pi & 4) && __popc(__activemask()) <= DFS_TAIL_PREFETCH) {
+                    // Few lanes of this warp are still walking (the end of a launch, or one very long walk): the warp has
+                    // issue slots to spare and every node costs it a full DRAM round trip.  The keep-base child's sector is
+                    // asked into L2 now (no register holds it), so that the child finds it there.
+                    const int np1 = right ? pos + 1 : pos - 1;
+                    if ((right ? np1 < to : np1 >= to) && (x.inv == -1 || (right ? x.inv + 1 >= k : x.inv <= 0))) {
+                        const unsigned long long nctx = right ? (x.code & (mask >> 2)) : (x.code >> 2);
+                        const unsigned long long nrc = rcx_revcomp(nctx, k - 1);
+                        const RcxEntry* pe = a.t.e + rcx_home(a.t, nrc < nctx ? nrc : nctx);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
+                    }
+                }
                 if (DFS_AHEAD) {
                     pf_on = false;
                     const int np1 = right ? pos + 1 : pos - 1;

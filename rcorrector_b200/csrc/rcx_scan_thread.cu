@@ -25,7 +25,10 @@
 // 512 threads per SM) 2 / 4 / 8: 26.0 / 27.4 / 40.4 ms (registers and instructions against latency hiding) -> 2; for 150-bp
 // reads (64-read tiles, 320 threads per SM) 2 / 4: 28.2 / 29.0 ms per 6 M reads -> 2 (profiles/r01_u_e2e_chunks.md).
 #ifndef TS_ROTATE
-#define TS_ROTATE 1
+// 1: rotating request pipeline (a sector is consumed one round after it was issued).  Measured equal or slightly slower
+// (10 M x 100 bp: 22.98 -> 23.14 ms; 48 M x 150 bp: 224.6 -> 225.8 ms; 3 / 4 requests in flight: 24.4 / 26.8 ms,
+// gpurun_out/r02_n2b): the scan is not waiting for its sectors, it is short of issue slots.
+#define TS_ROTATE 0
 #endif
 #ifndef TS_DEPTH_DEFAULT
 #define TS_DEPTH_DEFAULT 2
