@@ -107,8 +107,12 @@ static int sniff_type(const std::string& path) {  // Reads.h:108-132
     const char* p;
     size_t n;
     bool nl;
-    if (!r.getline(p, n, nl) || n == 0 || (p[0] != '>' && p[0] != '@')) {
-        fprintf(stderr, "\"%s\"'s format is wrong: %.*s\n", path.c_str(), (int)(r.getline(p, n, nl) ? n : 0), p);
+    const bool got = r.getline(p, n, nl);
+    if (!got || n == 0 || (p[0] != '>' && p[0] != '@')) {
+        // Reads.h:118-131 prints the buffer its Gets filled: the first line WITH its newline (an empty file leaves the
+        // reference's buffer uninitialised; nothing is shown here)
+        const std::string shown = got ? std::string(p, n) + (nl ? "\n" : "") : std::string();
+        fprintf(stderr, "\"%s\"'s format is wrong: %s\n", path.c_str(), shown.c_str());
         exit(1);
     }
     return p[0] == '@' ? 1 : 0;

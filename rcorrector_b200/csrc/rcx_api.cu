@@ -29,6 +29,17 @@ static int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
     } while (0)
 
+// device allocations of one call that must not outlive an early return
+struct DevGuard {
+    std::vector<void**> ptrs;
+    void watch(void** p) { ptrs.push_back(p); }
+    void release_all() {
+        for (void** p : ptrs)
+            if (*p) { cudaFree(*p); *p = nullptr; }
+    }
+    ~DevGuard() { release_all(); }
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -244,6 +255,9 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     const int32_t* d_counts_all = nullptr;
     unsigned long long* own_codes = nullptr;
     int32_t* own_counts = nullptr;
+    DevGuard guard;  // frees whatever is still set when the function returns (every CUDA_TRY below may return)
+    guard.watch((void**)&own_codes);
+    guard.watch((void**)&own_counts);
     const uint64_t chunk = 1ull << 24;
     if (src_on_device) {
         d_codes_all = (const unsigned long long*)fwd_codes;
@@ -275,9 +289,11 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
         return RCX_OK;
     };
     unsigned long long* d_stat = nullptr;  // [0] contexts claimed, [1] abort flag, [2] distinct k-mers, [3] saturated counts
+    guard.watch((void**)&d_stat);
     CUDA_TRY(cudaMalloc(&d_stat, 4 * sizeof(unsigned long long)));
     unsigned long long h_stat[4] = {0, 0, 0, 0};
     RcxEntry* e = nullptr;
+    guard.watch((void**)&e);
     for (int attempt = 0;; ++attempt) {
         CUDA_TRY(cudaMalloc(&e, nlines * 4 * sizeof(RcxEntry)));
         CUDA_TRY(rcx_launch_table_init(e, nlines, c->stream));
@@ -326,10 +342,13 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
         if (f >= 1024 && f < part) part = f;
     }
     unsigned int* d_win = nullptr;
+    guard.watch((void**)&d_win);
     CUDA_TRY(cudaMalloc(&d_win, part * 32));
     const unsigned long long big_cap = 1ull << 20;
     unsigned long long* d_big_keys = nullptr;
     unsigned int* d_big_counts = nullptr;
+    guard.watch((void**)&d_big_keys);
+    guard.watch((void**)&d_big_counts);
     CUDA_TRY(cudaMalloc(&d_big_keys, big_cap * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&d_big_counts, big_cap * sizeof(unsigned int)));
     for (unsigned long long lo = 0; lo < nsec; lo += part) {
@@ -346,14 +365,7 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     }
     CUDA_TRY(cudaMemcpyAsync(h_stat, d_stat, sizeof h_stat, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(d_win);
-    cudaFree(d_stat);
-    if (own_codes) cudaFree(own_codes);
-    if (own_counts) cudaFree(own_counts);
-    if (h_stat[3] > big_cap) {
-        cudaFree(e); cudaFree(d_big_keys); cudaFree(d_big_counts);
-        return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^20 k-mers with a count >= 2^24-1");
-    }
+    if (h_stat[3] > big_cap) return fail(RCX_ERR_ARG, "rcx_table_build: more than 2^20 k-mers with a count >= 2^24-1");
     // exact counts of the saturated 24-bit fields: sorted side list, binary-searched on the device
     c->nbig = (int)h_stat[3];
     if (c->nbig > 0) {
@@ -374,6 +386,7 @@ extern "C" int rcx_table_build(rcx_ctx* c, int k, const uint64_t* fwd_codes, con
     c->big_keys = d_big_keys;
     c->big_counts = d_big_counts;
     c->entries_dev = e;
+    d_big_keys = nullptr; d_big_counts = nullptr; e = nullptr;  // owned by the context now (the guard frees the temporaries)
     c->nlines = nlines;
     c->entries = h_stat[2];
     c->contexts = h_stat[0];

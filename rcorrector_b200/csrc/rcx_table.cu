@@ -78,6 +78,10 @@ rcx_table_claim_kernel(RcxEntry* e, unsigned long long nlines, int k, const unsi
                     break;
                 }
                 if (home_only) break;
+                if (j >= 4 * nlines) {  // every sector visited and none free: the table is full, whatever `fresh` says so far
+                    atomicExch(&stat[1], 1ull);
+                    return;
+                }
             }
         }
     }
