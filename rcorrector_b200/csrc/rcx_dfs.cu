@@ -92,7 +92,7 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #define DFS_AHEAD 0
 #endif
 #ifndef DFS_TAIL_PREFETCH
-#define DFS_TAIL_PREFETCH 4  // lanes: at or below this many active lanes in the node loop, the keep-base child's sector is prefetched into L2 (0: off)
+#define DFS_TAIL_PREFETCH 0  // lanes: at or below this many active lanes in the node loop, the keep-base child's sector is prefetched into L2.  Measured: no gain (2 GPUs, rank 1 search 54.96 ms off, 56.12 at 4 lanes, 56.38 at 12, gpurun_out/r02_n2c) -> off
 #endif
 #ifndef DFS_BATCH
 // 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
