@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--long", action="store_true")
     ap.add_argument("--wild-quals", action="store_true")
+    ap.add_argument("--iupac", action="store_true", help="pepper part of the reads with non-ACGT letters other than N (free substitutions: long edit lists)")
+    ap.add_argument("--chunks", action="store_true", help="random tiny RCX_CHUNK_READS per case (chunk boundaries, edit order of the compact interface)")
+    ap.add_argument("--count", action="store_true", help="also count the k-mers of the reads on the GPU and compare with the dump")
     a = ap.parse_args()
     F.LONG = a.long
     from rcorrector_b200 import Corrector
@@ -63,7 +66,18 @@ def main():
             if a.wild_quals:
                 F.wild_quals(rng, d["fq"])
             bs = [T.read_fastq(f) for f in d["fq"]]
+            if a.iupac:  # (after the dump was counted: the table stays that of the clean reads)
+                nrng = np.random.default_rng(rng.randrange(1 << 30))
+                for x in bs:
+                    seq = x.seq.copy()
+                    for r in range(0, x.n, rng.choice([2, 3, 5])):
+                        o, e = int(x.off[r]), int(x.off[r + 1])
+                        hit = o + np.flatnonzero(nrng.random(e - o) < rng.choice([0.02, 0.1, 0.25]))
+                        seq[hit] = nrng.choice(np.frombuffer(b"RYKMSWBDHV", dtype=np.uint8), size=len(hit))
+                    x.seq = seq
             b = T.interleave(*bs) if paired else bs[0]
+            if a.chunks:
+                os.environ["RCX_CHUNK_READS"] = str(rng.choice([2, 6, 50, 334, 1000]))
             codes, counts = T.dump_to_arrays(d["dump"], k)
             table = T.OracleTable(k)
             table.load_dump(d["dump"])
@@ -92,6 +106,11 @@ def main():
                     problems.append(name)
             if st["unsupported"]:
                 problems.append("unsupported=%d" % st["unsupported"])
+            if a.count and not a.iupac:  # the dump is the exact count of these reads
+                ccodes, ccounts, _, _ = gpu.count_kmers(k, [(x.seq, x.off) for x in bs])
+                want = dict(zip(codes.tolist(), counts.tolist()))
+                if dict(zip(ccodes.tolist(), ccounts.tolist())) != {kk: v for kk, v in want.items() if v >= 2}:
+                    problems.append("k-mer counts")
             tot["reads"] += b.n
             tot["corrected"] += int(exp[1][exp[1] > 0].sum())
             tot["unsupported"] += int(st["unsupported"])
