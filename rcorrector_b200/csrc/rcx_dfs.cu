@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
 #define PATH(p) path[(p) * 32]
 
     unsigned long long n_nodes = 0, n_probes = 0;
+#ifdef RCX_DIAG
+    unsigned long long diag_n0 = 0;
+    int diag_nun = 0;
+#endif
     // ---- per-item state
     int* st = nullptr;
     const unsigned char* pinfo = nullptr;
@@ -222,6 +226,9 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             pinfo = a.posbuf + o;
             fix = a.fixbuf + o;
             nseg = h1.y; trust = h1.x; fbound = h0.y;  // (ST_TOTALFIX carries rcx_force_bound(strong) in)
+#ifdef RCX_DIAG
+            diag_nun = h0.z; diag_n0 = n_nodes;
+#endif
             max_top2 = -1;
             na_base = 0;  // fix[] = -1 (:1113-1114): no accepted edits yet
             g = 0; total_fix = 0; bad_segments = 0; best_bn_all = RCX_INF; abort_read = false;
@@ -252,6 +259,15 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                 }
                 st[ST_TOTALFIX] = total_fix;
                 st[ST_BADSEG] = bad_segments;
+#ifdef RCX_DIAG
+                {   // walk length of the item against its number of untrusted k-windows (buckets of 32)
+                    const unsigned long long dn = n_nodes - diag_n0;
+                    const int bkt = diag_nun >= 128 ? 3 : (diag_nun >> 5);
+                    atomicMax(&a.counters[RCX_C_DIAG0], dn);
+                    atomicAdd(&a.counters[RCX_C_DIAG0 + 1 + bkt], 1ull);                 // items per bucket
+                    if (dn > 2000) { atomicAdd(&a.counters[RCX_C_DIAG0 + 5 + bkt], 1ull); atomicAdd(&a.counters[RCX_C_DIAG0 + 9 + bkt], dn); }
+                }
+#endif
                 if (rethreshold) {
                     if (a.pass == 0) {
                         st[ST_STATUS] = RCX_ST_RETHRESHOLD;  // the pass-1 prep kernel re-thresholds (:1247-1289)

@@ -18,6 +18,7 @@ enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SE
        RCX_C_NWORKH,                             // HEAVY work items (long untrusted spans): slots n-1, n-2, ... of the work list, searched first
        RCX_C_RESCAN_WINDOWS,                     // k-windows the finalize kernels looked up again (two per request on the thread path)
        RCX_C_NEDITS,                             // edits written by the gather kernel of the compact host interface
+       RCX_C_DIAG0, RCX_C_DIAG_END = RCX_C_DIAG0 + 13,  // diagnostic builds (-DRCX_DIAG): search-walk length against untrusted-window count
        RCX_C_SINK,                               // scratch word of the random-read micro-benchmark
        RCX_C_COUNT = RCX_C_SINK + 4 };
 

@@ -552,6 +552,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                 }
             }
             st[ST_STATUS] = RCX_ST_SEARCH; st[ST_TOTALFIX] = rcx_force_bound(strong, er); st[ST_BADSEG] = 0;
+#ifdef RCX_DIAG
+            st[ST_BADSEG] = nun;  // (in: the search kernel reads it at the fetch and overwrites it at the item's end)
+#endif
             st[ST_STRONG] = strong; st[ST_TRUST] = trust; st[ST_NSEG] = nseg < nseg_cap ? nseg : nseg_cap;
             st[ST_OFF] = (int)o; st[ST_LEN] = len;
         }

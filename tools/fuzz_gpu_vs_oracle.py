@@ -77,7 +77,7 @@ def main():
                     x.seq = seq
             b = T.interleave(*bs) if paired else bs[0]
             if a.chunks:
-                os.environ["RCX_CHUNK_READS"] = str(rng.choice([2, 6, 50, 334, 1000]))
+                os.environ["RCX_CHUNK_READS"] = str(rng.choice([26, 150, 334, 1000, 4000]))
             codes, counts = T.dump_to_arrays(d["dump"], k)
             table = T.OracleTable(k)
             table.load_dump(d["dump"])

@@ -17,6 +17,7 @@ def main():
 
     from rcorrector_b200 import INTERLEAVED, Corrector
 
+    only = [int(x) for x in sys.argv[1:] if x.isdigit()]  # read seeds to run (default: all eight)
     a = bench.parse_args(["--config", "3"])
     dev = torch.device("cuda", 0)
     td = bench.gen_table(a)
@@ -27,6 +28,8 @@ def main():
     cor.set_params(a.k, 0.01, ord("0"), a.maxcork)
     rows = []
     for rs, nr in bench.shard_plan(a, 1, 0):
+        if only and rs not in only:
+            continue
         d = bench.gen_shard(a, rs, nr)
         seq = torch.from_numpy(np.fromfile(os.path.join(d, "reads.seq"), dtype=np.uint8)).to(dev)
         qual = torch.from_numpy(np.fromfile(os.path.join(d, "reads.qual"), dtype=np.uint8)).to(dev)
@@ -47,6 +50,10 @@ def main():
         row = {"read_seed": rs, "ms_scan": round(best["ms_scan"], 2), "ms_dfs": round(best["ms_dfs"], 2), "ms_finalize": round(best["ms_finalize"], 2),
                "work_items": best["work_items"], "heavy_items": best["heavy_items"], "search_nodes": best["search_nodes"],
                "search_probes": best["search_probes"], "second_pass": best["second_pass"]}
+        if "diag" in os.environ.get("RCX_LIB", ""):  # -DRCX_DIAG build: walk length against untrusted-window count (buckets of 32)
+            dc = [int(x) for x in cor.debug_counters(36)[17:30]]
+            row["diag"] = {"max_nodes_of_one_item": dc[0], "items_by_untrusted_windows_0_32_64_96": dc[1:5],
+                           "items_over_2000_nodes": dc[5:9], "their_nodes": dc[9:13]}
         rows.append(row)
         print(json.dumps(row), flush=True)
         del seq, qual, off, work, res
