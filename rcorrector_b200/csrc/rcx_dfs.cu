@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     // whole warps (light ones of the first pass)
     const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
     const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
+    const long long nvh = a.pass == 0 ? (long long)a.counters[RCX_C_NVH] : 0;  // very heavy items: listed, taken before the sweep over the heavy slots
     const bool batch = BATCH && a.pass == 0;
-    const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
+    const long long ndyn = a.pass == 0 ? nvh + (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
     const long long nbatch = batch ? nlight : 0;
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
     // per-thread scratch, interleaved by lane
@@ -194,11 +195,14 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
 
     for (;;) {
         bool have_item = false;
+        int expect = RCX_ST_SEARCH;
         if (stage == T_FETCH) {
             if (nx_w < ndyn) {  // reserved while the previous item was searched
                 const long long w = nx_w;
                 nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
-                item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy items first
+                if (a.pass != 0) item = (long long)a.worklist2[w];
+                else if (w < nvh) { item = (long long)a.vhlist[w]; expect = RCX_ST_SEARCH_VH; }  // the likely longest walks first
+                else item = rcx_work_slot(w - nvh, nheavy, a.n);                                   // then the heavy slots, then the light ones
                 have_item = true;
             } else {
                 stage = T_IDLE;
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
             seg0a = *reinterpret_cast<const int4*>(st + 8);
             seg0b = *reinterpret_cast<const int4*>(st + 12);
-            if (h0.x != RCX_ST_SEARCH) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass): next one
+            if (h0.x != expect) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass), or a listed very heavy item met by the sweep: next one
             const uint32_t o = (uint32_t)h1.z;    // ST_OFF / ST_LEN: written with the header, no worklist -> off[] chase
             len = h1.w;
             pinfo = a.posbuf + o;
