@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
     const long long nvh = a.pass == 0 ? (long long)a.counters[RCX_C_NVH] : 0;  // very heavy items: listed, taken before the sweep over the heavy slots
     const bool batch = BATCH && a.pass == 0;
-    const long long ndyn = a.pass == 0 ? nvh + (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
+    const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
     const long long nbatch = batch ? nlight : 0;
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
     // per-thread scratch, interleaved by lane
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
 
     unsigned long long n_nodes = 0, n_probes = 0;
 #ifdef RCX_DIAG
-    unsigned long long diag_n0 = 0;
+    unsigned long long diag_n0 = 0, diag_p0 = 0;
     int diag_nun = 0;
 #endif
     // ---- per-item state
@@ -189,33 +189,54 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     RcxEntryRegs pf_d;
     pf_d.q0 = pf_d.q1 = pf_d.q2 = pf_d.q3 = 0;
     bool pf_on = false;
-    int stage = T_FETCH;
+    // Order of a launch (warp-uniform `phase`): 0 = the very heavy items, 32 listed slots per warp, the lanes that finish wait for
+    // their batch-mates -- so a walk of thousands of nodes ends up ALONE in its warp (1.4 us per node) instead of sharing its
+    // trips around the state machine with 31 other walks (3.4 us per node: one such read made one of eight 6 M-read shards
+    // take 20 ms instead of 12.5, profiles/r02_i, r02_k); 1 = items taken one by one per lane (heavy slots, second pass);
+    // 2 = light items in batches.
+    int phase = (a.pass == 0 && nvh > 0) ? 0 : 1;
+    int stage = phase == 0 ? T_IDLE : T_FETCH;
     int4 seg0a = make_int4(0, 0, 0, 0), seg0b = make_int4(0, 0, 0, 0);
-    long long nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
+    long long nx_w = -1;  // the lane's next dynamic item (reserved one ahead)
 
     for (;;) {
         bool have_item = false;
         int expect = RCX_ST_SEARCH;
         if (stage == T_FETCH) {
-            if (nx_w < ndyn) {  // reserved while the previous item was searched
-                const long long w = nx_w;
-                nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
-                if (a.pass != 0) item = (long long)a.worklist2[w];
-                else if (w < nvh) { item = (long long)a.vhlist[w]; expect = RCX_ST_SEARCH_VH; }  // the likely longest walks first
-                else item = rcx_work_slot(w - nvh, nheavy, a.n);                                   // then the heavy slots, then the light ones
-                have_item = true;
+            if (phase == 0) {
+                stage = T_IDLE;  // very heavy batch: wait for the batch-mates
             } else {
-                stage = T_IDLE;
+                if (nx_w < 0) nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
+                if (nx_w < ndyn) {  // reserved while the previous item was searched
+                    const long long w = nx_w;
+                    nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
+                    item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy slots first (listed very heavy ones are passed by)
+                    have_item = true;
+                } else {
+                    stage = T_IDLE;
+                }
             }
         }
-        {   // every lane comes by here once per trip: when the whole warp is out of work it takes the next 32 light items
+        {   // every lane comes by here once per trip: when the whole warp is out of work it takes the next batch of its phase
             const unsigned int idle = __ballot_sync(RCX_FULL, stage == T_IDLE);
             if (idle == RCX_FULL) {
                 long long base = 0;
-                if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
-                base = __shfl_sync(RCX_FULL, base, 0);
-                if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
-                if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
+                if (phase == 0) {
+                    if (lane == 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKV], 32ull);
+                    base = __shfl_sync(RCX_FULL, base, 0);
+                    if (base < nvh) {
+                        if (base + lane < nvh) { item = (long long)a.vhlist[base + lane]; expect = RCX_ST_SEARCH_VH; have_item = true; }
+                    } else {  // (uniform) the list is exhausted: on to the items taken one by one
+                        phase = 1;
+                        stage = T_FETCH;
+                        continue;
+                    }
+                } else {
+                    if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
+                    base = __shfl_sync(RCX_FULL, base, 0);
+                    if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
+                    if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
+                }
             }
         }
         if (have_item) {
@@ -231,7 +252,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             fix = a.fixbuf + o;
             nseg = h1.y; trust = h1.x; fbound = h0.y;  // (ST_TOTALFIX carries rcx_force_bound(strong) in)
 #ifdef RCX_DIAG
-            diag_nun = h0.z; diag_n0 = n_nodes;
+            diag_nun = h0.z; diag_n0 = n_nodes; diag_p0 = n_probes;
 #endif
             max_top2 = -1;
             na_base = 0;  // fix[] = -1 (:1113-1114): no accepted edits yet
@@ -269,7 +290,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     const int bkt = diag_nun >= 128 ? 3 : (diag_nun >> 5);
                     atomicMax(&a.counters[RCX_C_DIAG0], dn);
                     atomicAdd(&a.counters[RCX_C_DIAG0 + 1 + bkt], 1ull);                 // items per bucket
-                    if (dn > 2000) { atomicAdd(&a.counters[RCX_C_DIAG0 + 5 + bkt], 1ull); atomicAdd(&a.counters[RCX_C_DIAG0 + 9 + bkt], dn); }
+                    if (dn > 2000) { atomicAdd(&a.counters[RCX_C_DIAG0 + 5 + bkt], 1ull); atomicAdd(&a.counters[RCX_C_DIAG0 + 9 + bkt], n_probes - diag_p0); }
                 }
 #endif
                 if (rethreshold) {

@@ -15,6 +15,7 @@ enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SE
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
        RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
        RCX_C_NVH,                                // VERY heavy work items (nearly every k-window untrusted): listed apart, searched before everything else
+       RCX_C_WORKV,                              // search kernel: next batch of 32 very heavy items
        RCX_C_WORKB,                              // search kernel: next batch of 32 light items
        RCX_C_NWORKH,                             // HEAVY work items (long untrusted spans): slots n-1, n-2, ... of the work list, searched first
        RCX_C_RESCAN_WINDOWS,                     // k-windows the finalize kernels looked up again (two per request on the thread path)
