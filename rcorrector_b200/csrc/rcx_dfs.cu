@@ -94,6 +94,9 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #ifndef DFS_TAIL_PREFETCH
 #define DFS_TAIL_PREFETCH 0  // lanes: at or below this many active lanes in the node loop, the keep-base child's sector is prefetched into L2.  Measured: no gain (2 GPUs, rank 1 search 54.96 ms off, 56.12 at 4 lanes, 56.38 at 12, gpurun_out/r02_n2c) -> off
 #endif
+#ifndef DFS_EXCLUSIVE_NODES
+#define DFS_EXCLUSIVE_NODES 1500  // nodes after which a walk gets its warp to itself (0: never)
+#endif
 #ifndef DFS_BATCH
 // 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
 // taken by a whole warp at a time, 32 consecutive slots, and a lane that finishes waits for the others: items of one
@@ -198,11 +201,20 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     int stage = phase == 0 ? T_IDLE : T_FETCH;
     int4 seg0a = make_int4(0, 0, 0, 0), seg0b = make_int4(0, 0, 0, 0);
     long long nx_w = -1;  // the lane's next dynamic item (reserved one ahead)
+    unsigned int item_n0 = 0;  // node counter at the start of the lane's item
 
     for (;;) {
         bool have_item = false;
         int expect = RCX_ST_SEARCH;
-        if (stage == T_FETCH) {
+        // A walk that has run for DFS_EXCLUSIVE_NODES nodes gets the warp to itself: the other lanes finish their items and
+        // take no new one until it is done.  Sharing its trips around the state machine with 31 other walks such a walk
+        // advances at 3.4 us per node, alone at 1.4 (one read of 5 876 nodes made one of eight 6 M-read shards take 20 ms
+        // instead of 12.5: profiles/r02_i, r02_k); it happens once in millions of reads, so the idle lanes cost nothing.
+        const bool walking = stage != T_IDLE && stage != T_FETCH;
+        const unsigned int excl = DFS_EXCLUSIVE_NODES > 0
+                                      ? __ballot_sync(RCX_FULL, walking && (int)((unsigned int)n_nodes - item_n0) > DFS_EXCLUSIVE_NODES)
+                                      : 0u;
+        if (stage == T_FETCH && excl == 0) {
             if (phase == 0) {
                 stage = T_IDLE;  // very heavy batch: wait for the batch-mates
             } else {
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             }
         }
         if (have_item) {
+            item_n0 = (unsigned int)n_nodes;
             st = a.state + item * stride;
             // header (8 words) + first segment in one round trip: four independent 16-byte loads
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
