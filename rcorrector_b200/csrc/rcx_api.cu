@@ -722,11 +722,9 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     // heavy = at least 2k untrusted k-windows (one isolated error explains k of them); RCX_HEAVY_WINDOWS overrides, 0 = off
     sa.heavy_windows = 2 * c->k;
     if (const char* e = getenv("RCX_HEAVY_WINDOWS")) sa.heavy_windows = atoi(e);
-    // very heavy (RCX_VHEAVY_WINDOWS = n > 0, off by default): items with at least n untrusted windows are listed apart and searched
-    // first, 32 per warp.  Measured with n = 3/4 of the windows (gpurun_out/r02_m): the k = 31 / -maxcorK 8 shape gains (search 52.5 ->
-    // 41.7 ms), a shard with one 5 876-node walk gains (20.2 -> 15.2 ms), ordinary shards lose (13.5 -> 16.0 ms; 10 M x 100 bp
-    // 16.9 -> 17.9 ms): the long walk is handled by the exclusive mode of the search kernel instead.
-    sa.vheavy_windows = 0;
+    // very heavy = at least three quarters of the longest read's windows untrusted: listed apart; the search kernel takes them
+    // first, in warp batches, when they are at least a quarter of the work items (rcx_dfs.cu).  RCX_VHEAVY_WINDOWS overrides, 0 = off
+    sa.vheavy_windows = std::max(sa.heavy_windows + 1, 3 * (max_len - c->k + 1) / 4);
     if (const char* e = getenv("RCX_VHEAVY_WINDOWS")) sa.vheavy_windows = atoi(e);
     sa.vhlist = correct ? sl.d_worklist2.p + n : nullptr;
     if (!(thread_scan && rcx_finalize_thread_supported(max_len, c->k)))

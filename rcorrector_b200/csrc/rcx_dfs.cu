@@ -95,7 +95,8 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #define DFS_TAIL_PREFETCH 0  // lanes: at or below this many active lanes in the node loop, the keep-base child's sector is prefetched into L2.  Measured: no gain (2 GPUs, rank 1 search 54.96 ms off, 56.12 at 4 lanes, 56.38 at 12, gpurun_out/r02_n2c) -> off
 #endif
 #ifndef DFS_EXCLUSIVE_NODES
-#define DFS_EXCLUSIVE_NODES 1500  // nodes after which a walk gets its warp to itself (0: never)
+#define DFS_EXCLUSIVE_NODES 0  // nodes after which a walk gets its warp to itself (0: never).  Measured at 1 500 (gpurun_out/r02_n): slower everywhere
+                               // (10 M x 100 bp search 16.9 -> 18.2 ms; the shard with the 5 876-node walk 20.2 -> 24.0 ms): the ballot per trip costs more than the isolation gives
 #endif
 #ifndef DFS_BATCH
 // 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
@@ -146,7 +147,12 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     // whole warps (light ones of the first pass)
     const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
     const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
-    const long long nvh = a.pass == 0 ? (long long)a.counters[RCX_C_NVH] : 0;  // very heavy items: listed, taken before the sweep over the heavy slots
+    // very heavy items (listed by the scan): taken first, 32 per warp, when they are at least a quarter of the work items -- then
+    // they are the bulk of the search and alike (k = 31 / -maxcorK 8 / 5 % errors: 52.5 -> 42.7 ms); when they are few the batches'
+    // idle lanes cost more than they give (150-bp pairs at 1 % errors, 0.7 % of the items: 13.5 -> 16.0 ms) and they stay in the sweep
+    const long long nvh_listed = a.pass == 0 ? (long long)a.counters[RCX_C_NVH] : 0;
+    const bool use_vh = nvh_listed * 4 >= (long long)a.counters[RCX_C_NWORK] + (long long)a.counters[RCX_C_NWORKH] && nvh_listed > 0;
+    const long long nvh = use_vh ? nvh_listed : 0;
     const bool batch = BATCH && a.pass == 0;
     const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
     const long long nbatch = batch ? nlight : 0;
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
             seg0a = *reinterpret_cast<const int4*>(st + 8);
             seg0b = *reinterpret_cast<const int4*>(st + 12);
-            if (h0.x != expect) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass), or a listed very heavy item met by the sweep: next one
+            if (h0.x != expect && !(h0.x == RCX_ST_SEARCH_VH && !use_vh)) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass), or a listed very heavy item met by the sweep: next one
             const uint32_t o = (uint32_t)h1.z;    // ST_OFF / ST_LEN: written with the header, no worklist -> off[] chase
             len = h1.w;
             pinfo = a.posbuf + o;
