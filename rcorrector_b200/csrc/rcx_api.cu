@@ -702,7 +702,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     CUDA_TRY(sl.d_flags.ensure((size_t)n + 2));
     if (correct) {
         CUDA_TRY(sl.d_worklist.ensure((size_t)n + 2));
-        CUDA_TRY(sl.d_worklist2.ensure(2 * (size_t)n + 4));  // second-pass list, then (from n) the list of the very heavy items
+        CUDA_TRY(sl.d_worklist2.ensure((size_t)n + 2));
         CUDA_TRY(sl.d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
         CUDA_TRY(sl.d_fixbuf.ensure(2 * (span + 96)));  // dense fix[] (1 byte per base) or 16-bit edit lists (a count + up to len - 1 edits per read)
         CUDA_TRY(sl.d_posbuf.ensure(span + 96));
@@ -722,13 +722,8 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     // heavy = at least 2k untrusted k-windows (one isolated error explains k of them); RCX_HEAVY_WINDOWS overrides, 0 = off
     sa.heavy_windows = 2 * c->k;
     if (const char* e = getenv("RCX_HEAVY_WINDOWS")) sa.heavy_windows = atoi(e);
-    // very heavy = at least three quarters of the longest read's windows untrusted: listed apart; the search kernel takes them
-    // first, in warp batches, when they are at least a quarter of the work items (rcx_dfs.cu).  RCX_VHEAVY_WINDOWS overrides, 0 = off
-    sa.vheavy_windows = std::max(sa.heavy_windows + 1, 3 * (max_len - c->k + 1) / 4);
-    if (const char* e = getenv("RCX_VHEAVY_WINDOWS")) sa.vheavy_windows = atoi(e);
-    sa.vhlist = correct ? sl.d_worklist2.p + n : nullptr;
     if (!(thread_scan && rcx_finalize_thread_supported(max_len, c->k)))
-        sa.heavy_windows = sa.vheavy_windows = 0;  // (the warp-per-read kernels keep one list)
+        sa.heavy_windows = 0;  // (the warp-per-read kernels keep one list)
     sa.posbuf = correct ? sl.d_posbuf.p + lead - first_base : nullptr;
     sa.fixbuf = correct ? sl.d_fixbuf.p + lead - first_base : nullptr;
     sa.fixlist = correct ? reinterpret_cast<unsigned short*>(sl.d_fixbuf.p) + lead - first_base : nullptr;
@@ -749,7 +744,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         ca.qbits = d_qbits; ca.has_qual = has_qual; ca.emit_edits = emit_edits ? 1 : 0;
         ca.counts = sa.counts; ca.thr = sl.d_thr.p; ca.flags = sl.d_flags.p;
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = sl.d_counters;
-        ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.vhlist = sl.d_worklist2.p + n; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
+        ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
         int dfs_grid = 0;
         rcx_dfs_geometry(c->sm_count, max_len, c->k, c->params.max_fix_per_k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
         CUDA_TRY(sl.d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));

@@ -94,10 +94,6 @@ __device__ __forceinline__ int dfs_infer(int c0, int c1, int c2, int c3, int upp
 #ifndef DFS_TAIL_PREFETCH
 #define DFS_TAIL_PREFETCH 0  // lanes: at or below this many active lanes in the node loop, the keep-base child's sector is prefetched into L2.  Measured: no gain (2 GPUs, rank 1 search 54.96 ms off, 56.12 at 4 lanes, 56.38 at 12, gpurun_out/r02_n2c) -> off
 #endif
-#ifndef DFS_EXCLUSIVE_NODES
-#define DFS_EXCLUSIVE_NODES 0  // nodes after which a walk gets its warp to itself (0: never).  Measured at 1 500 (gpurun_out/r02_n): slower everywhere
-                               // (10 M x 100 bp search 16.9 -> 18.2 ms; the shard with the 5 876-node walk 20.2 -> 24.0 ms): the ballot per trip costs more than the isolation gives
-#endif
 #ifndef DFS_BATCH
 // 1: the LIGHT work items (the scan kernel files them sorted by their number of untrusted k-windows within every tile) are
 // taken by a whole warp at a time, 32 consecutive slots, and a lane that finishes waits for the others: items of one
@@ -147,12 +143,6 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     // whole warps (light ones of the first pass)
     const long long nheavy = a.pass == 0 ? (long long)a.counters[RCX_C_NWORKH] : 0;
     const long long nlight = a.pass == 0 ? (long long)a.counters[RCX_C_NWORK] : 0;
-    // very heavy items (listed by the scan): taken first, 32 per warp, when they are at least a quarter of the work items -- then
-    // they are the bulk of the search and alike (k = 31 / -maxcorK 8 / 5 % errors: 52.5 -> 42.7 ms); when they are few the batches'
-    // idle lanes cost more than they give (150-bp pairs at 1 % errors, 0.7 % of the items: 13.5 -> 16.0 ms) and they stay in the sweep
-    const long long nvh_listed = a.pass == 0 ? (long long)a.counters[RCX_C_NVH] : 0;
-    const bool use_vh = nvh_listed * 4 >= (long long)a.counters[RCX_C_NWORK] + (long long)a.counters[RCX_C_NWORKH] && nvh_listed > 0;
-    const long long nvh = use_vh ? nvh_listed : 0;
     const bool batch = BATCH && a.pass == 0;
     const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
     const long long nbatch = batch ? nlight : 0;
@@ -174,7 +164,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
 
     unsigned long long n_nodes = 0, n_probes = 0;
 #ifdef RCX_DIAG
-    unsigned long long diag_n0 = 0, diag_p0 = 0;
+    unsigned long long diag_n0 = 0;
     int diag_nun = 0;
 #endif
     // ---- per-item state
@@ -198,80 +188,46 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     RcxEntryRegs pf_d;
     pf_d.q0 = pf_d.q1 = pf_d.q2 = pf_d.q3 = 0;
     bool pf_on = false;
-    // Order of a launch (warp-uniform `phase`): 0 = the very heavy items, 32 listed slots per warp, the lanes that finish wait for
-    // their batch-mates -- so a walk of thousands of nodes ends up ALONE in its warp (1.4 us per node) instead of sharing its
-    // trips around the state machine with 31 other walks (3.4 us per node: one such read made one of eight 6 M-read shards
-    // take 20 ms instead of 12.5, profiles/r02_i, r02_k); 1 = items taken one by one per lane (heavy slots, second pass);
-    // 2 = light items in batches.
-    int phase = (a.pass == 0 && nvh > 0) ? 0 : 1;
-    int stage = phase == 0 ? T_IDLE : T_FETCH;
+    int stage = T_FETCH;
     int4 seg0a = make_int4(0, 0, 0, 0), seg0b = make_int4(0, 0, 0, 0);
-    long long nx_w = -1;  // the lane's next dynamic item (reserved one ahead)
-    unsigned int item_n0 = 0;  // node counter at the start of the lane's item
+    long long nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
 
     for (;;) {
         bool have_item = false;
-        int expect = RCX_ST_SEARCH;
-        // A walk that has run for DFS_EXCLUSIVE_NODES nodes gets the warp to itself: the other lanes finish their items and
-        // take no new one until it is done.  Sharing its trips around the state machine with 31 other walks such a walk
-        // advances at 3.4 us per node, alone at 1.4 (one read of 5 876 nodes made one of eight 6 M-read shards take 20 ms
-        // instead of 12.5: profiles/r02_i, r02_k); it happens once in millions of reads, so the idle lanes cost nothing.
-        const bool walking = stage != T_IDLE && stage != T_FETCH;
-        const unsigned int excl = DFS_EXCLUSIVE_NODES > 0
-                                      ? __ballot_sync(RCX_FULL, walking && (int)((unsigned int)n_nodes - item_n0) > DFS_EXCLUSIVE_NODES)
-                                      : 0u;
-        if (stage == T_FETCH && excl == 0) {
-            if (phase == 0) {
-                stage = T_IDLE;  // very heavy batch: wait for the batch-mates
+        if (stage == T_FETCH) {
+            if (nx_w < ndyn) {  // reserved while the previous item was searched
+                const long long w = nx_w;
+                nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
+                item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy items first
+                have_item = true;
             } else {
-                if (nx_w < 0) nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
-                if (nx_w < ndyn) {  // reserved while the previous item was searched
-                    const long long w = nx_w;
-                    nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
-                    item = a.pass == 0 ? rcx_work_slot(w, nheavy, a.n) : (long long)a.worklist2[w];  // heavy slots first (listed very heavy ones are passed by)
-                    have_item = true;
-                } else {
-                    stage = T_IDLE;
-                }
+                stage = T_IDLE;
             }
         }
-        {   // every lane comes by here once per trip: when the whole warp is out of work it takes the next batch of its phase
+        {   // every lane comes by here once per trip: when the whole warp is out of work it takes the next 32 light items
             const unsigned int idle = __ballot_sync(RCX_FULL, stage == T_IDLE);
             if (idle == RCX_FULL) {
                 long long base = 0;
-                if (phase == 0) {
-                    if (lane == 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKV], 32ull);
-                    base = __shfl_sync(RCX_FULL, base, 0);
-                    if (base < nvh) {
-                        if (base + lane < nvh) { item = (long long)a.vhlist[base + lane]; expect = RCX_ST_SEARCH_VH; have_item = true; }
-                    } else {  // (uniform) the list is exhausted: on to the items taken one by one
-                        phase = 1;
-                        stage = T_FETCH;
-                        continue;
-                    }
-                } else {
-                    if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
-                    base = __shfl_sync(RCX_FULL, base, 0);
-                    if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
-                    if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
-                }
+                if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
+                base = __shfl_sync(RCX_FULL, base, 0);
+                if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
+                if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
             }
         }
         if (have_item) {
-            item_n0 = (unsigned int)n_nodes;
             st = a.state + item * stride;
             // header (8 words) + first segment in one round trip: four independent 16-byte loads
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
             seg0a = *reinterpret_cast<const int4*>(st + 8);
             seg0b = *reinterpret_cast<const int4*>(st + 12);
-            if (h0.x != expect && !(h0.x == RCX_ST_SEARCH_VH && !use_vh)) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass), or a listed very heavy item met by the sweep: next one
+            if (h0.x != RCX_ST_SEARCH) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass): next one
             const uint32_t o = (uint32_t)h1.z;    // ST_OFF / ST_LEN: written with the header, no worklist -> off[] chase
             len = h1.w;
             pinfo = a.posbuf + o;
             fix = a.fixbuf + o;
             nseg = h1.y; trust = h1.x; fbound = h0.y;  // (ST_TOTALFIX carries rcx_force_bound(strong) in)
 #ifdef RCX_DIAG
-            diag_nun = h0.z; diag_n0 = n_nodes; diag_p0 = n_probes;
+            diag_nun = h0.z; diag_n0 = n_nodes;
 #endif
             max_top2 = -1;
             na_base = 0;  // fix[] = -1 (:1113-1114): no accepted edits yet
@@ -309,7 +265,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
                     const int bkt = diag_nun >= 128 ? 3 : (diag_nun >> 5);
                     atomicMax(&a.counters[RCX_C_DIAG0], dn);
                     atomicAdd(&a.counters[RCX_C_DIAG0 + 1 + bkt], 1ull);                 // items per bucket
-                    if (dn > 2000) { atomicAdd(&a.counters[RCX_C_DIAG0 + 5 + bkt], 1ull); atomicAdd(&a.counters[RCX_C_DIAG0 + 9 + bkt], n_probes - diag_p0); }
+                    if (dn > 2000) { atomicAdd(&a.counters[RCX_C_DIAG0 + 5 + bkt], 1ull); atomicAdd(&a.counters[RCX_C_DIAG0 + 9 + bkt], dn); }
                 }
 #endif
                 if (rethreshold) {

@@ -51,9 +51,9 @@ def main():
                "work_items": best["work_items"], "heavy_items": best["heavy_items"], "search_nodes": best["search_nodes"],
                "search_probes": best["search_probes"], "second_pass": best["second_pass"]}
         if "diag" in os.environ.get("RCX_LIB", ""):  # -DRCX_DIAG build: walk length against untrusted-window count (buckets of 32)
-            dc = [int(x) for x in cor.debug_counters(36)[18:31]]  # RCX_C_DIAG0 = 18
+            dc = [int(x) for x in cor.debug_counters(36)[17:30]]  # RCX_C_DIAG0 = 17
             row["diag"] = {"max_nodes_of_one_item": dc[0], "items_by_untrusted_windows_0_32_64_96": dc[1:5],
-                           "items_over_2000_nodes": dc[5:9], "their_table_requests": dc[9:13]}
+                           "items_over_2000_nodes": dc[5:9], "their_nodes": dc[9:13]}
         rows.append(row)
         print(json.dumps(row), flush=True)
         del seq, qual, off, work, res
