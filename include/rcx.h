@@ -61,6 +61,8 @@ typedef struct {
     uint64_t work_items;     /* reads that needed the search (not all-trusted, not rejected) */
     uint64_t second_pass;    /* of those, reads that took the second pass of the A.4 loop */
     uint64_t heavy_items;    /* of the work items, those filed as likely long searches (searched first) */
+    uint64_t vheavy_items;   /* of those, the ones with at least three quarters of their k-windows untrusted (a quarter of the work items being so
+                                switches the NEXT batch's search to warp batches over them) */
     uint64_t rescan_windows; /* k-windows of the l/m/h re-scan (GetKmerInformation looks every one of them up) */
     uint64_t unsupported;    /* must be 0: a read that would need a third A.4 pass, a count >= 2^29, an edit-row overflow */
 } rcx_stats;

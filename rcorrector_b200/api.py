@@ -33,7 +33,7 @@ class RcxStats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("ms_scan", C.c_float), ("ms_correct", C.c_float),
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_triage", C.c_float), ("ms_prep", C.c_float), ("ms_dfs", C.c_float), ("ms_finalize", C.c_float),
-                ("work_items", C.c_uint64), ("second_pass", C.c_uint64), ("heavy_items", C.c_uint64), ("rescan_windows", C.c_uint64), ("unsupported", C.c_uint64)]
+                ("work_items", C.c_uint64), ("second_pass", C.c_uint64), ("heavy_items", C.c_uint64), ("vheavy_items", C.c_uint64), ("rescan_windows", C.c_uint64), ("unsupported", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -118,6 +118,7 @@ struct rcx_ctx {
     int nslots = 3;  // slots a host batch cycles through (RCX_SLOTS)
     int chain = 0;   // RCX_CHAIN: 1 = a chunk's kernels start when the previous chunk has reached its finalize kernel, 2 = when it is done
     rcx_stats stats{};
+    bool vh_mode = false;  // the next batch's search starts with batches over its very heavy items (picked from the last harvested batch)
     // k-mer counting (rcx_count_kmers_*): the counting table, and after finish() the kept records
     unsigned long long* cnt_keys = nullptr;
     unsigned int* cnt_counts = nullptr;
@@ -702,7 +703,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     CUDA_TRY(sl.d_flags.ensure((size_t)n + 2));
     if (correct) {
         CUDA_TRY(sl.d_worklist.ensure((size_t)n + 2));
-        CUDA_TRY(sl.d_worklist2.ensure((size_t)n + 2));
+        CUDA_TRY(sl.d_worklist2.ensure(2 * (size_t)n + 4));  // second-pass list, then (from n) vh mode's list of the very heavy items
         CUDA_TRY(sl.d_state.ensure((size_t)n * rcx_state_words(max_len, c->k) + 64));
         CUDA_TRY(sl.d_fixbuf.ensure(2 * (span + 96)));  // dense fix[] (1 byte per base) or 16-bit edit lists (a count + up to len - 1 edits per read)
         CUDA_TRY(sl.d_posbuf.ensure(span + 96));
@@ -722,8 +723,14 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     // heavy = at least 2k untrusted k-windows (one isolated error explains k of them); RCX_HEAVY_WINDOWS overrides, 0 = off
     sa.heavy_windows = 2 * c->k;
     if (const char* e = getenv("RCX_HEAVY_WINDOWS")) sa.heavy_windows = atoi(e);
+    // very heavy = at least three quarters of the longest read's windows untrusted: always counted; in vh mode (the previous batch
+    // counted a quarter of its work items as such; RCX_VH_MODE=0/1 forces) also listed for the search kernel's opening batches
+    sa.vheavy_windows = std::max(sa.heavy_windows + 1, 3 * (max_len - c->k + 1) / 4);
+    sa.vh_mode = c->vh_mode ? 1 : 0;
+    if (const char* e = getenv("RCX_VH_MODE")) sa.vh_mode = atoi(e) != 0;
+    sa.vhlist = correct ? sl.d_worklist2.p + n : nullptr;
     if (!(thread_scan && rcx_finalize_thread_supported(max_len, c->k)))
-        sa.heavy_windows = 0;  // (the warp-per-read kernels keep one list)
+        sa.heavy_windows = sa.vheavy_windows = sa.vh_mode = 0;  // (the warp-per-read kernels keep one list)
     sa.posbuf = correct ? sl.d_posbuf.p + lead - first_base : nullptr;
     sa.fixbuf = correct ? sl.d_fixbuf.p + lead - first_base : nullptr;
     sa.fixlist = correct ? reinterpret_cast<unsigned short*>(sl.d_fixbuf.p) + lead - first_base : nullptr;
@@ -744,7 +751,7 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
         ca.qbits = d_qbits; ca.has_qual = has_qual; ca.emit_edits = emit_edits ? 1 : 0;
         ca.counts = sa.counts; ca.thr = sl.d_thr.p; ca.flags = sl.d_flags.p;
         ca.correction = d_corr; ca.l = d_l; ca.m = d_m; ca.h = d_h; ca.counters = sl.d_counters;
-        ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
+        ca.worklist = sl.d_worklist.p; ca.worklist2 = sl.d_worklist2.p; ca.vhlist = sl.d_worklist2.p + n; ca.vh_mode = sa.vh_mode; ca.state = sl.d_state.p; ca.fixbuf = sa.fixbuf; ca.pass = 0;
         int dfs_grid = 0;
         rcx_dfs_geometry(c->sm_count, max_len, c->k, c->params.max_fix_per_k, &dfs_grid, &ca.dfs_depth, &ca.dfs_lpad);
         CUDA_TRY(sl.d_dfs_stack.ensure(rcx_dfs_stack_words(dfs_grid, ca.dfs_depth)));
@@ -791,6 +798,9 @@ static int harvest(rcx_ctx* c, RcxSlot& sl) {
     c->stats.search_nodes += h[RCX_C_SEARCH_NODES];
     c->stats.work_items += h[RCX_C_NWORK] + h[RCX_C_NWORKH];
     c->stats.heavy_items += h[RCX_C_NWORKH];
+    c->stats.vheavy_items += h[RCX_C_NVH];
+    if (h[RCX_C_NWORK] + h[RCX_C_NWORKH] >= 1024)  // (a batch large enough to say something about the next one)
+        c->vh_mode = 4 * h[RCX_C_NVH] >= h[RCX_C_NWORK] + h[RCX_C_NWORKH];
     c->stats.second_pass += h[RCX_C_NWORK2];
     c->stats.unsupported += h[RCX_C_UNSUPPORTED];
     {   // test hook (tests/test_gpu_golden.py): RCX_TEST_FORCE_UNSUPPORTED=n flags the n-th harvested batch of the process

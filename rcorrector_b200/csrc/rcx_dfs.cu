@@ -125,7 +125,14 @@ __host__ __device__ inline int dfs_cap_path(int max_len, int k, int K) {
 // read filter does not count -- continues in a spill area of the same global scratch; both global lists have max_len
 // entries (a position is edited at most once: the segments are disjoint and substitutions happen on untrusted positions).
 __host__ __device__ inline int dfs_row_entries(int max_len, int k, int K) { return dfs_cap_path(max_len, k, K) | 1; }  // odd: rows spread over the banks
-template <bool SMEM, bool BATCH>
+// VH ("vh mode", first pass only): the launch starts with warp batches over the listed very heavy items (at least three quarters
+// of their k-windows untrusted) -- 32 listed slots per warp, a lane that finishes waits for the others -- before the items taken
+// one by one.  Where such items are the bulk of the work (k = 31 / -maxcorK 8 / 5 % errors) they are alike and long, and batches
+// of them are a fifth faster than the per-lane fetch (search 52.5 -> 41.7 ms per 8 M reads); where they are few (0.7 % of the
+// items of 150-bp pairs at 1 % errors) the batches' idle lanes cost more than they give, and the mere presence of the phase
+// logic slows the kernel by 8-20 % (profiles/r02_m_search_order_experiments.md) -- hence a template instantiation of its own,
+// which the host picks for a batch when the PREVIOUS batch counted at least a quarter of its work items as very heavy.
+template <bool SMEM, bool BATCH, bool VH>
 __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(RcxCorrectArgs a) {
     __shared__ int lut[DFS_LUT];
     extern __shared__ __align__(16) unsigned short dfs_rows[];
@@ -146,6 +153,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     const bool batch = BATCH && a.pass == 0;
     const long long ndyn = a.pass == 0 ? (batch ? nheavy : nheavy + nlight) : (long long)a.counters[RCX_C_NWORK2];
     const long long nbatch = batch ? nlight : 0;
+    const long long nvh = (VH && a.pass == 0) ? (long long)a.counters[RCX_C_NVH] : 0;
     const int fetch_counter = a.pass == 0 ? RCX_C_WORKX1 : RCX_C_WORKX3;
     // per-thread scratch, interleaved by lane
     const long long gwarp = ((long long)blockIdx.x * DFS_THREADS + threadIdx.x) >> 5;
@@ -188,13 +196,18 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
     RcxEntryRegs pf_d;
     pf_d.q0 = pf_d.q1 = pf_d.q2 = pf_d.q3 = 0;
     bool pf_on = false;
-    int stage = T_FETCH;
+    bool vh_phase = VH && nvh > 0;  // (warp-uniform) still in the batches over the listed very heavy items
+    int stage = vh_phase ? T_IDLE : T_FETCH;
     int4 seg0a = make_int4(0, 0, 0, 0), seg0b = make_int4(0, 0, 0, 0);
-    long long nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
+    long long nx_w = vh_phase ? -1 : (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
 
     for (;;) {
         bool have_item = false;
-        if (stage == T_FETCH) {
+        int expect = RCX_ST_SEARCH;
+        if (VH && vh_phase) {
+            if (stage == T_FETCH) stage = T_IDLE;  // wait for the batch-mates
+        } else if (stage == T_FETCH) {
+            if (VH && nx_w < 0) nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);
             if (nx_w < ndyn) {  // reserved while the previous item was searched
                 const long long w = nx_w;
                 nx_w = (long long)atomicAdd(&a.counters[fetch_counter], 1ull);  // the next one: its latency hides behind this search
@@ -208,10 +221,22 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             const unsigned int idle = __ballot_sync(RCX_FULL, stage == T_IDLE);
             if (idle == RCX_FULL) {
                 long long base = 0;
-                if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
-                base = __shfl_sync(RCX_FULL, base, 0);
-                if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
-                if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
+                if (VH && vh_phase) {
+                    if (lane == 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKV], 32ull);
+                    base = __shfl_sync(RCX_FULL, base, 0);
+                    if (base < nvh) {
+                        if (base + lane < nvh) { item = (long long)a.vhlist[base + lane]; expect = RCX_ST_SEARCH_VH; have_item = true; }
+                    } else {  // (uniform) the list is exhausted: on to the items taken one by one (the sweep passes the listed ones by)
+                        vh_phase = false;
+                        stage = T_FETCH;
+                        continue;
+                    }
+                } else {
+                    if (lane == 0 && nbatch > 0) base = (long long)atomicAdd(&a.counters[RCX_C_WORKB], 32ull);
+                    base = __shfl_sync(RCX_FULL, base, 0);
+                    if (nbatch <= 0 || base >= nbatch) break;  // (uniform) nothing left for this warp
+                    if (base + lane < nbatch) { item = rcx_work_slot(nheavy + base + lane, nheavy, a.n); have_item = true; }
+                }
             }
         }
         if (have_item) {
@@ -220,7 +245,7 @@ __global__ void __launch_bounds__(DFS_THREADS, DFS_MINBLOCKS) rcx_dfs_kernel(Rcx
             const int4 h0 = *reinterpret_cast<const int4*>(st), h1 = *reinterpret_cast<const int4*>(st + 4);
             seg0a = *reinterpret_cast<const int4*>(st + 8);
             seg0b = *reinterpret_cast<const int4*>(st + 12);
-            if (h0.x != RCX_ST_SEARCH) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass): next one
+            if (h0.x != (VH ? expect : RCX_ST_SEARCH)) { stage = T_FETCH; continue; }  // decided by the prep kernel (second pass), or (vh mode) a listed item met by the sweep: next one
             const uint32_t o = (uint32_t)h1.z;    // ST_OFF / ST_LEN: written with the header, no worklist -> off[] chase
             len = h1.w;
             pinfo = a.posbuf + o;
@@ -589,14 +614,17 @@ void rcx_dfs_geometry(int sm_count, int max_len, int k, int K, int* grid, int* d
     const size_t smem = dfs_smem_bytes(max_len, k, K);
     cudaError_t e;
     if (dfs_smem_rows(max_len)) {
-        cudaFuncSetAttribute(rcx_dfs_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(rcx_dfs_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<true, false>, DFS_THREADS, smem);
-        int per_sm_b = 0;
-        if (e == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, rcx_dfs_kernel<true, true>, DFS_THREADS, smem) == cudaSuccess &&
-            per_sm_b < per_sm) per_sm = per_sm_b;  // one grid (and scratch) size for both
+        cudaFuncSetAttribute(rcx_dfs_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(rcx_dfs_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(rcx_dfs_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(rcx_dfs_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<true, false, false>, DFS_THREADS, smem);
+        int other = 0;  // one grid (and scratch) size for every instantiation
+        if (e == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, rcx_dfs_kernel<true, true, false>, DFS_THREADS, smem) == cudaSuccess && other < per_sm) per_sm = other;
+        if (e == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, rcx_dfs_kernel<true, false, true>, DFS_THREADS, smem) == cudaSuccess && other < per_sm) per_sm = other;
+        if (e == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, rcx_dfs_kernel<true, true, true>, DFS_THREADS, smem) == cudaSuccess && other < per_sm) per_sm = other;
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<false, false>, DFS_THREADS, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_dfs_kernel<false, false, false>, DFS_THREADS, 0);
     }
     if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     *grid = sm_count * per_sm;
@@ -613,10 +641,13 @@ size_t rcx_dfs_path_bytes(int grid, int lpad) { return (size_t)grid * (DFS_THREA
 cudaError_t rcx_launch_dfs(const RcxCorrectArgs& a, int grid, cudaStream_t s) {
     const size_t smem = dfs_smem_bytes(a.max_len, a.t.k, a.max_fix_per_k);
     if (dfs_smem_rows(a.max_len)) {
-        if (DFS_BATCH && a.dfs_batch && a.pass == 0) rcx_dfs_kernel<true, true><<<grid, DFS_THREADS, smem, s>>>(a);
-        else rcx_dfs_kernel<true, false><<<grid, DFS_THREADS, smem, s>>>(a);
+        const bool batch = DFS_BATCH && a.dfs_batch && a.pass == 0, vh = a.vh_mode && a.pass == 0;
+        if (batch && vh) rcx_dfs_kernel<true, true, true><<<grid, DFS_THREADS, smem, s>>>(a);
+        else if (batch) rcx_dfs_kernel<true, true, false><<<grid, DFS_THREADS, smem, s>>>(a);
+        else if (vh) rcx_dfs_kernel<true, false, true><<<grid, DFS_THREADS, smem, s>>>(a);
+        else rcx_dfs_kernel<true, false, false><<<grid, DFS_THREADS, smem, s>>>(a);
     } else {
-        rcx_dfs_kernel<false, false><<<grid, DFS_THREADS, 0, s>>>(a);
+        rcx_dfs_kernel<false, false, false><<<grid, DFS_THREADS, 0, s>>>(a);
     }
     return cudaGetLastError();
 }

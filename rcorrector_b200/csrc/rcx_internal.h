@@ -14,6 +14,8 @@
 enum { RCX_C_SCAN_PROBES = 0, RCX_C_SEARCH_PROBES, RCX_C_RESCAN_PROBES, RCX_C_SEARCH_NODES, RCX_C_WORK,
        RCX_C_NWORK, RCX_C_WORK2,               // work-list length, finalize kernel's fetch counter
        RCX_C_NWORK2, RCX_C_WORKX0, RCX_C_WORKX1, RCX_C_WORKX2, RCX_C_WORKX3, RCX_C_UNSUPPORTED,  // second-pass list, per-kernel fetch counters
+       RCX_C_NVH,                                // work items with nearly every k-window untrusted (counted always; listed in vhlist[] in vh mode)
+       RCX_C_WORKV,                              // search kernel, vh mode: next batch of 32 listed items
        RCX_C_WORKB,                              // search kernel: next batch of 32 light items
        RCX_C_NWORKH,                             // HEAVY work items (long untrusted spans): slots n-1, n-2, ... of the work list, searched first
        RCX_C_RESCAN_WINDOWS,                     // k-windows the finalize kernels looked up again (two per request on the thread path)
@@ -50,6 +52,9 @@ struct RcxScanArgs {
     int compact_fix;   // edit-list hand-over to the thread-per-item finalize: only the count word of a read's list is cleared
     unsigned short* fixlist;  // [off[n]] 16-bit view of the fix buffer in that mode: fixlist[off[r]] = number of edits of read r, then pos | base << 8
     int heavy_windows; // work items with at least this many untrusted k-windows go to the heavy end of the work list (0: none)
+    int vheavy_windows;// ... and with at least this many are counted as VERY heavy (RCX_C_NVH; 0: none)
+    int vh_mode;       // vh mode: the very heavy items are also listed in vhlist[] (status RCX_ST_SEARCH_VH) for the search kernel's batches
+    uint32_t* vhlist;  // [n] work-list slots of the very heavy items
 };
 #define RCX_TS_MAX_KCNT 232  // reads with more k-windows use the warp-per-read kernels
 
@@ -75,6 +80,8 @@ struct RcxCorrectArgs {
     // hand-over between the triage / search / finalize kernels
     uint32_t* worklist;    // [n] indices of reads that need the search
     uint32_t* worklist2;   // [n] work items that asked for a second pass of A.4
+    uint32_t* vhlist;      // [n] vh mode: slots of the very heavy work items (status RCX_ST_SEARCH_VH until searched), taken first
+    int vh_mode;           // the search kernel's first pass starts with warp batches over vhlist[]
     int32_t* state;        // [n * rcx_state_words()] per work item: header, masks, segment list
     int pass;              // 0 / 1 (set by the launcher)
     signed char* fixbuf;   // [off[n]] fix[] (bestFix of the searches), -1 = no change
@@ -111,6 +118,7 @@ __device__ __forceinline__ bool rcx_has_qual(const RcxCorrectArgs& a, uint32_t o
 #define ST_HDR 8
 #define ST_SEGW 6   // start | to << 16, right | maxFixCnt << 1, seed code lo, hi, seed invalidPos, top2FixBottleNeck[1]
 #define RCX_ST_SEARCH (-4)       // waiting for the search kernel
+#define RCX_ST_SEARCH_VH (-5)    // the same, listed in vhlist[] (vh mode: the sweep over the heavy slots passes it by)
 #define RCX_ST_RETHRESHOLD (-3)  // first pass asked for a second one (forceNextRound)
 #define RCX_ST_POSTFILTER (-2)   // searches done: post-filters decide
 #define ST_OFF 6    // off[r] and length of the read: the search kernel gets them with the header instead of chasing worklist -> off[]

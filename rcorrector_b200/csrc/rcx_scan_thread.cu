@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         // The others are filed sorted by that number within the tile (counting sort in shared memory): the search kernel takes
         // them 32 consecutive slots per warp, and items with the same number of untrusted windows take nearly the same walk.
         const bool is_work = result == -2;
-        bool heavy = false;
+        bool heavy = false, vheavy = false;
         int nun = 0, pos_in_bin = 0;
         if (is_work) {
             for (int j = 0; j < kcnt; ++j) {
@@ -404,11 +404,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                 nun += (int)(x & TS_CMASK) < strong || (x & TS_STRICT) != 0;
             }
             heavy = a.heavy_windows > 0 && nun >= a.heavy_windows;
+            vheavy = heavy && a.vheavy_windows > 0 && nun >= a.vheavy_windows;
             if (nun >= TS_BINS) nun = TS_BINS - 1;
             if (!heavy) pos_in_bin = atomicAdd(&bins[nun], 1);
         }
-        const unsigned int wbh = __ballot_sync(RCX_FULL, is_work && heavy);
-        if (lane == 0) blk[4 + warp] = __popc(wbh);
+        const unsigned int wbh = __ballot_sync(RCX_FULL, is_work && heavy), wbv = __ballot_sync(RCX_FULL, vheavy);
+        if (lane == 0) { blk[4 + warp] = __popc(wbh); blk[warp] = __popc(wbv); }  // (blk[12..13] is the tile copy's barrier)
         __syncthreads();
         if (warp == 0) {  // exclusive prefix over the bins (TS_BINS / 32 per lane), total = light items of the tile
             int v[TS_BINS / 32], sum = 0;
@@ -421,10 +422,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
             for (int q = 0; q < TS_BINS / 32; ++q) { bins[lane * (TS_BINS / 32) + q] = run; run += v[q]; }
             const int tot = __shfl_sync(RCX_FULL, incl, 31);
             if (lane == 0) {
-                int toth = 0;
-                for (int w = 0; w < NT / 32; ++w) { const int ch = blk[4 + w]; blk[4 + w] = toth; toth += ch; }
+                int toth = 0, totv = 0;
+                for (int w = 0; w < NT / 32; ++w) {
+                    const int ch = blk[4 + w]; blk[4 + w] = toth; toth += ch;
+                    const int cv = blk[w]; blk[w] = totv; totv += cv;
+                }
                 blk[8] = tot ? (int)atomicAdd(&a.counters[RCX_C_NWORK], (unsigned long long)tot) : 0;
                 blk[9] = toth ? (int)atomicAdd(&a.counters[RCX_C_NWORKH], (unsigned long long)toth) : 0;
+                blk[10] = totv ? (int)atomicAdd(&a.counters[RCX_C_NVH], (unsigned long long)totv) : 0;  // (counted always: the host picks the mode of the NEXT batch from it)
             }
         }
         __syncthreads();
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
             const long long item = heavy ? a.n - 1 - ((long long)(unsigned int)blk[9] + blk[4 + warp] + __popc(wbh & ((1u << lane) - 1)))
                                          : (long long)(unsigned int)blk[8] + bins[nun] + pos_in_bin;
             a.worklist[item] = (uint32_t)r;
+            if (vheavy && a.vh_mode) a.vhlist[(unsigned int)blk[10] + blk[warp] + __popc(wbv & ((1u << lane) - 1))] = (uint32_t)item;
             int* st = a.state + item * stride;
             RcxMask<NW> T, S, LOWM, M;  // trusted k-mers (:875), strict poly-A k-mers, counts <= 2 && < trust, trusted positions
             T.clear(); S.clear(); LOWM.clear(); M.clear();
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                     B[i] = (unsigned char)((B[i] & 7) | (((ar >> b) & 1) << 3) | (((al >> b) & 1) << 4));
                 }
             }
-            st[ST_STATUS] = RCX_ST_SEARCH; st[ST_TOTALFIX] = rcx_force_bound(strong, er); st[ST_BADSEG] = 0;
+            st[ST_STATUS] = (vheavy && a.vh_mode) ? RCX_ST_SEARCH_VH : RCX_ST_SEARCH; st[ST_TOTALFIX] = rcx_force_bound(strong, er); st[ST_BADSEG] = 0;
 #ifdef RCX_DIAG
             st[ST_BADSEG] = nun;  // (in: the search kernel reads it at the fetch and overwrites it at the item's end)
 #endif

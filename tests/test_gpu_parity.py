@@ -402,3 +402,26 @@ def test_counts_of_2_to_the_29_take_the_warp_kernels(gpu, workdir):
     assert int(np.asarray(exp[4]).max()) >= 600_000_000           # the wide count reaches an h: tag
     for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
         assert np.array_equal(np.asarray(e), np.asarray(g)), nm
+
+
+@pytest.mark.parametrize("name,k,paired,maxcor,kw", [CASES[0], CASES[2], CASES[3], CASES[9]], ids=[CASES[0][0], CASES[2][0], CASES[3][0], CASES[9][0]])
+def test_vh_mode_batches_the_very_heavy_items_first(gpu, workdir, name, k, paired, maxcor, kw, monkeypatch):
+    """vh mode (picked by the library when a quarter of the previous batch's work items had nearly every k-window untrusted;
+    forced here): the search kernel opens with warp batches over the listed very heavy items.  Only the order changes."""
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    er = table.error_rate(d["dump"])
+    bq = T.oracle_bad_quality(bs[0])
+    mode = T.INTERLEAVED if paired else T.SINGLE
+    exp = T.oracle_correct(table, b, k, mode, er, bq, maxcor)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, er, bq, maxcor)
+    monkeypatch.setenv("RCX_VH_MODE", "1")
+    got = gpu.correct(mode, b.seq, b.qual, b.off)
+    st = gpu.stats()
+    assert st["vheavy_items"] > 0 and st["unsupported"] == 0
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
+        assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
+    _check_compact(gpu, mode, b, bq, exp)
