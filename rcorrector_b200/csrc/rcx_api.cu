@@ -860,6 +860,11 @@ extern "C" int rcx_correct_batch_device(rcx_ctx* c, int mode, int64_t n, char* s
     // Asynchronous on purpose: a device batch enqueued behind another one does not wait for it on the host (the kernels are
     // stream-ordered; counters and event times then describe the LAST batch).  Waiting here put a host round trip between
     // the steps of a loop of device batches -- 8 ms per step with eight processes on one host (profiles/r02_n8_bench.json).
+    if (sl.pending && cudaStreamQuery(sl.stream) == cudaSuccess) {  // the previous batch is already done: its counters cost nothing
+        rc = harvest(c, sl);                                        // (and they pick the search kernel's mode for this batch)
+        if (rc) return rc;
+    }
+    cudaGetLastError();
     sl.pending = false;
     rc = begin_call(c, (uint64_t)n, total);
     if (rc) return rc;
