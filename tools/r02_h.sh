@@ -16,3 +16,5 @@ print(" roofline", {k:d["roofline"][k] for k in ("kernel","achieved","frac","tra
 print(" cfg3 base", {k:(v if not isinstance(v,dict) else "...") for k,v in d.get("scaling_base_cfg3",{}).items()})
 P
 tail -3 $OUT/bench.err
+timeout 200 python bench.py --config 5 --no-cpu-baseline --no-parity --no-scaling-base --steps 5 --warmup 3 > $OUT/bench_cfg5.json 2>/dev/null; python -c "
+import json;d=json.loads(open('$OUT/bench_cfg5.json').read());print('cfg5', round(d['ms_per_step'],2), round(d['e2e']['ms_per_step'],2), {k:round(v['ms'],2) for k,v in d['kernels'].items()})"
