@@ -425,3 +425,28 @@ def test_vh_mode_batches_the_very_heavy_items_first(gpu, workdir, name, k, paire
         bad = np.nonzero(np.asarray(e) != np.asarray(g))[0]
         assert len(bad) == 0, "%s: %d mismatches, first at %d" % (nm, len(bad), bad[0])
     _check_compact(gpu, mode, b, bq, exp)
+
+
+def test_large_counts_below_2_to_the_29_stay_on_the_thread_kernels(gpu, workdir):
+    """Counts of millions (poly-A / repeat k-mers of a deep data set) on 150-bp reads: 3 M sits in the table's 24-bit fields,
+    30 M in its side list of saturated fields; both stay below the 29 bits the thread-per-read kernels keep next to their
+    flags, so those kernels run (5 launches) and the tags carry the large counts."""
+    name, k, paired, maxcor, kw = [c for c in CASES if c[0] == "k31deep"][0]
+    d, bs, b, codes, counts = _load(workdir, name, k, paired, kw)
+    counts = counts.copy()
+    hot = np.argsort(-counts.astype(np.int64))[:400]
+    counts[hot[:200]] = 3_000_000
+    counts[hot[200:400]] = 30_000_000
+    table = T.OracleTable(k)
+    table.put(codes, counts)
+    bq = T.oracle_bad_quality(bs[0])
+    mode = T.INTERLEAVED if paired else T.SINGLE
+    exp = T.oracle_correct(table, b, k, mode, 0.01, bq, maxcor)
+    gpu.build_table(k, codes, counts)
+    gpu.set_params(k, 0.01, bq, maxcor)
+    got = gpu.correct(mode, b.seq, b.qual, b.off)
+    st = gpu.stats()
+    assert st["unsupported"] == 0 and st["kernel_launches"] == 5
+    assert int(np.asarray(exp[4]).max()) >= 3_000_000
+    for nm, e, g in zip(["seq", "correction", "l", "m", "h"], exp, got):
+        assert np.array_equal(np.asarray(e), np.asarray(g)), nm
