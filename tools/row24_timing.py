@@ -2,7 +2,8 @@
 """The scan kernel's 24-bit shared-memory count rows (64-read tiles, rcx_scan_thread.cu) against its 32-bit rows (RCX_ROW24=0)
 on the configs[2]-shaped workload (paired 150 bp, the 197.6 M k-mer table, whose largest counts escape the 24-bit rows):
 kernel times from the library's CUDA events, and every output of the two runs compared.
-usage (GPU box): python tools/row24_timing.py [--subshards 1] [--out file.json]"""
+The two settings only differ with profiles/r02_u_row24_experiment.patch applied (the experiment was measured and not shipped:
+profiles/r02_u_row24_experiment.md).   usage (GPU box): python tools/row24_timing.py [--subshards 1] [--out file.json]"""
 import argparse
 import json
 import os
