@@ -737,8 +737,11 @@ static int launch_pipeline(rcx_ctx* c, RcxSlot& sl, int mode, int64_t n, char* d
     // ordinary read lengths: one thread per read (scan + thresholds + triage + first-pass preparation in one kernel);
     // long reads (or RCX_SCAN_WARP=1): the warp-per-read kernels
     sa.compact_fix = (thread_scan && rcx_finalize_thread_supported(max_len, c->k)) ? 1 : 0;
+    // RCX_ROW24=1 (experimental, off by default): 24-bit count rows in the scan's 64-read tiles (reads of more than 128 bases)
+    bool row24 = false;
+    if (const char* e = getenv("RCX_ROW24")) row24 = atoi(e) != 0;
     CUDA_TRY(cudaEventRecord(sl.ev[1], sl.stream));
-    if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, sl.stream));
+    if (thread_scan) CUDA_TRY(rcx_launch_scan_thread(sa, c->sm_count, sl.stream, row24));
     else CUDA_TRY(rcx_launch_scan(sa, c->sm_count, sl.stream));
     CUDA_TRY(cudaEventRecord(sl.ev[2], sl.stream));
     sl.launches = 1;

@@ -149,7 +149,8 @@ size_t rcx_scan_smem_per_warp(int max_len, int k);
 cudaError_t rcx_launch_scan(const RcxScanArgs& a, int sm_count, cudaStream_t s);
 // thread-per-read scan + thresholds + triage + first-pass preparation (rcx_scan_thread.cu)
 bool rcx_scan_thread_supported(int max_len, int k, const void* seq);
-cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s);
+cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s, bool row24 = false);  // row24: experimental, rcx_scan_thread24.cu
+cudaError_t rcx_launch_scan_thread24(const RcxScanArgs& a, int sm_count, cudaStream_t s);  // rcx_scan_thread24.cu
 // correction (rcx_correct.cu)
 size_t rcx_correct_smem_per_warp(int max_len, int k);
 size_t rcx_state_words(int max_len, int k);

@@ -1,24 +1,17 @@
-// rcx_scan_thread.cu — K1 for reads of ordinary length: ONE THREAD owns one read, a block stages a tile of reads
-// through shared memory.  Fuses, in one pass over the read:
-//   * the scan (ErrorCorrection.cpp:716-723 / :1494-1501): counts[j] for every k-window, one table sector per TWO windows;
-//   * GetStrongTrustedThreshold (:1482-1565);
-//   * the triage of ErrorCorrection (:713-755 rejects, :772-842 thresholds, :1110 "every k-mer trusted") with the
-//     l/m/h tags (GetKmerInformation, :1567-1602) of the reads that leave here;
-//   * for the reads that need the search, steps 1-4 of the iteration loop (:863-1046): trusted runs, island adjustment,
-//     trusted positions, segments with their seed k-mers and maxFixCnt, per-base info for the search kernel.
+// rcx_scan_thread24.cu — EXPERIMENTAL variant of the thread-per-read scan (rcx_scan_thread.cu, whose kernel body this file
+// repeats) for the 64-read tiles of reads longer than 128 bases, selected by RCX_ROW24=1 only.  Not the default: it was
+// measured at the very end of the round on one workload (profiles/r02_u_row24_experiment.md) and the GPU suite could not be
+// rerun on it.
 //
-// Why a thread per read (measured, profiles/r01_g): the warp-per-read version of this work executed ~2 000 warp
-// instructions per 100-bp read spread evenly over bit-plane construction, funnel shifts, ballots and reductions, ran at
-// 65 % issue utilisation and took the same 24 ms per 10 M reads whether the table needed 737 M or 369 M sector
-// requests: it was instruction-bound, not memory-bound.  The per-read work is scalar bookkeeping over ~80 windows; a
-// thread does it with a rolling k-mer in registers (~200 warp-instruction equivalents per read) and 32 reads share
-// every instruction.  The block keeps the memory side coalesced: the tile's bases are copied HBM -> shared with
-// 16-byte vector loads, each thread's counts live in its own conflict-free shared-memory row (odd stride), and
-// counts[] / per-base info / the cleared fix[] go back to HBM as contiguous block-wide copies.  Table lookups are
-// software-pipelined per thread (TS_DEPTH = 2: 512 threads x 2 independent sector requests in flight per SM).
-//
-// Reads with more than TS_MAX_KCNT windows keep the warp-per-read kernels (rcx_scan.cu, rcx_correct.cu).
+// What differs: the per-thread count rows in shared memory take 24 bits per k-window (two planes: low 16 bits, high 8 bits;
+// 21-bit count + the three flags) instead of 32 -- 392 instead of 516 bytes per 150-bp read, which lets a 6th block (12 instead
+// of 10 warps) onto an SM, where shared memory is the limit (profiles/r02_r_cfg3_full.md).  A count of 2^21 - 1 or more does not
+// fit: the row keeps the all-ones ESCAPE value, the exact count goes straight to counts[] in global memory (where the write-out
+// at the end of the tile would put it anyway), and the thread remembers that its row holds an escape: only such rows (a handful
+// of poly-A / repeat k-mers of a deep data set) run the loops over the row in their checking version.
 #include "rcx_internal.h"
+
+namespace rcx24 {
 
 #define TS_THREADS 128  // reads per tile for reads up to 128 bases; longer reads use 64-read tiles (more blocks fit the shared memory)
 // TS_DEPTH (template parameter DEPTH): sector requests in flight per thread.  Measured for 100-bp reads (128-read tiles,
@@ -45,23 +38,64 @@
 
 #define TS_BINS 256  // per-tile counting sort of the work items by their number of untrusted k-windows (<= RCX_TS_MAX_KCNT)
 struct TsLayout {
-    int cw;         // words per count row (odd)
+    int nt;         // rows (threads of the block)
+    int cw;         // words per 32-bit count row (odd)
+    int lo_bytes, hi_bytes;  // 24-bit rows: bytes per row of the low-16 plane and of the high-8 plane (a multiple of 4, odd number of words)
     int bytes_cap;  // staged bases
     size_t smem;
 };
-__host__ __device__ inline TsLayout ts_layout(int max_len, int k, int nt) {
+// Count rows, one per thread: 32 bits per k-window (29-bit count + three flags; kept for reference, not instantiated here) or,
+// W24, 24 bits in two planes (see the head of the file).
+__host__ __device__ inline TsLayout ts_layout(int max_len, int k, int nt, bool w24) {
     TsLayout L;
     int kc = max_len - k + 1;
     if (kc < 1) kc = 1;
+    L.nt = nt;
     L.cw = kc | 1;
+    L.lo_bytes = 4 * (((2 * kc + 3) / 4) | 1);
+    L.hi_bytes = 4 * (((kc + 3) / 4) | 1);
     L.bytes_cap = ((nt * max_len + 15) & ~15) + 32;
-    L.smem = sizeof(uint32_t) * (nt + 4) + sizeof(int) * (16 + TS_BINS) + sizeof(int) * (size_t)nt * L.cw + (size_t)L.bytes_cap;
+    const size_t row = w24 ? (size_t)(L.lo_bytes + L.hi_bytes) : sizeof(int) * (size_t)L.cw;
+    L.smem = sizeof(uint32_t) * (nt + 4) + sizeof(int) * (16 + TS_BINS) + (size_t)nt * row + (size_t)L.bytes_cap;
     return L;
 }
-bool rcx_scan_thread_supported(int max_len, int k, const void* seq) {
-    const int kc = max_len - k + 1;
-    return kc >= 1 && kc <= RCX_TS_MAX_KCNT && max_len <= 255 && ((uintptr_t)seq & 15) == 0 && ts_layout(max_len, k, max_len <= 128 ? TS_THREADS : 64).smem <= 200 * 1024;
-}
+// flag bits and count mask of a row entry as the kernel sees it: the 32-bit rows' own layout, or the 24 bits of the two planes
+template <bool W24>
+struct TsBits {
+    static constexpr unsigned int LOOSE = TS_LOOSE, STRICT = TS_STRICT, INVALID = TS_INVALID, CMASK = TS_CMASK;
+    static constexpr int SIGN_SHIFT = 0;  // left shift that brings LOOSE to the sign bit
+};
+template <>
+struct TsBits<true> {
+    static constexpr unsigned int LOOSE = 0x00800000u, STRICT = 0x00400000u, INVALID = 0x00200000u, CMASK = 0x001fffffu;  // count CMASK = escape
+    static constexpr int SIGN_SHIFT = 8;
+};
+template <bool W24>
+struct TsRow;
+template <>
+struct TsRow<false> {
+    unsigned int* p;
+    __device__ __forceinline__ TsRow(unsigned char* rows, const TsLayout& L, int t) : p(reinterpret_cast<unsigned int*>(rows) + (size_t)t * L.cw) {}
+    __device__ __forceinline__ unsigned int get(int j) const { return p[j]; }
+    __device__ __forceinline__ void set_flags(int j, unsigned int f) const { p[j] = f; }         // count bits 0
+    __device__ __forceinline__ void add_count(int j, unsigned int c) const { p[j] |= c; }         // once per entry, after set_flags
+};
+template <>
+struct TsRow<true> {
+    unsigned short* lo;
+    unsigned char* hi;
+    __device__ __forceinline__ TsRow(unsigned char* rows, const TsLayout& L, int t)
+        : lo(reinterpret_cast<unsigned short*>(rows + (size_t)t * L.lo_bytes)), hi(rows + (size_t)L.nt * L.lo_bytes + (size_t)t * L.hi_bytes) {}
+    __device__ __forceinline__ unsigned int get(int j) const { return (unsigned int)lo[j] | ((unsigned int)hi[j] << 16); }
+    __device__ __forceinline__ void set_flags(int j, unsigned int f) const {
+        lo[j] = 0;
+        hi[j] = (unsigned char)(f >> 16);
+    }
+    __device__ __forceinline__ void add_count(int j, unsigned int c) const {
+        lo[j] = (unsigned short)c;
+        if (c >> 16) hi[j] = (unsigned char)(hi[j] | (c >> 16));
+    }
+};
 
 struct TsPend {
     unsigned long long key;
@@ -97,30 +131,58 @@ __device__ __forceinline__ int ts_field(const RcxTable& t, const RcxEntryRegs& d
 }
 
 __device__ __forceinline__ int ts_octave(int v) { return v <= 0 ? 0 : 32 - __clz(v); }
-__device__ __forceinline__ int ts_masked(unsigned int x) { return (x & TS_LOOSE) ? -1 : (int)(x & TS_CMASK); }
+// count of row entry x = row.get(j).  ESC: the row holds escaped entries (24-bit rows only), gc = counts[] of the row's read
+template <bool W24, bool ESC>
+__device__ __forceinline__ int ts_count(unsigned int x, const int32_t* gc, int j) {
+    int c = (int)(x & TsBits<W24>::CMASK);
+    if (W24 && ESC) {
+        if (c == (int)TsBits<W24>::CMASK) c = __ldcg(gc + j);  // (L2: the select below reads other lanes' rows)
+    }
+    return c;
+}
+struct TsPlain { static constexpr bool value = false; };
+struct TsEscaped { static constexpr bool value = true; };
 
 // Selection: smallest x with #{value <= x} > rank over a row; kind 0: loose-masked counts, kind 1: valid windows with 0 -> 1.
 // Only a FEW lanes of a warp need one (reads without a drop, reads that leave at the triage):
 // instead of every lane walking its own row while the others idle, the warp serves the requests one after the other,
 // all 32 lanes counting a slice of the requester's row (conflict-free: consecutive words).  Must be called convergently.
-template <int KIND>
-__device__ __forceinline__ int ts_select_coop(const unsigned int* warp_rows, int cw, int lane, bool need, int kcnt, int rank, int lo, int hi) {
+template <int KIND, bool W24>
+__device__ __forceinline__ int ts_select_coop(unsigned char* rows, const TsLayout& L, int warp, int lane, bool need, int kcnt, int rank, int lo, int hi,
+                                              const int32_t* counts, uint32_t o, bool esc) {
+    using TB = TsBits<W24>;
     int result = lo;
     __syncwarp();  // the rows were written by their owner lanes
     unsigned int pending = __ballot_sync(RCX_FULL, need);
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        const unsigned int* row = warp_rows + (size_t)src * cw;
+        const TsRow<W24> row(rows, L, warp * 32 + src);
         const int n = __shfl_sync(RCX_FULL, kcnt, src), rk = __shfl_sync(RCX_FULL, rank, src);
+        const int32_t* gc = nullptr;
+        bool src_esc = false;
+        if (W24) {
+            gc = counts + __shfl_sync(RCX_FULL, o, src);
+            src_esc = __shfl_sync(RCX_FULL, (int)esc, src) != 0;  // (uniform over the warp)
+        }
         int l = __shfl_sync(RCX_FULL, lo, src), h = __shfl_sync(RCX_FULL, hi, src);
         while (l < h) {
             const int mid = l + (int)(((unsigned int)h - (unsigned int)l) >> 1);
             int c = 0;
-            for (int j = lane; j < n; j += 32) {
-                const unsigned int x = row[j];
-                if (KIND == 0) c += (int)(x & ~(TS_STRICT | TS_INVALID)) <= mid;  // a loose entry (bit 31) reads as negative: like its -1, never above a pivot >= -1
-                else if (!(x & TS_INVALID)) { int v = (int)(x & TS_CMASK); v = v == 0 ? 1 : v; c += v <= mid; }
+            if (W24 && src_esc) {
+                for (int j = lane; j < n; j += 32) {
+                    const unsigned int x = row.get(j);
+                    const int v = ts_count<W24, true>(x, gc, j);
+                    if (KIND == 0) c += ((x & TB::LOOSE) ? -1 : v) <= mid;
+                    else if (!(x & TB::INVALID)) c += (v == 0 ? 1 : v) <= mid;
+                }
+            } else {
+                for (int j = lane; j < n; j += 32) {
+                    const unsigned int x = row.get(j);
+                    // a loose entry (its flag shifted to the sign bit) reads as negative: like its -1, never above a pivot >= -1
+                    if (KIND == 0) c += (int)((x & ~(TB::STRICT | TB::INVALID)) << TB::SIGN_SHIFT) <= mid * (1 << TB::SIGN_SHIFT);
+                    else if (!(x & TB::INVALID)) { int v = (int)(x & TB::CMASK); v = v == 0 ? 1 : v; c += v <= mid; }
+                }
             }
             c = __reduce_add_sync(RCX_FULL, c);
             if (c > rk) h = mid; else l = mid + 1;
@@ -130,16 +192,17 @@ __device__ __forceinline__ int ts_select_coop(const unsigned int* warp_rows, int
     return result;
 }
 
-template <int NW, int NT, int TS_DEPTH>
+template <int NW, int NT, int TS_DEPTH, bool W24>
 __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.t.k;
-    const TsLayout LY = ts_layout(a.max_len, k, NT);
+    const TsLayout LY = ts_layout(a.max_len, k, NT, W24);
     uint32_t* offs = reinterpret_cast<uint32_t*>(smem_raw);                       // [T + 1] (+3 pad)
     int* blk = reinterpret_cast<int*>(offs + NT + 4);                     // [16] block scratch
     int* bins = blk + 16;                                                 // [TS_BINS] work items of the tile per untrusted-window count
-    unsigned int* cnt_all = reinterpret_cast<unsigned int*>(bins + TS_BINS);      // [T][cw]
-    unsigned char* bytes = reinterpret_cast<unsigned char*>(cnt_all + (size_t)NT * LY.cw);  // 16-byte aligned (all sizes above are multiples of 16)
+    unsigned char* cnt_all = reinterpret_cast<unsigned char*>(bins + TS_BINS);    // [T] count rows (TsRow)
+    unsigned char* bytes = cnt_all + (size_t)NT * (W24 ? (size_t)(LY.lo_bytes + LY.hi_bytes) : sizeof(int) * (size_t)LY.cw);  // 16-byte aligned (all sizes above are multiples of 16)
+    using TB = TsBits<W24>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1);
     const int loose_thr = (k / 2 > 7) ? k / 2 : 7;
@@ -188,7 +251,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         const int len = have ? (int)(offs[tid + 1] - o) : 0;
         const int kcnt = len - k + 1;
         unsigned char* B = bytes + (o - a0);
-        unsigned int* row = cnt_all + (size_t)tid * LY.cw;
+        const TsRow<W24> row(cnt_all, LY, tid);
+        int32_t* gc = a.counts + o;  // (24-bit rows: exact value of an escaped count)
+        bool esc = false;            // this row holds an escaped entry: its loops run in the checking version
+        // runs body(TsEscaped) for a row with escapes, body(TsPlain) otherwise (the only version of the 32-bit rows)
+        auto on_row = [&](auto body) {
+            if (W24 && esc) body(TsEscaped());
+            else body(TsPlain());
+        };
         int thr = -1;
         uint8_t flags = RCX_F_REJECT;
         int nN = 0, nA = 0, nT = 0;
@@ -229,7 +299,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                     j = i - k;  // window that ends at the base just appended
                     const bool lo_ = wA >= k - loose_thr || wT >= k - loose_thr;  // IsPolyA(seq + j, k, max(7, k/2))
                     const bool st_ = wA >= k - 2 || wT >= k - 2;                  // IsPolyA(seq + j, k, 2)
-                    row[j] = (lo_ ? TS_LOOSE : 0u) | (st_ ? TS_STRICT : 0u) | (run >= k ? 0u : TS_INVALID);
+                    row.set_flags(j, (lo_ ? TB::LOOSE : 0u) | (st_ ? TB::STRICT : 0u) | (run >= k ? 0u : TB::INVALID));
                     trig = (j & 1) || i == len;
                 }
                 if (trig) {
@@ -257,12 +327,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                     if (info & (1 << 14)) {
                         const int c = ts_field(a.t, p.d, p.key, flip, true, (info >> 10) & 3);
                         toobig |= (unsigned int)c > TS_CMASK;
-                        row[j - 1] |= (unsigned int)c & TS_CMASK;
+                        if (W24 && (unsigned int)c >= TB::CMASK) { gc[j - 1] = c; row.add_count(j - 1, TB::CMASK); esc = true; }
+                        else row.add_count(j - 1, (unsigned int)c & TB::CMASK);
                     }
                     if (info & (1 << 15)) {
                         const int c = ts_field(a.t, p.d, p.key, flip, false, (info >> 12) & 3);
                         toobig |= (unsigned int)c > TS_CMASK;
-                        row[j] |= (unsigned int)c & TS_CMASK;
+                        if (W24 && (unsigned int)c >= TB::CMASK) { gc[j] = c; row.add_count(j, TB::CMASK); esc = true; }
+                        else row.add_count(j, (unsigned int)c & TB::CMASK);
                     }
                 }
             };
@@ -305,17 +377,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         if (have && kcnt > 0 && !(nN > 5 || nA > len - k || nT > len - k)) {
             unsigned int present = 0;
             int nonpos = 0, gmin = 0x7fffffff, gmax = -1;
-            for (int j = 0; j < kcnt; ++j) {
-                const unsigned int x = row[j];
-                const int c = (int)(x & TS_CMASK);
-                const int m = (x & TS_LOOSE) ? -1 : c;
-                present |= 1u << ts_octave(m);
-                nonpos += m <= 0;
-                gmin = m < gmin ? m : gmin;
-                gmax = m > gmax ? m : gmax;
-                minc = c < minc ? c : minc;
-                any_strict |= (x & TS_STRICT) != 0;
-            }
+            on_row([&](auto E) {
+                for (int j = 0; j < kcnt; ++j) {
+                    const unsigned int x = row.get(j);
+                    const int c = ts_count<W24, decltype(E)::value>(x, gc, j);
+                    const int m = (x & TB::LOOSE) ? -1 : c;
+                    present |= 1u << ts_octave(m);
+                    nonpos += m <= 0;
+                    gmin = m < gmin ? m : gmin;
+                    gmax = m > gmax ? m : gmax;
+                    minc = c < minc ? c : minc;
+                    any_strict |= (x & TB::STRICT) != 0;
+                }
+            });
             bool found = false;
             int below = 0;
             unsigned int leftm = present;
@@ -325,11 +399,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                 if (b < 4 || lower == 0) break;  // values <= 10 cannot be a drop; the smallest element has no predecessor
                 const int lo_b = 1 << (b - 1);   // octave b = [2^(b-1), 2^b)
                 int mn = 0x7fffffff, mx = (int)0x80000000;
-                for (int j = 0; j < kcnt; ++j) {
-                    const int m = ts_masked(row[j]);
-                    if ((unsigned int)(m - lo_b) < (unsigned int)lo_b) mn = m < mn ? m : mn;  // smallest value of this octave
-                    else if (m < lo_b) mx = m > mx ? m : mx;                                  // largest value below it
-                }
+                on_row([&](auto E) {
+                    for (int j = 0; j < kcnt; ++j) {
+                        const unsigned int x = row.get(j);
+                        const int m = (x & TB::LOOSE) ? -1 : ts_count<W24, decltype(E)::value>(x, gc, j);
+                        if ((unsigned int)(m - lo_b) < (unsigned int)lo_b) mn = m < mn ? m : mn;  // smallest value of this octave
+                        else if (m < lo_b) mx = m > mx ? m : mx;                                  // largest value below it
+                    }
+                });
                 if (mn <= 10) break;  // everything further down is smaller still
                 if (mn > 2 * mx) { found = true; thr = mn; below = mx; break; }
                 leftm = lower;
@@ -338,7 +415,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
             flags = found ? (uint8_t)(RCX_F_DROP | (below == 2 ? RCX_F_PREV2 : 0)) : (uint8_t)0;
         }
         {
-            const int med = ts_select_coop<0>(cnt_all + (size_t)(warp * 32) * LY.cw, LY.cw, lane, need_sel, kcnt, sel_rank, sel_lo, sel_hi);
+            const int med = ts_select_coop<0, W24>(cnt_all, LY, warp, lane, need_sel, kcnt, sel_rank, sel_lo, sel_hi, a.counts, o, esc);
             if (need_sel) thr = med;
         }
         if (have) { a.thr[r] = thr; a.flags[r] = flags; }
@@ -369,22 +446,24 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
                     result = (!any_strict && minc >= strong) ? 0 : -2;  // every k-mer trusted (:875, :1110)
                 }
                 if (result != -2) {  // GetKmerInformation (:1567-1602) on the unchanged read
-                    for (int j = 0; j < kcnt; ++j) {
-                        const unsigned int x = row[j];
-                        if (!(x & TS_INVALID)) {
-                            int v = (int)(x & TS_CMASK);
-                            v = v == 0 ? 1 : v;
-                            ++nvalid;
-                            vmin = v < vmin ? v : vmin;
-                            vmax = v > vmax ? v : vmax;
+                    on_row([&](auto E) {
+                        for (int j = 0; j < kcnt; ++j) {
+                            const unsigned int x = row.get(j);
+                            if (!(x & TB::INVALID)) {
+                                int v = ts_count<W24, decltype(E)::value>(x, gc, j);
+                                v = v == 0 ? 1 : v;
+                                ++nvalid;
+                                vmin = v < vmin ? v : vmin;
+                                vmax = v > vmax ? v : vmax;
+                            }
                         }
-                    }
+                    });
                     need_info = true;
                 }
             }
         }
         {   // the median of the tags, served warp-cooperatively for the lanes that leave here
-            const int med = ts_select_coop<1>(cnt_all + (size_t)(warp * 32) * LY.cw, LY.cw, lane, need_info && nvalid > 0, kcnt, nvalid / 2, vmin, vmax);
+            const int med = ts_select_coop<1, W24>(cnt_all, LY, warp, lane, need_info && nvalid > 0, kcnt, nvalid / 2, vmin, vmax, a.counts, o, esc);
             if (need_info) {
                 int l = 0, m = 0, h = 0;
                 if (nvalid > 0) { l = vmin; h = vmax; m = med; }
@@ -399,10 +478,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         bool heavy = false, vheavy = false;
         int nun = 0, pos_in_bin = 0;
         if (is_work) {
-            for (int j = 0; j < kcnt; ++j) {
-                const unsigned int x = row[j];
-                nun += (int)(x & TS_CMASK) < strong || (x & TS_STRICT) != 0;
-            }
+            on_row([&](auto E) {
+                for (int j = 0; j < kcnt; ++j) {
+                    const unsigned int x = row.get(j);
+                    nun += ts_count<W24, decltype(E)::value>(x, gc, j) < strong || (x & TB::STRICT) != 0;
+                }
+            });
             heavy = a.heavy_windows > 0 && nun >= a.heavy_windows;
             vheavy = heavy && a.vheavy_windows > 0 && nun >= a.vheavy_windows;
             if (nun >= TS_BINS) nun = TS_BINS - 1;
@@ -449,14 +530,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
             for (int w = 0; w < NW; ++w) {
                 unsigned long long tw = 0, sw = 0, lw = 0;
                 const int jn = kcnt - 64 * w < 64 ? kcnt - 64 * w : 64;
-                for (int b = 0; b < jn; ++b) {
-                    const unsigned int x = row[64 * w + b];
-                    const int c = (int)(x & TS_CMASK);
-                    const bool strict = (x & TS_STRICT) != 0;
-                    tw |= (unsigned long long)(c >= strong && !strict) << b;
-                    sw |= (unsigned long long)strict << b;
-                    lw |= (unsigned long long)(c <= 2 && c < trust) << b;
-                }
+                on_row([&](auto E) {
+                    for (int b = 0; b < jn; ++b) {
+                        const unsigned int x = row.get(64 * w + b);
+                        const int c = ts_count<W24, decltype(E)::value>(x, gc, 64 * w + b);
+                        const bool strict = (x & TB::STRICT) != 0;
+                        tw |= (unsigned long long)(c >= strong && !strict) << b;
+                        sw |= (unsigned long long)strict << b;
+                        lw |= (unsigned long long)(c <= 2 && c < trust) << b;
+                    }
+                });
                 T.m[w] = tw; S.m[w] = sw; LOWM.m[w] = lw;
             }
             int longest = 0, tstart = 0, tend = -1;
@@ -570,9 +653,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
         for (int t = warp; t < nr; t += NT / 32) {
             const uint32_t ot = offs[t];
             const int kc = (int)(offs[t + 1] - ot) - k + 1;
-            const unsigned int* rw = cnt_all + (size_t)t * LY.cw;
+            const TsRow<W24> rw(cnt_all, LY, t);
             // (with the correction kernels downstream, bit 31 tells them that the window holds a non-ACGT base)
-            for (int j = lane; j < kc; j += 32) a.counts[ot + j] = (int)((rw[j] & TS_CMASK) | ((a.triage && (rw[j] & TS_INVALID)) ? RCX_COUNT_INVALID : 0u));
+            for (int j = lane; j < kc; j += 32) {
+                const unsigned int x = rw.get(j);
+                if (W24 && (x & TB::CMASK) == TB::CMASK) continue;  // escaped: the exact count is already there
+                a.counts[ot + j] = (int)((x & TB::CMASK) | ((a.triage && (x & TB::INVALID)) ? RCX_COUNT_INVALID : 0u));
+            }
         }
         if (a.triage) {
             for (unsigned long long p = g0 + tid; p < g1; p += NT) a.posbuf[p] = bytes[p - a0] & 31;
@@ -586,28 +673,28 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcx_scan_thread_kernel(RcxScanAr
     probes = __reduce_add_sync(RCX_FULL, probes);
     toobig = __reduce_or_sync(RCX_FULL, toobig);
     if (lane == 0 && probes) atomicAdd(&a.counters[RCX_C_SCAN_PROBES], (unsigned long long)probes);
-    if (lane == 0 && toobig) atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);  // a count >= 2^29: flagged, not hidden
+    if (lane == 0 && toobig) atomicAdd(&a.counters[RCX_C_UNSUPPORTED], 1ull);  // a count >= 2^29 (the host routes such tables to the warp-per-read kernels): flagged, not hidden
 }
 
-template <int NW, int NT, int DEPTH>
+template <int NW, int NT, int DEPTH, bool W24>
 static cudaError_t launch_scan_thread_nw(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
-    const TsLayout L = ts_layout(a.max_len, a.t.k, NT);
-    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW, NT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    const TsLayout L = ts_layout(a.max_len, a.t.k, NT, W24);
+    cudaError_t e = cudaFuncSetAttribute(rcx_scan_thread_kernel<NW, NT, DEPTH, W24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW, NT, DEPTH>, NT, L.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rcx_scan_thread_kernel<NW, NT, DEPTH, W24>, NT, L.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long want = (a.n + NT - 1) / NT;
     long long grid = (long long)sm_count * per_sm;  // persistent grid: a multiple of the SM count
     if (grid > want) grid = want;
-    rcx_scan_thread_kernel<NW, NT, DEPTH><<<(unsigned int)grid, NT, L.smem, s>>>(a);
+    rcx_scan_thread_kernel<NW, NT, DEPTH, W24><<<(unsigned int)grid, NT, L.smem, s>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t rcx_launch_scan_thread(const RcxScanArgs& a, int sm_count, cudaStream_t s, bool row24) {
+}  // namespace rcx24
+
+cudaError_t rcx_launch_scan_thread24(const RcxScanArgs& a, int sm_count, cudaStream_t s) {
     if (a.n <= 0) return cudaSuccess;
-    if (a.max_len <= 128) return launch_scan_thread_nw<2, TS_THREADS, TS_DEPTH_DEFAULT>(a, sm_count, s);
-    if (row24) return rcx_launch_scan_thread24(a, sm_count, s);  // experimental 24-bit count rows (RCX_ROW24=1; rcx_scan_thread24.cu)
-    return launch_scan_thread_nw<4, 64, TS_DEPTH_DEFAULT>(a, sm_count, s);  // max_len <= 255 (4 in flight measured on 150-bp reads: 28.2 -> 29.0 ms)
+    return rcx24::launch_scan_thread_nw<4, 64, TS_DEPTH_DEFAULT, true>(a, sm_count, s);  // 128 < max_len <= 255
 }

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""The scan kernel's 24-bit shared-memory count rows (64-read tiles, rcx_scan_thread.cu) against its 32-bit rows (RCX_ROW24=0)
-on the configs[2]-shaped workload (paired 150 bp, the 197.6 M k-mer table, whose largest counts escape the 24-bit rows):
-kernel times from the library's CUDA events, and every output of the two runs compared.
-The two settings only differ with profiles/r02_u_row24_experiment.patch applied (the experiment was measured and not shipped:
-profiles/r02_u_row24_experiment.md).   usage (GPU box): python tools/row24_timing.py [--subshards 1] [--out file.json]"""
+"""The experimental scan kernel with 24-bit shared-memory count rows (RCX_ROW24=1, rcx_scan_thread24.cu) against the shipped one
+(32-bit rows) on the configs[2]-shaped workload (paired 150 bp, the 197.6 M k-mer table, whose largest count escapes the
+24-bit rows): kernel times from the library's CUDA events, and every output of the two runs compared
+(profiles/r02_u_row24_experiment.md).
+usage (GPU box): python tools/row24_timing.py [--subshards 1] [--fast] [--out file.json]"""
 import argparse
 import json
 import os
@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--subshards", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--fast", action="store_true", help="skip the pre-pass: error rate 0.01 and quality threshold 48 as bench.py derives them for this workload")
     ap.add_argument("--out", default=None)
     o = ap.parse_args()
     import torch
@@ -34,7 +35,7 @@ def main():
     cor = Corrector(0)
     cor.build_table(a.k, codes, counts)
     cor.sync()
-    er = cor.estimate_error_rate(bench.dump_order_prefix(codes, counts), 0.95)
+    er = 0.01 if o.fast else cor.estimate_error_rate(bench.dump_order_prefix(codes, counts), 0.95)
     big = int((counts >= (1 << 21)).sum())
     res = {"workload": "configs[2] shape: %d sub-shard(s) of 6 M paired 150-bp reads, table of %d k-mers" % (o.subshards, len(codes)),
            "largest_count": int(counts.max()), "kmers_with_count_ge_2^21": big, "runs": {}}
@@ -50,7 +51,7 @@ def main():
         base += int(x[-1])
     off = np.concatenate(cat)
     n, total, max_len = len(off) - 1, int(off[-1]), int(np.diff(off).max())
-    bq = bench.bad_quality_threshold(quals[0], offs[0].astype(np.uint32), True, min(a.cpu_sample, n))
+    bq = 48 if o.fast else bench.bad_quality_threshold(quals[0], offs[0].astype(np.uint32), True, min(a.cpu_sample, n))
     cor.set_params(a.k, er, bq, a.maxcork)
     d_seq0 = torch.from_numpy(np.concatenate(seqs)).to(dev)
     d_qual = torch.from_numpy(np.concatenate(quals)).to(dev)
@@ -59,11 +60,8 @@ def main():
     outs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4)]
     stream = torch.cuda.ExternalStream(cor.stream(), device=dev)
     ref = None
-    for name, env in (("rows32", "0"), ("rows24", None), ("rows32 again", "0"), ("rows24 again", None)):
-        if env is None:
-            os.environ.pop("RCX_ROW24", None)
-        else:
-            os.environ["RCX_ROW24"] = env
+    for name, env in (("rows32", "0"), ("rows24", "1"), ("rows32 again", "0"), ("rows24 again", "1")):
+        os.environ["RCX_ROW24"] = env
         sts = []
         for it in range(1 + o.steps):
             with torch.cuda.stream(stream):
